@@ -1,0 +1,202 @@
+"""Engine: host-side owner of one z-slab of the FDTD state on one B200.
+
+PyTorch provides device memory and the stream; every arithmetic step is a hand-written
+sm_100a kernel in csrc/b200fdtd.cu reached through the C-ABI (include/b200fdtd.h).
+This object is what `openEMS.openEMS.Run` drives (the reference's FDTD.Run call,
+antenna_sim/solver_fdtd_openems_microstrip_3d.py:214).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, c_f, c_d, c_i32, c_i64
+
+
+def _np(a, dt):
+    return np.ascontiguousarray(a, dt)
+
+
+def _ptr(a, t):
+    return a.ctypes.data_as(t)
+
+
+def round_up(n, m):
+    return (n + m - 1) // m * m
+
+
+def lin(nz, ny, px, c, k, j, i):
+    """linear index of (component c, local plane k, row j, column i) — include/b200fdtd.h"""
+    return ((c * (nz + 2) + (k + 1)) * ny + j) * px + i
+
+
+class Engine:
+    """One z-slab on one GPU.  Arrays are torch float32 CUDA tensors of shape [3, nz+2, ny, px]."""
+
+    def __init__(self, nx, ny, nz, px=None, device=0, stream=None):
+        if not torch.cuda.is_available():
+            raise _lib.B200FDTDError("no CUDA device: the B200 engine has no CPU fallback")
+        self.L = _lib.lib()
+        self.nx, self.ny, self.nz = int(nx), int(ny), int(nz)
+        self.px = int(px) if px else round_up(self.nx, 32)
+        self.device = torch.device("cuda", int(device))
+        self.shape = (3, self.nz + 2, self.ny, self.px)
+        torch.cuda.set_device(self.device)
+        self.stream = stream if stream is not None else torch.cuda.current_stream(self.device)
+        self.h = C.c_void_p()
+        check(self.L.b200fdtd_create(C.byref(self.h), self.device.index, self.nx, self.ny, self.nz, self.px,
+                                      C.c_void_p(self.stream.cuda_stream)))
+        self.volt = torch.zeros(self.shape, dtype=torch.float32, device=self.device)
+        self.curr = torch.zeros(self.shape, dtype=torch.float32, device=self.device)
+        check(self.L.b200fdtd_bind_fields(self.h, self.volt.data_ptr(), self.curr.data_ptr()))
+        self.vv = self.vi = self.ii = self.iv = None
+        self._keep = {}
+        self.series = None
+        self.probe_dft = None
+        self.face_acc = []
+
+    # ---- lifetime ----
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.L.b200fdtd_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- inputs ----
+    def _dev(self, a):
+        if isinstance(a, torch.Tensor):
+            t = a.to(device=self.device, dtype=torch.float32)
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(a, np.float32)).to(self.device)
+        return t.contiguous()
+
+    def set_coeffs(self, vv, vi, ii, iv):
+        self.vv, self.vi, self.ii, self.iv = (self._dev(a).reshape(self.shape) for a in (vv, vi, ii, iv))
+        check(self.L.b200fdtd_bind_coeffs(self.h, self.vv.data_ptr(), self.vi.data_ptr(),
+                                          self.ii.data_ptr(), self.iv.data_ptr()))
+
+    def set_tuning(self, kz=16, ty=4, variant=0):
+        check(self.L.b200fdtd_set_tuning(self.h, int(kz), int(ty), int(variant)))
+
+    def set_excitation(self, idx, amp, delay, signal):
+        idx, amp, delay, signal = _np(idx, np.int64), _np(amp, np.float32), _np(delay, np.int32), _np(signal, np.float32)
+        check(self.L.b200fdtd_set_excitation(self.h, len(idx), _ptr(idx, c_i64), _ptr(amp, c_f), _ptr(delay, c_i32),
+                                             _ptr(signal, c_f), len(signal)))
+
+    def set_mur(self, dst, src, coeff):
+        dst, src, coeff = _np(dst, np.int64), _np(src, np.int64), _np(coeff, np.float32)
+        check(self.L.b200fdtd_set_mur(self.h, len(dst), _ptr(dst, c_i64), _ptr(src, c_i64), _ptr(coeff, c_f)))
+
+    def set_pml(self, boxes):
+        """boxes: list of dicts {x0,y0,z0,bx,by,bz, vv,vvfo,vvfn,ii,iifo,iifn: arrays [3][bz][by][bx]}"""
+        arr = (_lib.PmlBox * max(1, len(boxes)))()
+        keep = []
+        for b, B in enumerate(boxes):
+            shp = (3, int(B["bz"]), int(B["by"]), int(B["bx"]))
+            d = {n: self._dev(np.asarray(B[n], np.float32).reshape(shp)) for n in ("vv", "vvfo", "vvfn", "ii", "iifo", "iifn")}
+            d["flux_v"] = torch.zeros(shp, dtype=torch.float32, device=self.device)
+            d["flux_i"] = torch.zeros(shp, dtype=torch.float32, device=self.device)
+            keep.append(d)
+            for n in ("x0", "y0", "z0", "bx", "by", "bz"):
+                setattr(arr[b], n, int(B[n]))
+            for n, t in d.items():
+                setattr(arr[b], n, t.data_ptr())
+        self._keep["pml"] = keep
+        self.pml_arrays = keep
+        check(self.L.b200fdtd_set_pml(self.h, len(boxes), arr))
+
+    def set_probes(self, kind, offset, idx, weight, interval, max_samples, freqs, dt):
+        kind, offset = _np(kind, np.int32), _np(offset, np.int64)
+        idx, weight, freqs = _np(idx, np.int64), _np(weight, np.float32), _np(freqs, np.float64)
+        n = len(kind)
+        self.series = torch.zeros((n, int(max_samples)), dtype=torch.float32, device=self.device)
+        self.probe_dft = torch.zeros((n, max(1, len(freqs)), 2), dtype=torch.float32, device=self.device)
+        self.probe_freqs = freqs
+        self.interval = int(interval)
+        check(self.L.b200fdtd_set_probes(self.h, n, _ptr(kind, c_i32), _ptr(offset, c_i64), _ptr(idx, c_i64),
+                                         _ptr(weight, c_f), int(interval), int(max_samples), self.series.data_ptr(),
+                                         len(freqs), _ptr(freqs, c_d), self.probe_dft.data_ptr(), float(dt)))
+
+    def set_nf2ff(self, faces, freqs, interval, dt, inv_len, inv_dual):
+        """faces: list of dicts {normal, plane, a0, a1, b0, b1}; inv_len/inv_dual: 3 float arrays (z: nz+2 entries)"""
+        freqs = _np(freqs, np.float64)
+        arr = (_lib.Nf2ffFace * max(1, len(faces)))()
+        self.face_acc = []
+        for q, F in enumerate(faces):
+            na, nb = F["a1"] - F["a0"] + 1, F["b1"] - F["b0"] + 1
+            acc = torch.zeros((4, len(freqs), nb, na, 2), dtype=torch.float32, device=self.device)
+            self.face_acc.append(acc)
+            for n in ("normal", "plane", "a0", "a1", "b0", "b1"):
+                setattr(arr[q], n, int(F[n]))
+            arr[q].acc = acc.data_ptr()
+        il = [_np(a, np.float32) for a in inv_len]
+        idl = [_np(a, np.float32) for a in inv_dual]
+        self.nf_freqs = freqs
+        self.interval = int(interval)
+        check(self.L.b200fdtd_set_nf2ff(self.h, len(faces), arr, len(freqs), _ptr(freqs, c_d), int(interval), float(dt),
+                                        _ptr(il[0], c_f), _ptr(il[1], c_f), _ptr(il[2], c_f),
+                                        _ptr(idl[0], c_f), _ptr(idl[1], c_f), _ptr(idl[2], c_f)))
+
+    # ---- stepping ----
+    def run(self, nsteps, use_graph=True):
+        check(self.L.b200fdtd_run(self.h, int(nsteps), 1 if use_graph else 0))
+
+    def half_step(self, phase):
+        check(self.L.b200fdtd_half_step(self.h, int(phase)))
+
+    def update_only(self, which):
+        check(self.L.b200fdtd_update_only(self.h, int(which)))
+
+    def energy(self):
+        e = C.c_double()
+        check(self.L.b200fdtd_energy(self.h, C.byref(e)))
+        return e.value
+
+    def sync(self):
+        check(self.L.b200fdtd_sync(self.h))
+
+    @property
+    def ts(self):
+        v = C.c_int64()
+        check(self.L.b200fdtd_get_timestep(self.h, C.byref(v)))
+        return v.value
+
+    def set_timestep(self, ts):
+        check(self.L.b200fdtd_set_timestep(self.h, int(ts)))
+
+    @property
+    def num_samples(self):
+        v = C.c_int()
+        check(self.L.b200fdtd_num_samples(self.h, C.byref(v)))
+        return v.value
+
+
+def launch_count():
+    return int(_lib.lib().b200fdtd_launch_count())
+
+
+def farfield(pos, J, M, k, theta, phi, device=0):
+    """K11 on device.  pos [3][n], J/M [3][n] complex, theta/phi radians ->
+    (N_theta, N_phi, L_theta, L_phi) complex128 numpy arrays [ndir]."""
+    L = _lib.lib()
+    dev = torch.device("cuda", int(device))
+    pos_t = torch.as_tensor(np.ascontiguousarray(pos, np.float32), device=dev)
+    n = pos_t.shape[1]
+    Jt = torch.as_tensor(np.ascontiguousarray(np.stack([np.real(J), np.imag(J)], -1), np.float32), device=dev)
+    Mt = torch.as_tensor(np.ascontiguousarray(np.stack([np.real(M), np.imag(M)], -1), np.float32), device=dev)
+    th, ph = _np(theta, np.float64), _np(phi, np.float64)
+    out = torch.zeros((len(th), 4, 2), dtype=torch.float32, device=dev)
+    s = torch.cuda.current_stream(dev)
+    check(L.b200fdtd_farfield(dev.index, C.c_void_p(s.cuda_stream), n, pos_t.data_ptr(), Jt.data_ptr(), Mt.data_ptr(),
+                              float(k), len(th), _ptr(th, c_d), _ptr(ph, c_d), out.data_ptr()))
+    o = out.cpu().numpy().astype(np.float64)
+    oc = o[..., 0] + 1j * o[..., 1]
+    return oc[:, 0], oc[:, 1], oc[:, 2], oc[:, 3]

@@ -1,0 +1,974 @@
+// b200fdtd.cu — hand-written sm_100a kernels + C-ABI of the B200-native FDTD engine.
+//
+// Replaces the time-stepping core that the reference hands to openEMS through
+// FDTD.Run / CalcNF2FF / CalcPort (antenna_sim/solver_fdtd_openems_microstrip_3d.py:214,225;
+// antenna_sim/solver_fdtd_openems_microstrip.py:408-413).  Equations: SURVEY.md App. A.
+//
+// Data layout (see include/b200fdtd.h): fp32 [3][nz+2][ny][px], x fastest, z slowest, one
+// ghost plane below and above the owned z-slab.  All volume kernels stream whole x-rows
+// with 16-byte accesses, march along z keeping the z-neighbour plane in registers, take
+// the x-neighbour from the adjacent lane with a warp shuffle and the y-neighbour row from
+// L1/L2 (it is the row another warp of the same CTA streams at the same time).
+//
+// Arithmetic contract (bit-exact with oracle/fdtd_ref.c):
+//   curl = ((a - b) - c) + d          (three rounded fp32 adds, this order)
+//   f    = fmaf(ca, f, cb * curl)     (one rounded multiply, one fused multiply-add)
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <stdarg.h>
+#include <vector>
+#include <atomic>
+
+#include "b200fdtd.h"
+
+// ------------------------------------------------------------------------------------
+// error handling
+// ------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+static int fail(const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+    return 1;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+    return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+#define CKL() do { g_launches.fetch_add(1, std::memory_order_relaxed); cudaError_t e_ = cudaGetLastError(); \
+    if (e_ != cudaSuccess) return fail("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+extern "C" const char* b200fdtd_last_error(void) { return g_err; }
+extern "C" int b200fdtd_version(void) { return 1; }
+extern "C" int64_t b200fdtd_launch_count(void) { return g_launches.load(); }
+
+// ------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------
+struct PmlBoxDev {
+    int x0, y0, z0, bx, by, bz;
+    long long start;               // first flat element of this box in the concatenated space
+    float *flux_v, *flux_i;
+    const float *vv, *vvfo, *vvfn, *ii, *iifo, *iifn;
+};
+#define MAX_PML_BOXES 8
+struct PmlTable { int n; long long total; PmlBoxDev b[MAX_PML_BOXES]; };
+
+struct FaceDev {
+    int normal, plane, a0, a1, b0, b1;
+    float* acc;
+};
+#define MAX_FACES 8
+struct FaceTable { int n; FaceDev f[MAX_FACES]; };
+
+struct b200fdtd_ctx {
+    int device = 0;
+    int nx = 0, ny = 0, nz = 0, px = 0;
+    long long sz = 0, cs = 0;      // plane stride, component stride (floats)
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    float *volt = nullptr, *curr = nullptr;
+    const float *vv = nullptr, *vi = nullptr, *ii = nullptr, *iv = nullptr;
+    int kz = 16, ty = 4, variant = 0;
+    // step counter
+    int64_t ts = 0;
+    int* d_ts = nullptr;
+    // excitation
+    int64_t n_exc = 0; int64_t* exc_idx = nullptr; float* exc_amp = nullptr; int* exc_delay = nullptr;
+    float* exc_sig = nullptr; int exc_siglen = 0;
+    // mur
+    int64_t n_mur = 0; int64_t *mur_dst = nullptr, *mur_src = nullptr; float *mur_coeff = nullptr, *mur_tmp = nullptr;
+    // pml
+    PmlTable pml{};
+    // probes
+    int n_probes = 0; int* pr_kind = nullptr; int64_t* pr_off = nullptr; int64_t* pr_idx = nullptr; float* pr_w = nullptr;
+    int interval = 0; int max_samples = 0; float* pr_series = nullptr; int pr_nfreq = 0; double* pr_freqs = nullptr;
+    float* pr_dft = nullptr; double dt = 0.0;
+    // nf2ff
+    FaceTable faces{}; int nf_nfreq = 0; double* nf_freqs = nullptr; int nf_interval = 0; double nf_dt = 0.0;
+    float* inv_len[3] = {nullptr, nullptr, nullptr}; float* inv_dual[3] = {nullptr, nullptr, nullptr};
+    int nf_max_nodes = 0;
+    // energy
+    double* d_partials = nullptr; int n_partials = 0; double* d_energy = nullptr;
+    // graph
+    cudaGraphExec_t graph = nullptr; int graph_steps = 0; int64_t graph_kernels = 0;
+    // device copies of the slab / face tables
+    PmlTable* d_pml = nullptr; FaceTable* d_faces = nullptr;
+};
+
+static int sample_interval(const b200fdtd_ctx* c) {
+    if (c->n_probes > 0 && c->interval > 0) return c->interval;
+    if (c->faces.n > 0 && c->nf_interval > 0) return c->nf_interval;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------
+// volume kernels (K1 E update, K2 H update)
+// ------------------------------------------------------------------------------------
+struct VolParams {
+    float* __restrict__ f;          // field updated in place (volt for E, curr for H)
+    const float* __restrict__ g;    // the other field (read only in this pass)
+    const float* __restrict__ ca;   // vv / ii
+    const float* __restrict__ cb;   // vi / iv
+    int nx, ny, nz, px;
+    long long sz, cs;
+    int kz;                         // planes marched per CTA
+    int k0, k1;                     // plane range [k0,k1) handled by this launch
+};
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ld4_stream(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ld4_ro(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+
+// f = fmaf(ca, f, cb*(((a-b)-c)+d)) per lane of a float4
+__device__ __forceinline__ float upd1(float ca, float f, float cb, float a, float b, float c, float d) {
+    float curl = __fadd_rn(__fsub_rn(__fsub_rn(a, b), c), d);
+    return __fmaf_rn(ca, f, __fmul_rn(cb, curl));
+}
+__device__ __forceinline__ float4 upd4(float4 ca, float4 f, float4 cb, float4 a, float4 b, float4 c, float4 d) {
+    float4 r;
+    r.x = upd1(ca.x, f.x, cb.x, a.x, b.x, c.x, d.x);
+    r.y = upd1(ca.y, f.y, cb.y, a.y, b.y, c.y, d.y);
+    r.z = upd1(ca.z, f.z, cb.z, a.z, b.z, c.z, d.z);
+    r.w = upd1(ca.w, f.w, cb.w, a.w, b.w, c.w, d.w);
+    return r;
+}
+
+// E update: volt_n = vv_n volt_n + vi_n curl_n(curr)   (App. A1)
+//   x: ((Hz - Hz[j-1]) - Hy) + Hy[k-1]
+//   y: ((Hx - Hx[k-1]) - Hz) + Hz[i-1]
+//   z: ((Hy - Hy[i-1]) - Hx) + Hx[j-1]
+template <int TY>
+__global__ void __launch_bounds__(32 * TY) update_e_kernel(const VolParams p)
+{
+    const int lane = threadIdx.x;
+    const int i0 = (blockIdx.x * 32 + lane) * 4;
+    const int j = blockIdx.y * TY + threadIdx.y;
+    if (j >= p.ny) return;                                  // warp-uniform
+    const bool act = i0 < p.px;
+    const int kbeg = p.k0 + blockIdx.z * p.kz;
+    const int kend = min(kbeg + p.kz, p.k1);
+    const long long cs = p.cs, sz = p.sz;
+    const float* __restrict__ g = p.g;
+    float* __restrict__ f = p.f;
+
+    long long base = (long long)kbeg * sz + (long long)j * p.px + i0;   // plane kbeg-1 (ghost offset +1 applied below)
+    float4 hx_km = zero4(), hy_km = zero4();
+    if (act) { hx_km = ld4(g + base); hy_km = ld4(g + cs + base); }
+    base += sz;                                             // plane kbeg
+    const bool has_jm = j > 0;
+    const bool edge_load = act && lane == 0 && i0 > 0;
+
+    for (int k = kbeg; k < kend; ++k, base += sz) {
+        float4 hx = zero4(), hy = zero4(), hz = zero4(), hz_jm = zero4(), hx_jm = zero4();
+        float4 ex = zero4(), ey = zero4(), ez = zero4();
+        float4 ax = zero4(), ay = zero4(), az = zero4(), bx = zero4(), by = zero4(), bz = zero4();
+        float hz_e = 0.f, hy_e = 0.f;
+        if (act) {
+            hx = ld4(g + base); hy = ld4(g + cs + base); hz = ld4(g + 2 * cs + base);
+            if (has_jm) { hz_jm = ld4(g + 2 * cs + base - p.px); hx_jm = ld4(g + base - p.px); }
+            ex = ld4_stream(f + base); ey = ld4_stream(f + cs + base); ez = ld4_stream(f + 2 * cs + base);
+            ax = ld4_ro(p.ca + base); ay = ld4_ro(p.ca + cs + base); az = ld4_ro(p.ca + 2 * cs + base);
+            bx = ld4_ro(p.cb + base); by = ld4_ro(p.cb + cs + base); bz = ld4_ro(p.cb + 2 * cs + base);
+        }
+        if (edge_load) { hz_e = g[2 * cs + base - 1]; hy_e = g[cs + base - 1]; }
+        float hz_l = __shfl_up_sync(0xffffffffu, hz.w, 1);
+        float hy_l = __shfl_up_sync(0xffffffffu, hy.w, 1);
+        if (lane == 0) { hz_l = hz_e; hy_l = hy_e; }
+        const float4 hz_im = make_float4(hz_l, hz.x, hz.y, hz.z);
+        const float4 hy_im = make_float4(hy_l, hy.x, hy.y, hy.z);
+
+        ex = upd4(ax, ex, bx, hz, hz_jm, hy, hy_km);
+        ey = upd4(ay, ey, by, hx, hx_km, hz, hz_im);
+        ez = upd4(az, ez, bz, hy, hy_im, hx, hx_jm);
+        if (act) {
+            st4(f + base, ex); st4(f + cs + base, ey); st4(f + 2 * cs + base, ez);
+        }
+        hx_km = hx; hy_km = hy;
+    }
+}
+
+// H update: curr_n = ii_n curr_n + iv_n curl_n(volt)   (App. A1), marching downwards in z
+//   x: ((Ez - Ez[j+1]) - Ey) + Ey[k+1]
+//   y: ((Ex - Ex[k+1]) - Ez) + Ez[i+1]
+//   z: ((Ey - Ey[i+1]) - Ex) + Ex[j+1]
+template <int TY>
+__global__ void __launch_bounds__(32 * TY) update_h_kernel(const VolParams p)
+{
+    const int lane = threadIdx.x;
+    const int i0 = (blockIdx.x * 32 + lane) * 4;
+    const int j = blockIdx.y * TY + threadIdx.y;
+    if (j >= p.ny) return;
+    const bool act = i0 < p.px;
+    const int kbeg = p.k0 + blockIdx.z * p.kz;
+    const int kend = min(kbeg + p.kz, p.k1);
+    const long long cs = p.cs, sz = p.sz;
+    const float* __restrict__ g = p.g;
+    float* __restrict__ f = p.f;
+
+    long long base = (long long)(kend + 1) * sz + (long long)j * p.px + i0;   // plane kend (k+1 of the first plane)
+    float4 ex_kp = zero4(), ey_kp = zero4();
+    if (act) { ex_kp = ld4(g + base); ey_kp = ld4(g + cs + base); }
+    base -= sz;
+    const bool has_jp = j + 1 < p.ny;
+    const bool last = act && (lane == 31 || i0 + 4 >= p.px);
+    const bool edge_load = last && (i0 + 4 < p.px);
+
+    for (int k = kend - 1; k >= kbeg; --k, base -= sz) {
+        float4 ex = zero4(), ey = zero4(), ez = zero4(), ez_jp = zero4(), ex_jp = zero4();
+        float4 hx = zero4(), hy = zero4(), hz = zero4();
+        float4 ax = zero4(), ay = zero4(), az = zero4(), bx = zero4(), by = zero4(), bz = zero4();
+        float ez_e = 0.f, ey_e = 0.f;
+        if (act) {
+            ex = ld4(g + base); ey = ld4(g + cs + base); ez = ld4(g + 2 * cs + base);
+            if (has_jp) { ez_jp = ld4(g + 2 * cs + base + p.px); ex_jp = ld4(g + base + p.px); }
+            hx = ld4_stream(f + base); hy = ld4_stream(f + cs + base); hz = ld4_stream(f + 2 * cs + base);
+            ax = ld4_ro(p.ca + base); ay = ld4_ro(p.ca + cs + base); az = ld4_ro(p.ca + 2 * cs + base);
+            bx = ld4_ro(p.cb + base); by = ld4_ro(p.cb + cs + base); bz = ld4_ro(p.cb + 2 * cs + base);
+        }
+        if (edge_load) { ez_e = g[2 * cs + base + 4]; ey_e = g[cs + base + 4]; }
+        float ez_r = __shfl_down_sync(0xffffffffu, ez.x, 1);
+        float ey_r = __shfl_down_sync(0xffffffffu, ey.x, 1);
+        if (last || !act) { ez_r = ez_e; ey_r = ey_e; }
+        const float4 ez_ip = make_float4(ez.y, ez.z, ez.w, ez_r);
+        const float4 ey_ip = make_float4(ey.y, ey.z, ey.w, ey_r);
+
+        hx = upd4(ax, hx, bx, ez, ez_jp, ey, ey_kp);
+        hy = upd4(ay, hy, by, ex, ex_kp, ez, ez_ip);
+        hz = upd4(az, hz, bz, ey, ey_ip, ex, ex_jp);
+        if (act) {
+            st4(f + base, hx); st4(f + cs + base, hy); st4(f + 2 * cs + base, hz);
+        }
+        ex_kp = ex; ey_kp = ey;
+    }
+}
+
+static int launch_volume(b200fdtd_ctx* c, int which, int k0, int k1)
+{
+    if (!c->volt || !c->vv) return fail("fields/coefficients not bound");
+    if (k1 <= k0) return 0;
+    VolParams p;
+    p.f = which == 0 ? c->volt : c->curr;
+    p.g = which == 0 ? c->curr : c->volt;
+    p.ca = which == 0 ? c->vv : c->ii;
+    p.cb = which == 0 ? c->vi : c->iv;
+    p.nx = c->nx; p.ny = c->ny; p.nz = c->nz; p.px = c->px; p.sz = c->sz; p.cs = c->cs;
+    p.kz = c->kz; p.k0 = k0; p.k1 = k1;
+    const int ty = c->ty;
+    dim3 block(32, ty);
+    dim3 grid((c->px + 127) / 128, (c->ny + ty - 1) / ty, (k1 - k0 + c->kz - 1) / c->kz);
+    if (grid.y > 65535 || grid.z > 65535) return fail("grid too large for launch (ny/ty=%u, nz/kz=%u)", grid.y, grid.z);
+#define LAUNCH(TYV) do { if (which == 0) update_e_kernel<TYV><<<grid, block, 0, c->stream>>>(p); \
+                         else update_h_kernel<TYV><<<grid, block, 0, c->stream>>>(p); } while (0)
+    switch (ty) {
+        case 1: LAUNCH(1); break;
+        case 2: LAUNCH(2); break;
+        case 4: LAUNCH(4); break;
+        case 8: LAUNCH(8); break;
+        case 16: LAUNCH(16); break;
+        default: return fail("unsupported ty=%d", ty);
+    }
+#undef LAUNCH
+    CKL();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------
+// narrow-band kernels
+// ------------------------------------------------------------------------------------
+// K5 excitation (Apply2Voltages): volt[idx] += amp * signal[ts - delay]
+__global__ void excite_kernel(float* __restrict__ volt, const int64_t* __restrict__ idx,
+                              const float* __restrict__ amp, const int* __restrict__ delay,
+                              const float* __restrict__ sig, int siglen, int64_t n,
+                              const int* __restrict__ d_ts, int ts_off)
+{
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const int pos = *d_ts + ts_off - delay[e];
+    if (pos < 0 || pos >= siglen) return;
+    const int64_t q = idx[e];
+    volt[q] = __fmaf_rn(amp[e], sig[pos], volt[q]);
+}
+
+// K3 Mur (App. A3): pre: tmp = volt[src] - k volt[dst]; post: tmp += k volt[src]; apply: volt[dst] = tmp
+__global__ void mur_kernel(float* __restrict__ volt, const int64_t* __restrict__ dst,
+                           const int64_t* __restrict__ src, const float* __restrict__ coeff,
+                           float* __restrict__ tmp, int64_t n, int phase)
+{
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    if (phase == 0) {
+        tmp[e] = __fmaf_rn(-coeff[e], volt[dst[e]], volt[src[e]]);
+    } else if (phase == 1) {
+        tmp[e] = __fmaf_rn(coeff[e], volt[src[e]], tmp[e]);
+    } else {
+        volt[dst[e]] = tmp[e];
+    }
+}
+
+// K4 PML_8 (App. A4): split-flux UPML, pre and post passes over the slab boxes.
+//   pre : h = a*f - fo*flux ; f = flux ; flux = h
+//   post: h = flux ; flux = f ; f = h + fn*flux
+__global__ void pml_kernel(float* __restrict__ field, const PmlTable* __restrict__ tab, int which, int post,
+                           int ny, int px, long long sz, long long cs)
+{
+    const long long n = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (n >= tab->total) return;
+    int b = 0;
+    while (b + 1 < tab->n && n >= tab->b[b + 1].start) ++b;
+    const PmlBoxDev& B = tab->b[b];
+    long long r = n - B.start;
+    const int x = (int)(r % B.bx); r /= B.bx;
+    const int y = (int)(r % B.by); r /= B.by;
+    const int z = (int)(r % B.bz); r /= B.bz;
+    const int comp = (int)r;
+    const long long q = comp * cs + (long long)(B.z0 + z + 1) * sz + (long long)(B.y0 + y) * px + (B.x0 + x);
+    const long long l = n - B.start;
+    float* flux = which == 0 ? B.flux_v : B.flux_i;
+    if (!post) {
+        const float* a = which == 0 ? B.vv : B.ii;
+        const float* fo = which == 0 ? B.vvfo : B.iifo;
+        const float fl = flux[l];
+        const float h = __fmaf_rn(a[l], field[q], -__fmul_rn(fo[l], fl));
+        field[q] = fl;
+        flux[l] = h;
+    } else {
+        const float* fn = which == 0 ? B.vvfn : B.iifn;
+        const float h = flux[l];
+        const float v = field[q];
+        flux[l] = v;
+        field[q] = __fmaf_rn(fn[l], v, h);
+    }
+}
+
+// tiny: advance the device step counter
+__global__ void ts_add_kernel(int* d_ts, int n) { if (threadIdx.x == 0 && blockIdx.x == 0) *d_ts += n; }
+
+// K6+K7 probes: weighted line/loop sums with a warp-shuffle reduction, time series and running DFT
+__global__ void __launch_bounds__(128) probe_kernel(const float* __restrict__ volt, const float* __restrict__ curr,
+        const int* __restrict__ kind, const int64_t* __restrict__ off, const int64_t* __restrict__ idx,
+        const float* __restrict__ w, int interval, int max_samples, float* __restrict__ series,
+        int nfreq, const double* __restrict__ freqs, float* __restrict__ dft, double dt,
+        const int* __restrict__ d_ts, int ts_off)
+{
+    const int p = blockIdx.x;
+    const int ts = *d_ts + ts_off;                 // completed steps
+    const int s = ts / interval - 1;
+    if (s < 0 || s >= max_samples) return;
+    const float* fld = kind[p] == 0 ? volt : curr;
+    float acc = 0.f;
+    for (int64_t e = off[p] + threadIdx.x; e < off[p + 1]; e += blockDim.x) acc = __fmaf_rn(w[e], fld[idx[e]], acc);
+    __shared__ float red[4];
+    __shared__ float total;
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const float t = (red[0] + red[1]) + (red[2] + red[3]);
+        total = t;
+        series[(int64_t)p * max_samples + s] = t;
+    }
+    __syncthreads();
+    const float val = total;
+    const double tm = (kind[p] == 0 ? (double)ts : (double)ts + 0.5) * dt;
+    for (int q = threadIdx.x; q < nfreq; q += blockDim.x) {
+        double ph = freqs[q] * tm; ph -= floor(ph);
+        double sn, cn; sincospi(2.0 * ph, &sn, &cn);
+        float* a = dft + ((int64_t)p * nfreq + q) * 2;
+        a[0] = __fmaf_rn(val, (float)cn, a[0]);
+        a[1] = __fmaf_rn(-val, (float)sn, a[1]);
+    }
+}
+
+// K8 NF2FF: running DFT of node-interpolated tangential E/H on the Huygens box faces (App. A6)
+struct Nf2ffParams {
+    const float* volt; const float* curr;
+    int ny, px; long long sz, cs;
+    const float* il[3]; const float* idl[3];     // inverse primal / dual edge lengths (z arrays offset by one entry)
+    int nfreq; const double* freqs; double dt;
+    const int* d_ts; int ts_off;
+};
+__global__ void __launch_bounds__(128) nf2ff_kernel(const FaceTable* __restrict__ tab, const Nf2ffParams P)
+{
+    extern __shared__ float tw[];                  // [nfreq][4] = cosE, sinE, cosH, sinH
+    const FaceDev& F = tab->f[blockIdx.y];
+    const int na = F.a1 - F.a0 + 1, nb = F.b1 - F.b0 + 1;
+    const long long nn = (long long)na * nb;
+    if ((long long)blockIdx.x * blockDim.x >= nn) return;
+    const int ts = *P.d_ts + P.ts_off;
+    for (int q = threadIdx.x; q < P.nfreq; q += blockDim.x) {
+        double sn, cn;
+        double ph = P.freqs[q] * ((double)ts * P.dt); ph -= floor(ph);
+        sincospi(2.0 * ph, &sn, &cn); tw[4 * q] = (float)cn; tw[4 * q + 1] = (float)sn;
+        ph = P.freqs[q] * (((double)ts + 0.5) * P.dt); ph -= floor(ph);
+        sincospi(2.0 * ph, &sn, &cn); tw[4 * q + 2] = (float)cn; tw[4 * q + 3] = (float)sn;
+    }
+    __syncthreads();
+    const long long node = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (node >= nn) return;
+    const int n = F.normal, a = (n + 1) % 3, b = (n + 2) % 3;
+    const int ia = F.a0 + (int)(node % na), ib = F.b0 + (int)(node / na);
+    int co[3]; co[n] = F.plane; co[a] = ia; co[b] = ib;
+    const long long st[3] = {1, (long long)P.px, P.sz};
+    const long long lin0 = (long long)(co[2] + 1) * P.sz + (long long)co[1] * P.px + co[0];
+    const int oa = (a == 2), ob = (b == 2);
+    const float* va = P.volt + a * P.cs; const float* vb = P.volt + b * P.cs;
+    const float* ca = P.curr + a * P.cs; const float* cb = P.curr + b * P.cs;
+    const float Ea = 0.5f * (va[lin0] * P.il[a][ia + oa] + va[lin0 - st[a]] * P.il[a][ia + oa - 1]);
+    const float Eb = 0.5f * (vb[lin0] * P.il[b][ib + ob] + vb[lin0 - st[b]] * P.il[b][ib + ob - 1]);
+    const float Ha = 0.25f * P.idl[a][ia + oa] *
+        ((ca[lin0] + ca[lin0 - st[b]]) + (ca[lin0 - st[n]] + ca[lin0 - st[b] - st[n]]));
+    const float Hb = 0.25f * P.idl[b][ib + ob] *
+        ((cb[lin0] + cb[lin0 - st[a]]) + (cb[lin0 - st[n]] + cb[lin0 - st[a] - st[n]]));
+    const float v[4] = {Ea, Eb, Ha, Hb};
+    float2* acc = reinterpret_cast<float2*>(F.acc);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        for (int q = 0; q < P.nfreq; ++q) {
+            const float cn = tw[4 * q + (c >= 2 ? 2 : 0)], sn = tw[4 * q + (c >= 2 ? 3 : 1)];
+            float2* d = acc + ((long long)c * P.nfreq + q) * nn + node;
+            float2 t = *d;
+            t.x = __fmaf_rn(v[c], cn, t.x);
+            t.y = __fmaf_rn(-v[c], sn, t.y);
+            *d = t;
+        }
+    }
+}
+
+// K9 energy: deterministic two-stage reduction of sum(f^2) over the owned planes
+__global__ void __launch_bounds__(256) energy_partial_kernel(const float* __restrict__ volt, const float* __restrict__ curr,
+        long long sz, long long cs, long long n_owned, double* __restrict__ partials)
+{
+    // partials[2*block + 0/1] = sum volt^2 / sum curr^2 of this block's grid-stride share
+    double sv = 0.0, sc = 0.0;
+    const long long n4 = n_owned / 4;              // n_owned = nz*sz, multiple of 4
+    for (int c = 0; c < 3; ++c) {
+        const float4* v = reinterpret_cast<const float4*>(volt + c * cs + sz);
+        const float4* h = reinterpret_cast<const float4*>(curr + c * cs + sz);
+        for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n4; q += (long long)gridDim.x * blockDim.x) {
+            const float4 a = v[q], b = h[q];
+            sv += (double)(a.x * a.x + a.y * a.y) + (double)(a.z * a.z + a.w * a.w);
+            sc += (double)(b.x * b.x + b.y * b.y) + (double)(b.z * b.z + b.w * b.w);
+        }
+    }
+    __shared__ double rv[8], rc[8];
+    for (int o = 16; o > 0; o >>= 1) { sv += __shfl_down_sync(0xffffffffu, sv, o); sc += __shfl_down_sync(0xffffffffu, sc, o); }
+    if ((threadIdx.x & 31) == 0) { rv[threadIdx.x >> 5] = sv; rc[threadIdx.x >> 5] = sc; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0, b = 0;
+        for (int i = 0; i < 8; ++i) { a += rv[i]; b += rc[i]; }
+        partials[2 * blockIdx.x] = a; partials[2 * blockIdx.x + 1] = b;
+    }
+}
+__global__ void energy_final_kernel(const double* __restrict__ partials, int n, double* __restrict__ out)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double a = 0, b = 0;
+        for (int i = 0; i < n; ++i) { a += partials[2 * i]; b += partials[2 * i + 1]; }
+        out[0] = a; out[1] = b;
+    }
+}
+
+// K11 far field: N = sum J e^{jk r^.r'}, L = sum M e^{jk r^.r'} projected on theta^/phi^ (App. A6)
+__global__ void __launch_bounds__(256) farfield_kernel(long long npts, const float* __restrict__ pos,
+        const float* __restrict__ J, const float* __restrict__ M, double k, int ndir,
+        const double* __restrict__ theta, const double* __restrict__ phi, float* __restrict__ out)
+{
+    const int d = blockIdx.x;
+    if (d >= ndir) return;
+    double st, ct, sp, cp;
+    sincos(theta[d], &st, &ct); sincos(phi[d], &sp, &cp);
+    const float ux = (float)(k * st * cp), uy = (float)(k * st * sp), uz = (float)(k * ct);
+    double a[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) a[i] = 0.0;
+    for (long long q = threadIdx.x; q < npts; q += blockDim.x) {
+        const float ph = ux * pos[q] + uy * pos[npts + q] + uz * pos[2 * npts + q];
+        float sn, cn; sincosf(ph, &sn, &cn);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float jr = J[(c * npts + q) * 2], ji = J[(c * npts + q) * 2 + 1];
+            const float mr = M[(c * npts + q) * 2], mi = M[(c * npts + q) * 2 + 1];
+            a[2 * c] += (double)(jr * cn - ji * sn); a[2 * c + 1] += (double)(jr * sn + ji * cn);
+            a[6 + 2 * c] += (double)(mr * cn - mi * sn); a[6 + 2 * c + 1] += (double)(mr * sn + mi * cn);
+        }
+    }
+    __shared__ double red[8][12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        double v = a[i];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s[12];
+        for (int i = 0; i < 12; ++i) { s[i] = 0; for (int wv = 0; wv < 8; ++wv) s[i] += red[wv][i]; }
+        // theta^ = (ct cp, ct sp, -st), phi^ = (-sp, cp, 0)
+        for (int part = 0; part < 2; ++part) {         // 0: N from J, 1: L from M
+            const double* v = s + 6 * part;
+            for (int ri = 0; ri < 2; ++ri) {
+                const double vx = v[ri], vy = v[2 + ri], vz = v[4 + ri];
+                out[((long long)d * 4 + 2 * part) * 2 + ri] = (float)(vx * ct * cp + vy * ct * sp - vz * st);
+                out[((long long)d * 4 + 2 * part + 1) * 2 + ri] = (float)(-vx * sp + vy * cp);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------
+template <typename T>
+static int upload(T** dst, const T* src, int64_t n, cudaStream_t s)
+{
+    if (*dst) { cudaFree(*dst); *dst = nullptr; }
+    if (n <= 0) return 0;
+    CK(cudaMalloc((void**)dst, sizeof(T) * n));
+    CK(cudaMemcpyAsync(*dst, src, sizeof(T) * n, cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));
+    return 0;
+}
+static void drop_graph(b200fdtd_ctx* c) { if (c->graph) { cudaGraphExecDestroy(c->graph); c->graph = nullptr; c->graph_steps = 0; } }
+
+
+// ------------------------------------------------------------------------------------
+// C-ABI
+// ------------------------------------------------------------------------------------
+extern "C" int b200fdtd_create(b200fdtd_ctx** out, int device, int nx, int ny, int nz, int px, void* stream)
+{
+    if (!out) return fail("out is NULL");
+    if (nx < 2 || ny < 2 || nz < 1) return fail("grid too small: %d x %d x %d", nx, ny, nz);
+    if (px < nx || (px % 4) != 0) return fail("px=%d must be >= nx=%d and a multiple of 4", px, nx);
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail("device %d out of range (%d devices)", device, ndev);
+    CK(cudaSetDevice(device));
+    b200fdtd_ctx* c = new b200fdtd_ctx();
+    c->device = device; c->nx = nx; c->ny = ny; c->nz = nz; c->px = px;
+    c->sz = (long long)ny * px; c->cs = (long long)(nz + 2) * c->sz;
+    if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
+    else { CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+    CK(cudaMalloc((void**)&c->d_ts, sizeof(int)));
+    CK(cudaMemsetAsync(c->d_ts, 0, sizeof(int), c->stream));
+    c->n_partials = 148 * 8;
+    CK(cudaMalloc((void**)&c->d_partials, sizeof(double) * 2 * c->n_partials));
+    CK(cudaMalloc((void**)&c->d_energy, sizeof(double) * 2));
+    *out = c;
+    return 0;
+}
+
+extern "C" int b200fdtd_destroy(b200fdtd_ctx* c)
+{
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    drop_graph(c);
+    cudaFree(c->d_ts); cudaFree(c->d_partials); cudaFree(c->d_energy);
+    cudaFree(c->exc_idx); cudaFree(c->exc_amp); cudaFree(c->exc_delay); cudaFree(c->exc_sig);
+    cudaFree(c->mur_dst); cudaFree(c->mur_src); cudaFree(c->mur_coeff); cudaFree(c->mur_tmp);
+    cudaFree(c->pr_kind); cudaFree(c->pr_off); cudaFree(c->pr_idx); cudaFree(c->pr_w); cudaFree(c->pr_freqs);
+    cudaFree(c->nf_freqs);
+    for (int a = 0; a < 3; ++a) { cudaFree(c->inv_len[a]); cudaFree(c->inv_dual[a]); }
+    cudaFree(c->d_pml); cudaFree(c->d_faces);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+
+extern "C" int b200fdtd_bind_fields(b200fdtd_ctx* c, float* volt, float* curr)
+{
+    if (!c || !volt || !curr) return fail("NULL argument");
+    if (((uintptr_t)volt | (uintptr_t)curr) & 15) return fail("field pointers must be 16-byte aligned");
+    c->volt = volt; c->curr = curr; drop_graph(c);
+    return 0;
+}
+
+extern "C" int b200fdtd_bind_coeffs(b200fdtd_ctx* c, const float* vv, const float* vi, const float* ii, const float* iv)
+{
+    if (!c || !vv || !vi || !ii || !iv) return fail("NULL argument");
+    if (((uintptr_t)vv | (uintptr_t)vi | (uintptr_t)ii | (uintptr_t)iv) & 15) return fail("coefficient pointers must be 16-byte aligned");
+    c->vv = vv; c->vi = vi; c->ii = ii; c->iv = iv; drop_graph(c);
+    return 0;
+}
+
+extern "C" int b200fdtd_set_tuning(b200fdtd_ctx* c, int kz, int ty, int variant)
+{
+    if (!c) return fail("NULL ctx");
+    if (kz < 1) return fail("kz must be >= 1");
+    if (!(ty == 1 || ty == 2 || ty == 4 || ty == 8 || ty == 16)) return fail("ty must be 1,2,4,8 or 16");
+    c->kz = kz; c->ty = ty; c->variant = variant; drop_graph(c);
+    return 0;
+}
+
+extern "C" int b200fdtd_set_excitation(b200fdtd_ctx* c, int64_t n, const int64_t* idx, const float* amp,
+                                        const int32_t* delay, const float* signal, int32_t siglen)
+{
+    if (!c) return fail("NULL ctx");
+    if (n < 0 || (n > 0 && (!idx || !amp || !delay || !signal || siglen <= 0))) return fail("bad excitation arguments");
+    CK(cudaSetDevice(c->device));
+    const long long total = 3 * c->cs;
+    for (int64_t e = 0; e < n; ++e) if (idx[e] < 0 || idx[e] >= total) return fail("excitation index %lld out of range", (long long)idx[e]);
+    drop_graph(c);
+    c->n_exc = n; c->exc_siglen = siglen;
+    if (upload(&c->exc_idx, idx, n, c->stream)) return 1;
+    if (upload(&c->exc_amp, amp, n, c->stream)) return 1;
+    if (upload(&c->exc_delay, (const int*)delay, n, c->stream)) return 1;
+    if (upload(&c->exc_sig, signal, n > 0 ? siglen : 0, c->stream)) return 1;
+    return 0;
+}
+
+extern "C" int b200fdtd_set_mur(b200fdtd_ctx* c, int64_t n, const int64_t* dst, const int64_t* src, const float* coeff)
+{
+    if (!c) return fail("NULL ctx");
+    if (n < 0 || (n > 0 && (!dst || !src || !coeff))) return fail("bad Mur arguments");
+    CK(cudaSetDevice(c->device));
+    const long long total = 3 * c->cs;
+    for (int64_t e = 0; e < n; ++e)
+        if (dst[e] < 0 || dst[e] >= total || src[e] < 0 || src[e] >= total) return fail("Mur index out of range at entry %lld", (long long)e);
+    drop_graph(c);
+    c->n_mur = n;
+    if (upload(&c->mur_dst, dst, n, c->stream)) return 1;
+    if (upload(&c->mur_src, src, n, c->stream)) return 1;
+    if (upload(&c->mur_coeff, coeff, n, c->stream)) return 1;
+    if (c->mur_tmp) { cudaFree(c->mur_tmp); c->mur_tmp = nullptr; }
+    if (n > 0) { CK(cudaMalloc((void**)&c->mur_tmp, sizeof(float) * n)); CK(cudaMemsetAsync(c->mur_tmp, 0, sizeof(float) * n, c->stream)); }
+    return 0;
+}
+
+extern "C" int b200fdtd_set_pml(b200fdtd_ctx* c, int nboxes, const b200fdtd_pml_box* boxes)
+{
+    if (!c) return fail("NULL ctx");
+    if (nboxes < 0 || nboxes > MAX_PML_BOXES) return fail("nboxes=%d out of range (max %d)", nboxes, MAX_PML_BOXES);
+    CK(cudaSetDevice(c->device));
+    drop_graph(c);
+    PmlTable t; memset(&t, 0, sizeof(t));
+    t.n = nboxes; long long start = 0;
+    for (int b = 0; b < nboxes; ++b) {
+        const b200fdtd_pml_box& B = boxes[b];
+        if (B.bx <= 0 || B.by <= 0 || B.bz <= 0 || B.x0 < 0 || B.y0 < 0 || B.z0 < 0 ||
+            B.x0 + B.bx > c->nx || B.y0 + B.by > c->ny || B.z0 + B.bz > c->nz)
+            return fail("PML box %d outside the grid", b);
+        if (!B.flux_v || !B.flux_i || !B.vv || !B.vvfo || !B.vvfn || !B.ii || !B.iifo || !B.iifn) return fail("PML box %d has NULL arrays", b);
+        PmlBoxDev& D = t.b[b];
+        D.x0 = B.x0; D.y0 = B.y0; D.z0 = B.z0; D.bx = B.bx; D.by = B.by; D.bz = B.bz; D.start = start;
+        D.flux_v = B.flux_v; D.flux_i = B.flux_i; D.vv = B.vv; D.vvfo = B.vvfo; D.vvfn = B.vvfn; D.ii = B.ii; D.iifo = B.iifo; D.iifn = B.iifn;
+        start += 3LL * B.bx * B.by * B.bz;
+    }
+    t.total = start;
+    c->pml = t;
+    if (!c->d_pml) CK(cudaMalloc((void**)&c->d_pml, sizeof(PmlTable)));
+    CK(cudaMemcpyAsync(c->d_pml, &t, sizeof(PmlTable), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int b200fdtd_set_probes(b200fdtd_ctx* c, int nprobes, const int32_t* kind, const int64_t* offset,
+                                    const int64_t* idx, const float* weight, int interval, int max_samples,
+                                    float* series, int nfreq, const double* freqs, float* dft, double dt)
+{
+    if (!c) return fail("NULL ctx");
+    if (nprobes < 0) return fail("nprobes < 0");
+    CK(cudaSetDevice(c->device));
+    drop_graph(c);
+    c->n_probes = nprobes;
+    if (nprobes == 0) return 0;
+    if (!kind || !offset || !idx || !weight || !series) return fail("NULL probe argument");
+    if (interval < 1 || max_samples < 1) return fail("interval and max_samples must be >= 1");
+    if (nfreq < 0 || (nfreq > 0 && (!freqs || !dft))) return fail("bad probe DFT arguments");
+    if (c->faces.n > 0 && c->nf_interval != interval) return fail("probe interval %d differs from NF2FF interval %d", interval, c->nf_interval);
+    const long long total = 3 * c->cs;
+    const int64_t ne = offset[nprobes];
+    for (int64_t e = 0; e < ne; ++e) if (idx[e] < 0 || idx[e] >= total) return fail("probe index out of range at entry %lld", (long long)e);
+    c->interval = interval; c->max_samples = max_samples; c->pr_series = series; c->pr_nfreq = nfreq; c->pr_dft = dft; c->dt = dt;
+    if (upload(&c->pr_kind, (const int*)kind, nprobes, c->stream)) return 1;
+    if (upload(&c->pr_off, offset, nprobes + 1, c->stream)) return 1;
+    if (upload(&c->pr_idx, idx, ne, c->stream)) return 1;
+    if (upload(&c->pr_w, weight, ne, c->stream)) return 1;
+    if (upload(&c->pr_freqs, freqs, nfreq, c->stream)) return 1;
+    return 0;
+}
+
+extern "C" int b200fdtd_set_nf2ff(b200fdtd_ctx* c, int nfaces, const b200fdtd_nf2ff_face* faces, int nfreq,
+                                   const double* freqs, int interval, double dt,
+                                   const float* ilx, const float* ily, const float* ilz,
+                                   const float* idx_, const float* idy, const float* idz)
+{
+    if (!c) return fail("NULL ctx");
+    if (nfaces < 0 || nfaces > MAX_FACES) return fail("nfaces=%d out of range (max %d)", nfaces, MAX_FACES);
+    CK(cudaSetDevice(c->device));
+    drop_graph(c);
+    c->faces.n = nfaces;
+    if (nfaces == 0) return 0;
+    if (nfreq < 1 || !freqs || interval < 1) return fail("bad NF2FF frequency/interval arguments");
+    if (c->n_probes > 0 && c->interval != interval) return fail("NF2FF interval %d differs from probe interval %d", interval, c->interval);
+    if (!ilx || !ily || !ilz || !idx_ || !idy || !idz) return fail("NULL mesh spacing array");
+    const int dims[3] = {c->nx, c->ny, c->nz};
+    int max_nodes = 0;
+    for (int q = 0; q < nfaces; ++q) {
+        const b200fdtd_nf2ff_face& F = faces[q];
+        if (F.normal < 0 || F.normal > 2 || !F.acc) return fail("bad NF2FF face %d", q);
+        const int a = (F.normal + 1) % 3, b = (F.normal + 2) % 3;
+        // z indices may touch plane 0 of the slab (needs the ghost plane below); x/y must be interior
+        const int lo_n = F.normal == 2 ? 0 : 1, lo_a = a == 2 ? 0 : 1, lo_b = b == 2 ? 0 : 1;
+        if (F.plane < lo_n || F.plane >= dims[F.normal] || F.a0 < lo_a || F.a1 >= dims[a] || F.a0 > F.a1 ||
+            F.b0 < lo_b || F.b1 >= dims[b] || F.b0 > F.b1)
+            return fail("NF2FF face %d outside the grid", q);
+        FaceDev& D = c->faces.f[q];
+        D.normal = F.normal; D.plane = F.plane; D.a0 = F.a0; D.a1 = F.a1; D.b0 = F.b0; D.b1 = F.b1; D.acc = F.acc;
+        const int nn = (F.a1 - F.a0 + 1) * (F.b1 - F.b0 + 1);
+        if (nn > max_nodes) max_nodes = nn;
+    }
+    c->nf_max_nodes = max_nodes; c->nf_nfreq = nfreq; c->nf_interval = interval; c->nf_dt = dt;
+    if (upload(&c->nf_freqs, freqs, nfreq, c->stream)) return 1;
+    const float* il[3] = {ilx, ily, ilz}; const float* id[3] = {idx_, idy, idz};
+    for (int a = 0; a < 3; ++a) {
+        const int n = a == 2 ? c->nz + 2 : dims[a];
+        if (upload(&c->inv_len[a], il[a], n, c->stream)) return 1;
+        if (upload(&c->inv_dual[a], id[a], n, c->stream)) return 1;
+    }
+    if (!c->d_faces) CK(cudaMalloc((void**)&c->d_faces, sizeof(FaceTable)));
+    CK(cudaMemcpyAsync(c->d_faces, &c->faces, sizeof(FaceTable), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int b200fdtd_get_timestep(b200fdtd_ctx* c, int64_t* ts) { if (!c || !ts) return fail("NULL argument"); *ts = c->ts; return 0; }
+
+extern "C" int b200fdtd_set_timestep(b200fdtd_ctx* c, int64_t ts)
+{
+    if (!c) return fail("NULL ctx");
+    if (ts < 0 || ts > 0x7fffffff) return fail("timestep out of range");
+    CK(cudaSetDevice(c->device));
+    int v = (int)ts;
+    CK(cudaMemcpyAsync(c->d_ts, &v, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->ts = ts;
+    return 0;
+}
+
+// ---- one step, expressed as launches with a device-side step offset -----------------
+static int launch_pml(b200fdtd_ctx* c, int which, int post)
+{
+    if (c->pml.n == 0 || c->pml.total == 0) return 0;
+    const int threads = 256;
+    const long long blocks = (c->pml.total + threads - 1) / threads;
+    pml_kernel<<<(unsigned)blocks, threads, 0, c->stream>>>(which == 0 ? c->volt : c->curr, c->d_pml, which, post,
+                                                          c->ny, c->px, c->sz, c->cs);
+    CKL();
+    return 0;
+}
+static int launch_mur(b200fdtd_ctx* c, int phase)
+{
+    if (c->n_mur == 0) return 0;
+    const int threads = 256;
+    mur_kernel<<<(unsigned)((c->n_mur + threads - 1) / threads), threads, 0, c->stream>>>(c->volt, c->mur_dst, c->mur_src,
+                                                                                       c->mur_coeff, c->mur_tmp, c->n_mur, phase);
+    CKL();
+    return 0;
+}
+static int launch_excite(b200fdtd_ctx* c, int ts_off)
+{
+    if (c->n_exc == 0) return 0;
+    const int threads = 128;
+    excite_kernel<<<(unsigned)((c->n_exc + threads - 1) / threads), threads, 0, c->stream>>>(c->volt, c->exc_idx, c->exc_amp,
+        c->exc_delay, c->exc_sig, c->exc_siglen, c->n_exc, c->d_ts, ts_off);
+    CKL();
+    return 0;
+}
+static int launch_sampling(b200fdtd_ctx* c, int ts_off)
+{
+    if (c->n_probes > 0) {
+        probe_kernel<<<c->n_probes, 128, 0, c->stream>>>(c->volt, c->curr, c->pr_kind, c->pr_off, c->pr_idx, c->pr_w,
+            c->interval, c->max_samples, c->pr_series, c->pr_nfreq, c->pr_freqs, c->pr_dft, c->dt, c->d_ts, ts_off);
+        CKL();
+    }
+    if (c->faces.n > 0) {
+        Nf2ffParams P;
+        P.volt = c->volt; P.curr = c->curr; P.ny = c->ny; P.px = c->px; P.sz = c->sz; P.cs = c->cs;
+        for (int a = 0; a < 3; ++a) { P.il[a] = c->inv_len[a]; P.idl[a] = c->inv_dual[a]; }
+        P.nfreq = c->nf_nfreq; P.freqs = c->nf_freqs; P.dt = c->nf_dt; P.d_ts = c->d_ts; P.ts_off = ts_off;
+        dim3 grid((c->nf_max_nodes + 127) / 128, c->faces.n);
+        nf2ff_kernel<<<grid, 128, sizeof(float) * 4 * c->nf_nfreq, c->stream>>>(c->d_faces, P);
+        CKL();
+    }
+    return 0;
+}
+static int launch_ts_add(b200fdtd_ctx* c, int n)
+{
+    ts_add_kernel<<<1, 32, 0, c->stream>>>(c->d_ts, n);
+    CKL();
+    return 0;
+}
+
+// E half step with device step offset `off` (host knows ts + off)
+static int e_half(b200fdtd_ctx* c, int off)
+{
+    if (launch_pml(c, 0, 0)) return 1;
+    if (launch_mur(c, 0)) return 1;
+    if (launch_volume(c, 0, 0, c->nz)) return 1;
+    if (launch_pml(c, 0, 1)) return 1;
+    if (launch_mur(c, 1)) return 1;
+    if (launch_excite(c, off)) return 1;
+    if (launch_mur(c, 2)) return 1;
+    return 0;
+}
+static int h_half(b200fdtd_ctx* c)
+{
+    if (launch_pml(c, 1, 0)) return 1;
+    if (launch_volume(c, 1, 0, c->nz)) return 1;
+    if (launch_pml(c, 1, 1)) return 1;
+    return 0;
+}
+
+static int run_eager(b200fdtd_ctx* c, int64_t n)
+{
+    const int iv = sample_interval(c);
+    for (int64_t s = 0; s < n; ++s) {
+        if (e_half(c, 0)) return 1;
+        if (h_half(c)) return 1;
+        if (launch_ts_add(c, 1)) return 1;
+        c->ts += 1;
+        if (iv > 0 && (c->ts % iv) == 0) if (launch_sampling(c, 0)) return 1;
+    }
+    return 0;
+}
+
+static int build_graph(b200fdtd_ctx* c, int steps)
+{
+    drop_graph(c);
+    const int iv = sample_interval(c);
+    cudaGraph_t g = nullptr;
+    const int64_t before = g_launches.load();
+    CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = 0;
+    for (int s = 0; s < steps && !rc; ++s) {
+        rc = e_half(c, s);
+        if (!rc) rc = h_half(c);
+    }
+    if (!rc && iv > 0) rc = launch_sampling(c, steps);      // graph starts at ts % iv == 0 and spans iv steps
+    if (!rc) rc = launch_ts_add(c, steps);
+    cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+    if (rc) { if (g) cudaGraphDestroy(g); return 1; }
+    if (e != cudaSuccess) return fail("cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&c->graph, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) { c->graph = nullptr; return fail("cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); }
+    c->graph_steps = steps;
+    c->graph_kernels = g_launches.load() - before;      // kernel nodes in the graph
+    g_launches.fetch_sub(c->graph_kernels);             // capturing is not launching
+    return 0;
+}
+
+extern "C" int b200fdtd_run(b200fdtd_ctx* c, int64_t nsteps, int use_graph)
+{
+    if (!c) return fail("NULL ctx");
+    if (nsteps < 0) return fail("nsteps < 0");
+    if (!c->volt || !c->vv) return fail("fields/coefficients not bound");
+    CK(cudaSetDevice(c->device));
+    if (!use_graph) return run_eager(c, nsteps);
+    const int iv = sample_interval(c);
+    const int chunk = iv > 0 ? iv : 16;
+    int64_t left = nsteps;
+    // align to a chunk boundary
+    const int64_t mis = c->ts % chunk;
+    if (mis != 0) {
+        const int64_t n = (chunk - mis) < left ? (chunk - mis) : left;
+        if (run_eager(c, n)) return 1;
+        left -= n;
+    }
+    if (left >= chunk) {
+        if (!c->graph || c->graph_steps != chunk) if (build_graph(c, chunk)) return 1;
+        while (left >= chunk) {
+            CK(cudaGraphLaunch(c->graph, c->stream));
+            g_launches.fetch_add(c->graph_kernels, std::memory_order_relaxed);
+            c->ts += chunk; left -= chunk;
+        }
+    }
+    if (left > 0) if (run_eager(c, left)) return 1;
+    return 0;
+}
+
+extern "C" int b200fdtd_half_step(b200fdtd_ctx* c, int phase)
+{
+    if (!c) return fail("NULL ctx");
+    if (!c->volt || !c->vv) return fail("fields/coefficients not bound");
+    CK(cudaSetDevice(c->device));
+    if (phase == 0) return e_half(c, 0);
+    if (phase == 1) {
+        if (h_half(c)) return 1;
+        if (launch_ts_add(c, 1)) return 1;
+        c->ts += 1;
+        const int iv = sample_interval(c);
+        if (iv > 0 && (c->ts % iv) == 0) return launch_sampling(c, 0);
+        return 0;
+    }
+    return fail("phase must be 0 or 1");
+}
+
+extern "C" int b200fdtd_update_only(b200fdtd_ctx* c, int which)
+{
+    if (!c) return fail("NULL ctx");
+    if (which != 0 && which != 1) return fail("which must be 0 or 1");
+    CK(cudaSetDevice(c->device));
+    return launch_volume(c, which, 0, c->nz);
+}
+
+extern "C" int b200fdtd_energy(b200fdtd_ctx* c, double* energy)
+{
+    if (!c || !energy) return fail("NULL argument");
+    if (!c->volt) return fail("fields not bound");
+    CK(cudaSetDevice(c->device));
+    const long long n_owned = (long long)c->nz * c->sz;
+    energy_partial_kernel<<<c->n_partials, 256, 0, c->stream>>>(c->volt, c->curr, c->sz, c->cs, n_owned, c->d_partials);
+    CKL();
+    energy_final_kernel<<<1, 32, 0, c->stream>>>(c->d_partials, c->n_partials, c->d_energy);
+    CKL();
+    double h[2];
+    CK(cudaMemcpyAsync(h, c->d_energy, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    const double EPS0 = 8.85418781762e-12, MUE0 = 1.256637062e-6;
+    *energy = 0.5 * EPS0 * h[0] + 0.5 * MUE0 * h[1];
+    return 0;
+}
+
+extern "C" int b200fdtd_sync(b200fdtd_ctx* c)
+{
+    if (!c) return fail("NULL ctx");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int b200fdtd_num_samples(b200fdtd_ctx* c, int* n)
+{
+    if (!c || !n) return fail("NULL argument");
+    const int iv = sample_interval(c);
+    int s = iv > 0 ? (int)(c->ts / iv) : 0;
+    if (c->n_probes > 0 && s > c->max_samples) s = c->max_samples;
+    *n = s;
+    return 0;
+}
+
+extern "C" int b200fdtd_farfield(int device, void* stream, int64_t npts, const float* pos, const float* J,
+                                  const float* M, double k, int ndir, const double* theta, const double* phi, float* out)
+{
+    if (npts <= 0 || ndir <= 0 || !pos || !J || !M || !theta || !phi || !out) return fail("bad far-field arguments");
+    CK(cudaSetDevice(device));
+    cudaStream_t s = (cudaStream_t)stream;
+    double *d_th = nullptr, *d_ph = nullptr;
+    CK(cudaMalloc((void**)&d_th, sizeof(double) * ndir));
+    CK(cudaMalloc((void**)&d_ph, sizeof(double) * ndir));
+    CK(cudaMemcpyAsync(d_th, theta, sizeof(double) * ndir, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_ph, phi, sizeof(double) * ndir, cudaMemcpyHostToDevice, s));
+    farfield_kernel<<<ndir, 256, 0, s>>>(npts, pos, J, M, k, ndir, d_th, d_ph, out);
+    g_launches.fetch_add(1);
+    cudaError_t e = cudaGetLastError();
+    cudaStreamSynchronize(s);
+    cudaFree(d_th); cudaFree(d_ph);
+    if (e != cudaSuccess) return fail("farfield launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}

@@ -1,0 +1,151 @@
+/*
+ * b200fdtd.h — C-ABI of the B200-native FDTD time-stepping engine (libb200fdtd.so).
+ *
+ * This is the drop-in boundary underneath the CSXCAD/openEMS-style Python surface that
+ * the reference's solver backends call.  The reference has no FFI of its own: the seam
+ * is `FDTD.Run(sim_path, ...)` / `nf2ff.CalcNF2FF(...)` / `port.CalcPort(...)`
+ *   antenna_sim/solver_fdtd_openems_microstrip_3d.py:82-93,176-179,214,225
+ *   antenna_sim/solver_fdtd_openems_microstrip_multi_3d.py:287-292,541,564,610,621
+ *   antenna_sim/solver_fdtd_openems_microstrip.py:406-416 (CalcPort / S11)
+ * Every entry point below names the openEMS engine facility that `Run` used to provide
+ * and that the shim (fdtd-solver-antennas_b200/openEMS) now binds through ctypes.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no torch types.  "dev" pointers are CUDA device
+ *    pointers (torch tensor .data_ptr()); "host" pointers are ordinary host memory and
+ *    are copied during the call.
+ *  - every function returns 0 on success, non-zero on failure; the message is
+ *    available from b200fdtd_last_error() (thread local).  Nothing aborts.
+ *  - volumetric arrays are fp32, laid out [3][nz+2][ny][px]: component, z-plane,
+ *    y-row, x (fastest).  Plane 0 and plane nz+1 are ghost planes (z-slab halos; zero
+ *    on a global boundary), px >= nx is the row pitch in floats (multiple of 4).
+ *    lin(c,k,j,i) = ((c*(nz+2) + k+1)*ny + j)*px + i   with k in [-1, nz].
+ *  - state: volt = edge voltages E·dl, curr = edge currents H·dl~ (openEMS convention);
+ *    update equations: SURVEY.md App. A1.
+ */
+#ifndef B200FDTD_H
+#define B200FDTD_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200fdtd_ctx b200fdtd_ctx;
+
+/* last error message of the calling thread ("" if none) */
+const char* b200fdtd_last_error(void);
+/* library/ABI version (bumped when a signature changes) */
+int b200fdtd_version(void);
+/* number of kernels this library has launched since load (all contexts) */
+int64_t b200fdtd_launch_count(void);
+
+/* ---- context ------------------------------------------------------------------ */
+/* Engine instance for one z-slab on one GPU.  `stream` is a cudaStream_t (0 = the
+ * library creates its own non-blocking stream).  Replaces openEMS::SetupFDTD's engine
+ * allocation inside FDTD.Run (…microstrip_3d.py:214). */
+int b200fdtd_create(b200fdtd_ctx** out, int device, int nx, int ny, int nz, int px, void* stream);
+int b200fdtd_destroy(b200fdtd_ctx* ctx);
+
+/* volt/curr [3][nz+2][ny][px] (dev, read-write) */
+int b200fdtd_bind_fields(b200fdtd_ctx* ctx, float* volt, float* curr);
+/* vv,vi,ii,iv [3][nz+2][ny][px] (dev, read-only): the openEMS operator (App. A2) */
+int b200fdtd_bind_coeffs(b200fdtd_ctx* ctx, const float* vv, const float* vi,
+                         const float* ii, const float* iv);
+/* tuning knobs of the volume kernels: planes marched per CTA (kz), rows per CTA (ty in {2,4,8}),
+ * variant (0 = register z-march) */
+int b200fdtd_set_tuning(b200fdtd_ctx* ctx, int kz, int ty, int variant);
+
+/* ---- excitation (openEMS Engine_Ext_Excitation::Apply2Voltages; AddLumpedPort's
+ *      soft E-field source, …microstrip_3d.py:176; SetGaussExcite :83) ------------- */
+/* n edges: volt[idx[e]] += amp[e] * signal[ts - delay[e]]  (0 outside [0,siglen)).
+ * idx/amp/delay/signal are host arrays. */
+int b200fdtd_set_excitation(b200fdtd_ctx* ctx, int64_t n, const int64_t* idx, const float* amp,
+                            const int32_t* delay, const float* signal, int32_t siglen);
+
+/* ---- Mur 1st-order ABC (SetBoundaryCond(['MUR']*6), …microstrip_3d.py:84-90) ---- */
+/* n boundary edges (host arrays): dst = linear index of the boundary edge, src = its
+ * inward neighbour, coeff = (c dt - d)/(c dt + d). */
+int b200fdtd_set_mur(b200fdtd_ctx* ctx, int64_t n, const int64_t* dst, const int64_t* src,
+                     const float* coeff);
+
+/* ---- PML_8 split-flux UPML slabs (SetBoundaryCond(['PML_8']*6)) ------------------ */
+typedef struct {
+    int32_t x0, y0, z0;            /* start of the box; z0 in local plane coordinates   */
+    int32_t bx, by, bz;            /* extent of the box in cells                         */
+    float* flux_v;                 /* dev [3][bz][by][bx] voltage flux (zero-initialised) */
+    float* flux_i;                 /* dev [3][bz][by][bx] current flux                   */
+    const float* vv;               /* dev [3][bz][by][bx] 2nd-stage self coefficient     */
+    const float* vvfo;             /* dev … old-flux coefficient                          */
+    const float* vvfn;             /* dev … new-flux coefficient                          */
+    const float* ii;               /* dev same three for the currents                    */
+    const float* iifo;
+    const float* iifn;
+} b200fdtd_pml_box;
+int b200fdtd_set_pml(b200fdtd_ctx* ctx, int nboxes, const b200fdtd_pml_box* boxes /*host*/);
+
+/* ---- probes: voltage line integrals / current loop integrals, their time series
+ *      and a running DFT (AddLumpedPort's port_ut/port_it probes; CalcPort,
+ *      …microstrip.py:408-413) ------------------------------------------------------ */
+/* nprobes probes; probe p sums weight[e]*field[idx[e]] for e in [offset[p],offset[p+1])
+ * where field = volt (kind 0, time stamp ts*dt) or curr (kind 1, time stamp (ts+1/2)*dt).
+ * Sampled every `interval` steps.  series: dev [nprobes][max_samples] f32.
+ * dft: dev [nprobes][nfreq][2] f32 (re,im) running sum of x(t) exp(-j 2 pi f t)
+ * (may be NULL with nfreq 0).  kind/offset/idx/weight/freqs are host arrays. */
+int b200fdtd_set_probes(b200fdtd_ctx* ctx, int nprobes, const int32_t* kind, const int64_t* offset,
+                        const int64_t* idx, const float* weight, int interval, int max_samples,
+                        float* series, int nfreq, const double* freqs, float* dft, double dt);
+
+/* ---- NF2FF Huygens box: running DFT of node-interpolated tangential E and H
+ *      (CreateNF2FFBox, …microstrip_3d.py:179; CalcNF2FF :225) ---------------------- */
+typedef struct {
+    int32_t normal;                /* 0,1,2 = x,y,z                                       */
+    int32_t plane;                 /* line index of the face along `normal` (local for z) */
+    int32_t a0, a1;                /* inclusive node range along axis (normal+1)%3        */
+    int32_t b0, b1;                /* inclusive node range along axis (normal+2)%3        */
+    float* acc;                    /* dev [4][nfreq][nb][na][2] f32: Ea,Eb,Ha,Hb          */
+} b200fdtd_nf2ff_face;
+/* inv_len[axis] (host, n_axis floats each): 1/primal edge length; inv_dual: 1/dual
+ * edge length.  For z both arrays are local to the slab and carry nz+2 entries with
+ * entry 0 describing plane -1. */
+int b200fdtd_set_nf2ff(b200fdtd_ctx* ctx, int nfaces, const b200fdtd_nf2ff_face* faces /*host*/,
+                       int nfreq, const double* freqs /*host*/, int interval, double dt,
+                       const float* inv_len_x, const float* inv_len_y, const float* inv_len_z,
+                       const float* inv_dual_x, const float* inv_dual_y, const float* inv_dual_z);
+
+/* ---- time stepping (FDTD.Run, …microstrip_3d.py:214) ---------------------------- */
+/* current time-step counter (number of completed steps) */
+int b200fdtd_get_timestep(b200fdtd_ctx* ctx, int64_t* ts);
+int b200fdtd_set_timestep(b200fdtd_ctx* ctx, int64_t ts);
+/* run n full steps (pre/post extensions, E update, excitation, H update, sampling).
+ * use_graph != 0 replays a captured CUDA graph of one sampling interval. */
+int b200fdtd_run(b200fdtd_ctx* ctx, int64_t nsteps, int use_graph);
+/* split phases for z-slab halo exchange (host drives the exchange between them):
+ *   phase 0: everything up to and including Apply2Voltages (E half step)
+ *   phase 1: current half step and sampling; increments the step counter */
+int b200fdtd_half_step(b200fdtd_ctx* ctx, int phase);
+/* only the volume kernels (bench / roofline): which = 0 E update, 1 H update */
+int b200fdtd_update_only(b200fdtd_ctx* ctx, int which);
+/* openEMS CalcFastEnergy: 0.5*eps0*sum(volt^2) + 0.5*mu0*sum(curr^2) over owned planes
+ * (synchronises the stream) */
+int b200fdtd_energy(b200fdtd_ctx* ctx, double* energy);
+/* wait for the context's stream */
+int b200fdtd_sync(b200fdtd_ctx* ctx);
+/* number of probe samples taken so far */
+int b200fdtd_num_samples(b200fdtd_ctx* ctx, int* n);
+
+/* ---- far field (nf2ff.CalcNF2FF radiation integral, …microstrip_3d.py:225) ------ */
+/* npts surface points with equivalent currents (dev, f32 SoA arrays of npts):
+ *   pos[3][npts], J[3][npts][2], M[3][npts][2] (already multiplied by dA).
+ * For each of ndir directions (theta,phi host arrays, radians) computes
+ *   N = sum J e^{+j k r^.r'},  L = sum M e^{+j k r^.r'}  projected on theta^,phi^
+ * out: dev [ndir][4][2] f32 = (N_theta, N_phi, L_theta, L_phi). */
+int b200fdtd_farfield(int device, void* stream, int64_t npts, const float* pos, const float* J,
+                      const float* M, double k, int ndir, const double* theta, const double* phi,
+                      float* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200FDTD_H */

@@ -1,0 +1,116 @@
+"""CUDA engine vs CPU oracle on identical seeded engine-level inputs (through the C-ABI).
+
+Bar: volt/curr bit-exact (fp32, same operation order); probe series and DFT accumulators within
+the stated tolerance of the oracle's double-precision accumulators.
+"""
+import numpy as np
+import pytest
+
+import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _engines(P):
+    from oracle.fdtd_ref import RefEngine
+    from b200fdtd.engine import Engine
+    R = RefEngine(P["nx"], P["ny"], P["nz"], P["px"])
+    G = Engine(P["nx"], P["ny"], P["nz"], P["px"])
+    synth.apply(R, P, True)
+    synth.apply(G, P, False)
+    return R, G
+
+
+def _assert_fields_equal(R, G, what=""):
+    gv, gc = G.volt.cpu().numpy(), G.curr.cpu().numpy()
+    nz = R.nz
+    # owned planes must agree bit for bit; ghost planes must be untouched
+    assert np.array_equal(gv[:, 1:nz + 1].view(np.uint32), R.volt[:, 1:nz + 1].view(np.uint32)), "volt differs " + what
+    assert np.array_equal(gc[:, 1:nz + 1].view(np.uint32), R.curr[:, 1:nz + 1].view(np.uint32)), "curr differs " + what
+    assert np.array_equal(gv[:, [0, nz + 1]], R.volt[:, [0, nz + 1]])
+    assert np.array_equal(gc[:, [0, nz + 1]], R.curr[:, [0, nz + 1]])
+
+
+@pytest.mark.parametrize("shape", [(37, 29, 23, 40), (128, 16, 9, 128), (130, 9, 5, 160), (5, 4, 3, 8), (257, 33, 17, 288)])
+@pytest.mark.parametrize("tune", [(16, 4), (1, 8), (5, 2), (64, 1), (3, 16)])
+def test_volume_kernels_bit_exact(shape, tune):
+    nx, ny, nz, px = shape
+    P = synth.make_problem(nx, ny, nz, px, seed=nx + ny, with_pml=False, with_mur=False, with_exc=False,
+                           with_probes=False, with_nf2ff=False)
+    R, G = _engines(P)
+    G.set_tuning(kz=tune[0], ty=tune[1])
+    for it in range(3):
+        R.update_only(0); G.update_only(0)
+        _assert_fields_equal(R, G, f"after E update {it}")
+        R.update_only(1); G.update_only(1)
+        _assert_fields_equal(R, G, f"after H update {it}")
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_full_step_all_extensions(use_graph):
+    P = synth.make_problem(37, 29, 23, 40, seed=3)
+    R, G = _engines(P)
+    n = 20
+    R.run(n); G.run(n, use_graph=use_graph)
+    _assert_fields_equal(R, G, "after 20 full steps")
+    assert G.ts == R.ts == n
+    ns = n // P["interval"]
+    assert G.num_samples == ns
+    s_g = G.series.cpu().numpy()[:, :ns].astype(np.float64)
+    s_r = R.series[:, :ns]
+    scale = np.abs(s_r).max()
+    assert np.abs(s_g - s_r).max() <= 2e-6 * scale * 300 ** 0.5, "probe series"
+    d_g = G.probe_dft.cpu().numpy().astype(np.float64)
+    assert np.abs(d_g - R.probe_dft).max() <= 1e-5 * np.abs(R.probe_dft).max(), "probe DFT"
+    for fa_g, fa_r in zip(G.face_acc, R.face_acc):
+        a = fa_g.cpu().numpy().astype(np.float64)
+        assert np.abs(a - fa_r).max() <= 1e-5 * np.abs(fa_r).max(), "NF2FF face DFT"
+    e_r, e_g = R.energy(), G.energy()
+    assert abs(e_g - e_r) <= 1e-6 * abs(e_r)
+
+
+def test_half_steps_equal_run():
+    P = synth.make_problem(33, 17, 11, 64, seed=5)
+    R, G = _engines(P)
+    for _ in range(7):
+        G.half_step(0); G.half_step(1)
+    R.run(7)
+    _assert_fields_equal(R, G, "half steps")
+
+
+def test_graph_resume_and_misaligned_chunks():
+    P = synth.make_problem(21, 13, 9, 32, seed=7, interval=4)
+    R, G = _engines(P)
+    for n in (1, 2, 9, 4, 3):          # crosses chunk boundaries at odd offsets
+        G.run(n, use_graph=True); R.run(n)
+        _assert_fields_equal(R, G, f"after +{n}")
+    ns = R.ts // 4
+    assert np.abs(G.series.cpu().numpy()[:, :ns] - R.series[:, :ns]).max() <= 1e-4 * np.abs(R.series).max()
+
+
+def test_farfield_kernel():
+    from oracle import fdtd_ref
+    from b200fdtd.engine import farfield
+    rng = np.random.default_rng(0)
+    n = 5000
+    pos = rng.uniform(-0.1, 0.1, (3, n))
+    J = rng.standard_normal((3, n)) + 1j * rng.standard_normal((3, n))
+    M = rng.standard_normal((3, n)) + 1j * rng.standard_normal((3, n))
+    th = np.deg2rad(np.arange(0, 181, 10.0)); ph = np.deg2rad(np.full_like(th, 35.0))
+    k = 2 * np.pi * 2.45e9 / 299792458.0
+    ref = fdtd_ref.farfield(pos, J, M, k, th, ph)
+    got = farfield(pos, J, M, k, th, ph)
+    for r, g in zip(ref, got):
+        assert np.abs(r - g).max() <= 2e-5 * np.abs(np.concatenate(ref)).max()
+
+
+def test_errors_are_reported_not_fatal():
+    from b200fdtd.engine import Engine
+    from b200fdtd import B200FDTDError
+    with pytest.raises(B200FDTDError):
+        Engine(1, 4, 4, 4)                       # grid too small
+    G = Engine(8, 8, 4, 8)
+    with pytest.raises(B200FDTDError):
+        G.run(1)                                 # coefficients not bound
+    with pytest.raises(B200FDTDError):
+        G.set_excitation([10 ** 12], [1.0], [0], [0.0, 1.0])   # index out of range
