@@ -45,7 +45,9 @@ class Engine:
         self.device = torch.device("cuda", int(device))
         self.shape = (3, self.nz + 2, self.ny, self.px)
         torch.cuda.set_device(self.device)
-        self.stream = stream if stream is not None else torch.cuda.current_stream(self.device)
+        # a dedicated stream (graph capture needs a non-default stream); joined with torch's current
+        # stream before and after every stepping call so tensor reads/writes stay ordered
+        self.stream = stream if stream is not None else torch.cuda.Stream(self.device)
         self.h = C.c_void_p()
         check(self.L.b200fdtd_create(C.byref(self.h), self.device.index, self.nx, self.ny, self.nz, self.px,
                                       C.c_void_p(self.stream.cuda_stream)))
@@ -146,16 +148,31 @@ class Engine:
                                         _ptr(idl[0], c_f), _ptr(idl[1], c_f), _ptr(idl[2], c_f)))
 
     # ---- stepping ----
+    def _pre(self):
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+
+    def _post(self):
+        torch.cuda.current_stream(self.device).wait_stream(self.stream)
+
     def run(self, nsteps, use_graph=True):
+        self._pre()
         check(self.L.b200fdtd_run(self.h, int(nsteps), 1 if use_graph else 0))
+        self._post()
 
     def half_step(self, phase):
+        self._pre()
         check(self.L.b200fdtd_half_step(self.h, int(phase)))
+        self._post()
 
-    def update_only(self, which):
+    def update_only(self, which, join=True):
+        if join:
+            self._pre()
         check(self.L.b200fdtd_update_only(self.h, int(which)))
+        if join:
+            self._post()
 
     def energy(self):
+        self._pre()
         e = C.c_double()
         check(self.L.b200fdtd_energy(self.h, C.byref(e)))
         return e.value

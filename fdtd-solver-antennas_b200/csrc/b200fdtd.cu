@@ -550,8 +550,8 @@ extern "C" int b200fdtd_create(b200fdtd_ctx** out, int device, int nx, int ny, i
     b200fdtd_ctx* c = new b200fdtd_ctx();
     c->device = device; c->nx = nx; c->ny = ny; c->nz = nz; c->px = px;
     c->sz = (long long)ny * px; c->cs = (long long)(nz + 2) * c->sz;
-    if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
-    else { CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+    c->stream = (cudaStream_t)stream;                       // NULL = the default stream (torch's default stream)
+    c->own_stream = false;
     CK(cudaMalloc((void**)&c->d_ts, sizeof(int)));
     CK(cudaMemsetAsync(c->d_ts, 0, sizeof(int), c->stream));
     c->n_partials = 148 * 8;
@@ -869,7 +869,7 @@ extern "C" int b200fdtd_run(b200fdtd_ctx* c, int64_t nsteps, int use_graph)
     if (nsteps < 0) return fail("nsteps < 0");
     if (!c->volt || !c->vv) return fail("fields/coefficients not bound");
     CK(cudaSetDevice(c->device));
-    if (!use_graph) return run_eager(c, nsteps);
+    if (!use_graph || c->stream == nullptr) return run_eager(c, nsteps);   // the NULL stream cannot be captured
     const int iv = sample_interval(c);
     const int chunk = iv > 0 ? iv : 16;
     int64_t left = nsteps;

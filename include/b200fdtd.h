@@ -42,8 +42,9 @@ int b200fdtd_version(void);
 int64_t b200fdtd_launch_count(void);
 
 /* ---- context ------------------------------------------------------------------ */
-/* Engine instance for one z-slab on one GPU.  `stream` is a cudaStream_t (0 = the
- * library creates its own non-blocking stream).  Replaces openEMS::SetupFDTD's engine
+/* Engine instance for one z-slab on one GPU.  `stream` is a cudaStream_t; every kernel and
+ * copy of this context is issued on it (NULL = the default stream, which is also
+ * torch's default stream).  Replaces openEMS::SetupFDTD's engine
  * allocation inside FDTD.Run (…microstrip_3d.py:214). */
 int b200fdtd_create(b200fdtd_ctx** out, int device, int nx, int ny, int nz, int px, void* stream);
 int b200fdtd_destroy(b200fdtd_ctx* ctx);

@@ -35,13 +35,13 @@ for variant in [int(v) for v in args.variant.split(",")]:
             E.set_tuning(kz=kz, ty=ty, variant=variant)
             for which in (0, 1):
                 for _ in range(3):
-                    E.update_only(which)
-                torch.cuda.synchronize()
+                    E.update_only(which, join=False)
+                E._pre(); torch.cuda.synchronize()
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
+                a.record(E.stream)
                 for _ in range(args.iters):
-                    E.update_only(which)
-                b.record()
+                    E.update_only(which, join=False)
+                b.record(E.stream)
                 torch.cuda.synchronize()
                 ms = a.elapsed_time(b) / args.iters
                 gbs = cells * 60 / ms / 1e6
