@@ -1,0 +1,82 @@
+"""Post-processing of a finished run: port spectra (CalcPort) and the NF2FF transform (CalcNF2FF).
+
+Formulas: SURVEY.md App. A5/A6; call sites in the reference:
+  port.CalcPort(sim_path, f); s11 = port.uf_ref / port.uf_inc      antenna_sim/solver_fdtd_openems_microstrip.py:408-413
+  nf2ff.CalcNF2FF(sim_path, f_res, theta, phi, center=…)            antenna_sim/solver_fdtd_openems_microstrip_3d.py:225
+The radiation integral over all directions runs on the GPU (K11, csrc/b200fdtd.cu farfield_kernel).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .constants import C0, Z0
+
+
+def dft_time2freq(t, val, freq):
+    """openEMS utilities.DFT_time2freq, signal_type 'pulse': 2*dt*sum(val*exp(-j 2 pi f t))"""
+    t = np.asarray(t, np.float64); val = np.asarray(val, np.float64); freq = np.atleast_1d(np.asarray(freq, np.float64))
+    if len(t) < 2:
+        return np.zeros(len(freq), np.complex128)
+    out = np.empty(len(freq), np.complex128)
+    for n, f in enumerate(freq):
+        out[n] = np.sum(val * np.exp(-2j * np.pi * f * t))
+    return 2.0 * (t[1] - t[0]) * out
+
+
+def port_spectrum(probe, freq, probe_freqs=None):
+    """spectrum of one probe record (dict from Simulation.collect): device running DFT when `freq` is the
+    registered grid, otherwise a host DFT of the stored time series (any frequency)."""
+    freq = np.atleast_1d(np.asarray(freq, np.float64))
+    if probe.get("dft") is not None and probe_freqs is not None and len(probe_freqs) == len(freq) \
+            and np.allclose(probe_freqs, freq, rtol=1e-12, atol=0.0):
+        dts = probe["t"][1] - probe["t"][0] if len(probe["t"]) > 1 else 0.0
+        return 2.0 * dts * np.asarray(probe["dft"], np.complex128)
+    return dft_time2freq(probe["t"], probe["val"], freq)
+
+
+def surface_currents(nf, fidx, center):
+    """equivalent currents on the Huygens box for frequency index fidx.
+    Returns pos [3][N] (relative to center, m), J [3][N], M [3][N] (already times dA), Prad."""
+    pos, Jl, Ml = [], [], []
+    prad = 0.0
+    for F, acc, (xa, xb, wa, wb) in zip(nf["faces"], nf["acc"], nf["weights"]):
+        n = F["normal"]; a, b = (n + 1) % 3, (n + 2) % 3
+        s = 1.0 if F["side"] == 1 else -1.0
+        Ea, Eb, Ha, Hb = (acc[c, fidx] for c in range(4))           # [nb][na]
+        dA = wb[:, None] * wa[None, :]
+        XA, XB = np.meshgrid(xa, xb)                                 # [nb][na]
+        P = np.zeros((3,) + dA.shape)
+        P[n] = F["coord"]; P[a] = XA; P[b] = XB
+        J = np.zeros((3,) + dA.shape, np.complex128); M = np.zeros_like(J)
+        J[a] = -s * Hb * dA; J[b] = s * Ha * dA                     # J = n x H
+        M[a] = s * Eb * dA;  M[b] = -s * Ea * dA                    # M = -n x E
+        prad += 0.5 * s * np.sum(np.real(Ea * np.conj(Hb) - Eb * np.conj(Ha)) * dA)
+        pos.append(P.reshape(3, -1)); Jl.append(J.reshape(3, -1)); Ml.append(M.reshape(3, -1))
+    pos = np.concatenate(pos, 1) - np.asarray(center, np.float64).reshape(3, 1)
+    return pos, np.concatenate(Jl, 1), np.concatenate(Ml, 1), float(prad)
+
+
+def far_field(nf, freq, theta_deg, phi_deg, center=(0, 0, 0), radius=1.0, farfield_fn=None, device=0):
+    """E_theta/E_phi on the theta x phi grid (degrees) for one frequency of the box spectra."""
+    freqs = np.asarray(nf["freqs"], np.float64)
+    hit = np.where(np.isclose(freqs, freq, rtol=1e-9, atol=0.0))[0]
+    if len(hit) == 0:
+        raise ValueError(f"NF2FF frequency {freq:g} Hz was not registered for the running DFT "
+                         f"(available: {freqs.tolist()}); pass frequency=[...] to CreateNF2FFBox")
+    fidx = int(hit[0])
+    pos, J, M, prad = surface_currents(nf, fidx, center)
+    th = np.deg2rad(np.atleast_1d(np.asarray(theta_deg, np.float64)))
+    ph = np.deg2rad(np.atleast_1d(np.asarray(phi_deg, np.float64)))
+    TH, PH = np.meshgrid(th, ph, indexing="ij")
+    k = 2.0 * np.pi * float(freq) / C0
+    if farfield_fn is None:
+        from .engine import farfield as farfield_fn     # CUDA kernel K11
+        Nt, Np_, Lt, Lp = farfield_fn(pos, J, M, k, TH.ravel(), PH.ravel(), device=device)
+    else:
+        Nt, Np_, Lt, Lp = farfield_fn(pos, J, M, k, TH.ravel(), PH.ravel())
+    fac = 1j * k * np.exp(-1j * k * radius) / (4.0 * np.pi * radius)
+    E_theta = (-fac * (Lp + Z0 * Nt)).reshape(TH.shape)
+    E_phi = (fac * (Lt - Z0 * Np_)).reshape(TH.shape)
+    P_rad = (np.abs(E_theta) ** 2 + np.abs(E_phi) ** 2) / (2.0 * Z0)
+    Dmax = 4.0 * np.pi * radius ** 2 * P_rad.max() / prad if prad > 0 else float("nan")
+    return dict(E_theta=E_theta, E_phi=E_phi, P_rad=P_rad, Prad=prad, Dmax=Dmax)

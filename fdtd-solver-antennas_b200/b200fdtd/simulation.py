@@ -1,0 +1,324 @@
+"""Simulation: what `FDTD.Run` does (antenna_sim/solver_fdtd_openems_microstrip_3d.py:214).
+
+Builds the operator for this rank's z-slab, loads it into the CUDA engine, runs the time loop
+(end criterion on the energy estimate, App. A7; progress lines the GUI recognises,
+gui_app.py:493-495) and collects probe series / DFTs and the NF2FF face spectra.
+
+Multi-GPU: one process per GPU (torch.distributed); the grid is cut into z-slabs, each half
+step is followed by a one-plane halo exchange with the z-neighbours.
+"""
+from __future__ import annotations
+
+import math
+import time
+
+import numpy as np
+import torch
+
+from .constants import C0
+from .operator import OperatorBuilder, Setup, gauss_signal, BC_MUR, BC_PML  # noqa: F401
+
+
+def _np(t):
+    return t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
+
+
+def _round_up(n, m):
+    return (n + m - 1) // m * m
+
+
+def slab_ranges(nz, world):
+    """contiguous, balanced z-slabs of node planes: [(K0, K1)] * world"""
+    base, rem = divmod(nz, world)
+    out, k = [], 0
+    for r in range(world):
+        n = base + (1 if r < rem else 0)
+        out.append((k, k + n))
+        k += n
+    return out
+
+
+def _default_engine_factory(nx, ny, nz, px, device):
+    from .engine import Engine
+    return Engine(nx, ny, nz, px=px, device=device)
+
+
+class Simulation:
+    def __init__(self, setup: Setup, device=0, rank=0, world=1, group=None, engine_factory=None,
+                 build_device=None, px_align=32, log=None, nf2ff_freqs=None, probe_freqs=None):
+        self.setup = setup
+        self.rank, self.world, self.group = int(rank), int(world), group
+        self.device = device
+        self.log = log or (lambda *a: None)
+        self.engine_factory = engine_factory or _default_engine_factory
+        if build_device is None:
+            build_device = torch.device("cuda", device) if torch.cuda.is_available() else torch.device("cpu")
+        self.build_device = build_device
+        self.px_align = px_align
+        self.nf2ff_freqs = None if nf2ff_freqs is None else np.atleast_1d(np.asarray(nf2ff_freqs, np.float64))
+        self.probe_freqs = None if probe_freqs is None else np.atleast_1d(np.asarray(probe_freqs, np.float64))
+        self.engine = None
+        self.results = None
+
+    # ------------------------------------------------------------------ set-up
+    def prepare(self):
+        s = self.setup
+        t0 = time.time()
+        nz_glob = len(s.lines[2])
+        self.slabs = slab_ranges(nz_glob, self.world)
+        if min(b - a for a, b in self.slabs) < 2:
+            raise ValueError(f"{nz_glob} z-planes are too few for {self.world} slabs")
+        self.K0, self.K1 = self.slabs[self.rank]
+        B = self.builder = OperatorBuilder(s, device=self.build_device, k_nodes=(self.K0, self.K1))
+        nx, ny, nz = B.n
+        self.nx, self.ny, self.nz_glob = nx, ny, nz
+        self.nz = self.K1 - self.K0
+        self.px = _round_up(nx, self.px_align)
+        dt = B.estimate_timestep() * s.timestep_factor
+        if self.world > 1:
+            t = torch.tensor([dt], dtype=torch.float64)
+            if torch.distributed.get_backend(self.group) == "nccl":
+                t = t.cuda(self.device)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MIN, group=self.group)
+            dt = float(t.item())
+        self.dt = dt
+        self.signal, self.exc_len = gauss_signal(s.f0, s.fc, dt, s.nrts) if s.f0 > 0 else (np.zeros(1, np.float32), 0)
+        self.nyquist = B.nyquist(dt)
+        self.interval = max(1, self.nyquist // max(1, s.oversampling))
+        E = self.engine = self.engine_factory(nx, ny, self.nz, self.px, self.device)
+        vv, vi, ii, iv = B.coefficients(self.K0, self.K1, self.px, dt)
+        E.set_coeffs(vv, vi, ii, iv)
+        del vv, vi, ii, iv
+        lin = lambda c, k, j, i: ((c * (self.nz + 2) + (k - self.K0 + 1)) * ny + j) * self.px + i   # noqa: E731
+        own = lambda k: (k >= self.K0) & (k < self.K1)                                                  # noqa: E731
+        # excitation
+        comp, i, j, k, amp, delay = B.excitation_list(dt)
+        sel = own(k)
+        self.n_exc = int(sel.sum())
+        if self.n_exc:
+            E.set_excitation(lin(comp[sel], k[sel], j[sel], i[sel]), amp[sel], delay[sel], self.signal)
+        # Mur
+        mur = B.mur_list(dt)
+        self.n_mur = 0
+        if mur is not None:
+            comp, dst, src, coeff = mur
+            sel = own(dst[2])
+            self.n_mur = int(sel.sum())
+            if self.n_mur:
+                # the inward neighbour of a z-face edge lives in the same slab (checked by the builder)
+                E.set_mur(lin(comp[sel], dst[2][sel], dst[1][sel], dst[0][sel]),
+                          lin(comp[sel], src[2][sel], src[1][sel], src[0][sel]), coeff[sel])
+        # PML
+        boxes = []
+        self.pml_cells = 0
+        for (ri, rj, rk) in B.pml_boxes():
+            k0, k1 = max(rk[0], self.K0), min(rk[1], self.K1)
+            if k1 <= k0:
+                continue
+            co = B.pml_coefficients((ri, rj, (k0, k1)), dt)
+            box = dict(x0=ri[0], y0=rj[0], z0=k0 - self.K0, bx=ri[1] - ri[0], by=rj[1] - rj[0], bz=k1 - k0)
+            box.update(co)
+            self.pml_cells += box["bx"] * box["by"] * box["bz"]
+            boxes.append(box)
+        if boxes:
+            E.set_pml(boxes)
+        # probes
+        self.max_samples = s.nrts // self.interval + 2
+        self.probe_names, kinds, offs, idxs, ws = [], [], [0], [], []
+        for (name, kind, comp, i, j, k, w) in B.probe_lists():
+            sel = own(k)
+            self.probe_names.append(name); kinds.append(kind)
+            idxs.append(lin(comp[sel], k[sel], j[sel], i[sel])); ws.append(w[sel])
+            offs.append(offs[-1] + int(sel.sum()))
+        if self.probe_freqs is None:
+            self.probe_freqs = s.probe_freqs if s.probe_freqs is not None else np.zeros(0)
+        if kinds:
+            E.set_probes(kinds, offs, np.concatenate(idxs) if idxs else np.zeros(0, np.int64),
+                         np.concatenate(ws) if ws else np.zeros(0), self.interval, self.max_samples, self.probe_freqs, dt)
+        # NF2FF
+        self.faces = B.nf2ff_faces()
+        self.local_faces = []
+        if self.faces:
+            if self.nf2ff_freqs is None:
+                fr = s.nf2ff.get("frequency") if s.nf2ff else None
+                self.nf2ff_freqs = np.atleast_1d(np.asarray(fr if fr is not None else [s.f0], np.float64))
+            loc = []
+            for fi, F in enumerate(self.faces):
+                n = F["normal"]; a, b = (n + 1) % 3, (n + 2) % 3
+                L = dict(normal=n, plane=F["plane"], a0=F["a0"], a1=F["a1"], b0=F["b0"], b1=F["b1"])
+                if n == 2:
+                    if not own(np.array(F["plane"])):
+                        continue
+                    L["plane"] = F["plane"] - self.K0
+                else:
+                    key0, key1 = ("a0", "a1") if a == 2 else ("b0", "b1")
+                    z0, z1 = max(F[key0], self.K0), min(F[key1], self.K1 - 1)
+                    if z1 < z0:
+                        continue
+                    L[key0], L[key1] = z0 - self.K0, z1 - self.K0
+                    L["z_off"] = z0 - F[key0]
+                L["face"] = fi
+                loc.append(L)
+            self.local_faces = loc
+            if loc:
+                il = [1.0 / B.len_p[0], 1.0 / B.len_p[1], self._z_slice(1.0 / B.len_p[2])]
+                idl = [1.0 / B.len_d[0], 1.0 / B.len_d[1], self._z_slice(1.0 / B.len_d[2])]
+                E.set_nf2ff(loc, self.nf2ff_freqs, self.interval, dt, il, idl)
+        self.prepare_s = time.time() - t0
+        self.cells = nx * ny * nz
+        return self
+
+    def _z_slice(self, arr):
+        """global per-line array -> local array with nz+2 entries (entry 0 = plane K0-1)"""
+        out = np.ones(self.nz + 2)
+        lo, hi = self.K0 - 1, self.K1 + 1
+        a, b = max(lo, 0), min(hi, len(arr))
+        out[a - lo:b - lo] = arr[a:b]
+        return out
+
+    # ------------------------------------------------------------------ halo exchange (z-slabs)
+    def _exchange(self, field, comps, direction, all_comps=False):
+        """direction +1: my top owned plane -> upper neighbour's lower ghost; -1: my bottom plane -> lower neighbour's upper ghost"""
+        dist = torch.distributed
+        E = self.engine
+        f = E.curr if field == 1 else E.volt
+        ops, bufs = [], []
+        up, dn = self.rank + 1, self.rank - 1
+        cs = slice(0, 3) if all_comps else slice(0, 2)
+        if direction > 0:
+            if up < self.world:
+                send = f[cs, self.nz].contiguous(); bufs.append(send)
+                ops.append(dist.P2POp(dist.isend, send, up, self.group))
+            if dn >= 0:
+                recv = torch.empty_like(f[cs, 0]); bufs.append(recv)
+                ops.append(dist.P2POp(dist.irecv, recv, dn, self.group))
+        else:
+            if dn >= 0:
+                send = f[cs, 1].contiguous(); bufs.append(send)
+                ops.append(dist.P2POp(dist.isend, send, dn, self.group))
+            if up < self.world:
+                recv = torch.empty_like(f[cs, self.nz + 1]); bufs.append(recv)
+                ops.append(dist.P2POp(dist.irecv, recv, up, self.group))
+        if not ops:
+            return
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+        if direction > 0 and dn >= 0:
+            f[cs, 0].copy_(recv)
+        if direction < 0 and up < self.world:
+            f[cs, self.nz + 1].copy_(recv)
+
+    def _step_multi(self, n):
+        E = self.engine
+        for _ in range(n):
+            E.half_step(0)
+            self._exchange(0, None, -1)              # E bottom plane -> lower neighbour (read by its H update)
+            ts_next = E.ts + 1
+            if self.local_faces is not None and self.faces and (ts_next % self.interval) == 0:
+                self._exchange(0, None, +1, all_comps=True)   # E top plane -> upper neighbour's lower ghost (NF2FF node interpolation)
+            E.half_step(1)
+            self._exchange(1, None, +1)              # H top plane -> upper neighbour (read by its E update)
+            E.half_step(2)                           # sampling, after the halo
+
+    # ------------------------------------------------------------------ time loop
+    def energy(self):
+        e = self.engine.energy()
+        if self.world > 1:
+            t = torch.tensor([e], dtype=torch.float64)
+            if torch.distributed.get_backend(self.group) == "nccl":
+                t = t.cuda(self.device)
+            torch.distributed.all_reduce(t, group=self.group)
+            e = float(t.item())
+        return e
+
+    def run(self, nrts=None, end_criteria=None, verbose=0, check_every=None, use_graph=True):
+        s = self.setup
+        nrts = int(s.nrts if nrts is None else nrts)
+        end_criteria = float(s.end_criteria if end_criteria is None else end_criteria)
+        E = self.engine
+        if check_every is None:
+            # a multiple of the sampling interval close to ~1% of the run
+            check_every = self.interval * max(1, int(round(max(50, nrts / 100) / self.interval)))
+        e_max, e_now = 0.0, 0.0
+        t0 = time.time(); t_last = t0; ts_last = 0
+        stop_reason = "NrTS"
+        while E.ts < nrts:
+            n = min(check_every, nrts - E.ts)
+            if self.world > 1:
+                self._step_multi(n)
+            else:
+                E.run(n, use_graph=use_graph)
+            e_now = self.energy()
+            if not math.isfinite(e_now):
+                raise FloatingPointError(f"field energy is not finite at timestep {E.ts} (unstable time step?)")
+            e_max = max(e_max, e_now)
+            now = time.time()
+            if verbose and self.rank == 0:
+                speed = self.cells * (E.ts - ts_last) / max(now - t_last, 1e-9) / 1e6
+                db = 10.0 * math.log10(e_now / e_max) if e_now > 0 and e_max > 0 else -200.0
+                self.log(f"[@ {now - t0:8.2f}s] Timestep: {E.ts:>8d} || Speed: {speed:8.1f} MC/s "
+                         f"({(now - t_last) / max(E.ts - ts_last, 1):.3e}s/TS) || Energy: ~{e_now:.2e} ({db:6.2f}dB)")
+            t_last, ts_last = now, E.ts
+            if e_max > 0 and e_now / e_max < end_criteria and E.ts > self.exc_len:
+                stop_reason = "EndCriteria"
+                break
+        self.wall_s = time.time() - t0
+        self.stop_reason = stop_reason
+        self.timesteps = E.ts
+        self.collect()
+        return self
+
+    # ------------------------------------------------------------------ results
+    def collect(self):
+        """bring the (small) results to the host; sums partial probe values over the slabs"""
+        E = self.engine
+        ns = E.num_samples if hasattr(E, "num_samples") else E.ts // self.interval
+        if not isinstance(ns, int):
+            ns = int(ns)
+        ns = min(ns, E.ts // self.interval)
+        res = {"dt": self.dt, "interval": self.interval, "timesteps": E.ts, "n_samples": ns, "probes": {}}
+        if self.probe_names:
+            series = _np(E.series)[:, :ns].astype(np.float64)
+            dft = _np(E.probe_dft).astype(np.float64)
+            if self.world > 1:
+                series = self._allreduce_np(series); dft = self._allreduce_np(dft)
+            k_list = [pl[1] for pl in self.builder.probe_lists()]
+            for p, name in enumerate(self.probe_names):
+                kind = k_list[p]
+                t = (np.arange(1, ns + 1) * self.interval + (0.5 if kind == 1 else 0.0)) * self.dt
+                res["probes"][name] = dict(kind=kind, t=t, val=series[p],
+                                           dft=(dft[p, :, 0] + 1j * dft[p, :, 1]) if len(self.probe_freqs) else None)
+            res["probe_freqs"] = self.probe_freqs
+        if self.faces:
+            nf = len(self.nf2ff_freqs)
+            full = []
+            for F in self.faces:
+                na, nb = F["a1"] - F["a0"] + 1, F["b1"] - F["b0"] + 1
+                full.append(np.zeros((4, nf, nb, na), np.complex128))
+            for q, L in enumerate(self.local_faces):
+                acc = _np(E.face_acc[q]).astype(np.float64)
+                acc = acc[..., 0] + 1j * acc[..., 1]
+                F = self.faces[L["face"]]
+                n = F["normal"]; a = (n + 1) % 3
+                if n == 2:
+                    full[L["face"]][...] = acc
+                elif a == 2:      # a-axis is z
+                    o = L["z_off"]; full[L["face"]][:, :, :, o:o + acc.shape[3]] = acc
+                else:             # b-axis is z
+                    o = L["z_off"]; full[L["face"]][:, :, o:o + acc.shape[2], :] = acc
+            if self.world > 1:
+                full = [self._allreduce_np(np.stack([f.real, f.imag], -1)) for f in full]
+                full = [f[..., 0] + 1j * f[..., 1] for f in full]
+            scale = 2.0 * self.interval * self.dt          # single-sided pulse spectrum, like DFT_time2freq (App. A5/A6)
+            full = [f * scale for f in full]
+            res["nf2ff"] = dict(faces=self.faces, acc=full, freqs=self.nf2ff_freqs,
+                                weights=[self.builder.face_weights(F) for F in self.faces])
+        self.results = res
+        return res
+
+    def _allreduce_np(self, a):
+        t = torch.from_numpy(np.ascontiguousarray(a, np.float64))
+        if torch.distributed.get_backend(self.group) == "nccl":
+            t = t.cuda(self.device)
+        torch.distributed.all_reduce(t, group=self.group)
+        return t.cpu().numpy()

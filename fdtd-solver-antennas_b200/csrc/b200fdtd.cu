@@ -902,11 +902,14 @@ extern "C" int b200fdtd_half_step(b200fdtd_ctx* c, int phase)
         if (h_half(c)) return 1;
         if (launch_ts_add(c, 1)) return 1;
         c->ts += 1;
+        return 0;
+    }
+    if (phase == 2) {
         const int iv = sample_interval(c);
         if (iv > 0 && (c->ts % iv) == 0) return launch_sampling(c, 0);
         return 0;
     }
-    return fail("phase must be 0 or 1");
+    return fail("phase must be 0, 1 or 2");
 }
 
 extern "C" int b200fdtd_update_only(b200fdtd_ctx* c, int which)

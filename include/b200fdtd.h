@@ -124,7 +124,9 @@ int b200fdtd_set_timestep(b200fdtd_ctx* ctx, int64_t ts);
 int b200fdtd_run(b200fdtd_ctx* ctx, int64_t nsteps, int use_graph);
 /* split phases for z-slab halo exchange (host drives the exchange between them):
  *   phase 0: everything up to and including Apply2Voltages (E half step)
- *   phase 1: current half step and sampling; increments the step counter */
+ *   phase 1: current half step; increments the step counter
+ *   phase 2: probe / NF2FF sampling if the new step count is a multiple of the interval
+ *            (after the H halo so slab-boundary nodes see their neighbour's new values) */
 int b200fdtd_half_step(b200fdtd_ctx* ctx, int phase);
 /* only the volume kernels (bench / roofline): which = 0 E update, 1 H update */
 int b200fdtd_update_only(b200fdtd_ctx* ctx, int which);

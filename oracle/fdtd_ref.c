@@ -285,14 +285,15 @@ void ref_step(ref_engine* e)
 
 void ref_run(ref_engine* e, int64_t nsteps) { for (int64_t s = 0; s < nsteps; ++s) ref_step(e); }
 
-/* split phases (z-slab halo tests): phase 0 = E half step, 1 = H half step + sampling */
+/* split phases (z-slab halo tests): phase 0 = E half step, 1 = H half step, 2 = sampling if due */
 void ref_half_step(ref_engine* e, int phase)
 {
     if (phase == 0) {
         ref_pml(e, 0, 0); ref_mur(e, 0); ref_update_e(e); ref_pml(e, 0, 1); ref_mur(e, 1); ref_excite(e); ref_mur(e, 2);
-    } else {
+    } else if (phase == 1) {
         ref_pml(e, 1, 0); ref_update_h(e); ref_pml(e, 1, 1);
         e->ts += 1;
+    } else {
         if (e->interval > 0 && (e->ts % e->interval) == 0) {
             if (e->n_probes > 0) ref_probes(e);
             if (e->n_faces > 0) ref_nf2ff(e);

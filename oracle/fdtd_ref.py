@@ -105,6 +105,7 @@ class RefEngine:
         self.ii = np.zeros(shape, np.float32)
         self.iv = np.zeros(shape, np.float32)
         self._keep = {}
+        self.series = np.zeros((0, 0)); self.probe_dft = np.zeros((0, 0, 2)); self.face_acc = []
         self.e = _Engine()
         self.e.nx, self.e.ny, self.e.nz, self.e.px = self.nx, self.ny, self.nz, self.px
         self.e.threads = int(threads)
@@ -195,8 +196,15 @@ class RefEngine:
         e.interval = int(interval); e.dt = float(dt)
 
     # --- stepping ---
-    def run(self, nsteps):
+    def run(self, nsteps, use_graph=False):
         lib().ref_run(C.byref(self.e), int(nsteps))
+
+    @property
+    def num_samples(self):
+        return int(self.e.ts // self.e.interval) if self.e.interval > 0 else 0
+
+    def sync(self):
+        pass
 
     def half_step(self, phase):
         lib().ref_half_step(C.byref(self.e), int(phase))

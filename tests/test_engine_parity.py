@@ -73,7 +73,7 @@ def test_half_steps_equal_run():
     P = synth.make_problem(33, 17, 11, 64, seed=5)
     R, G = _engines(P)
     for _ in range(7):
-        G.half_step(0); G.half_step(1)
+        G.half_step(0); G.half_step(1); G.half_step(2)
     R.run(7)
     _assert_fields_equal(R, G, "half steps")
 

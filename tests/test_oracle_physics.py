@@ -1,0 +1,92 @@
+"""Analytic known-answer tests that validate the ORACLE chain (operator build + C engine + post-processing).
+
+The reference pins no numbers for this path (parity unpinned), so the oracle is validated
+physically: cavity resonances, absorber quality, dipole pattern/directivity and power balance.
+Everything here runs on the CPU with the oracle engine injected into the shim's Run.
+"""
+import numpy as np
+import pytest
+
+import scenes
+from b200fdtd.constants import C0
+from b200fdtd.postproc import dft_time2freq
+
+
+@pytest.fixture(autouse=True)
+def _oracle():
+    scenes.use_oracle_engine(threads=4)
+    yield
+    scenes.use_cuda_engine()
+
+
+def _peak_freqs(t, v, f, halfwidth=40):
+    """spectral peaks of a ringing (lossless) record: Hann window against sinc side lobes, then dominant local maxima"""
+    w = np.hanning(len(v))
+    s = np.abs(dft_time2freq(t, v * w, f))
+    pk = [i for i in range(halfwidth, len(f) - halfwidth)
+          if s[i] == s[i - halfwidth:i + halfwidth + 1].max() and s[i] > 0.05 * s.max()]
+    return f[pk], s[pk]
+
+
+@pytest.mark.parametrize("eps_r", [1.0, 4.0])
+def test_pec_cavity_resonances(eps_r):
+    a, b, c = 0.05, 0.04, 0.03
+    F = scenes.cavity(a, b, c, eps_r=eps_r, nrts=6000, f0=5e9 / np.sqrt(eps_r), fc=3e9 / np.sqrt(eps_r))
+    F.Run(scenes.tmp_sim_path("cav"), cleanup=True)
+    pr = F.results["probes"]["ut_cav"]
+    f = np.linspace(3e9, 9e9, 3001) / np.sqrt(eps_r)
+    fp, sp = _peak_freqs(pr["t"], pr["val"], f)
+    # modes with an Ez component: TM_mn0 (m,n>=1) and any mode with p>=1 and m,n>=1
+    def fm(m, n, p):
+        return C0 / (2 * np.sqrt(eps_r)) * np.sqrt((m / a) ** 2 + (n / b) ** 2 + (p / c) ** 2)
+    expected = sorted(fm(m, n, p) for m in range(1, 4) for n in range(1, 4) for p in range(0, 3))
+    assert len(fp) >= 3
+    for fpk in fp[:4]:
+        rel = min(abs(fpk - fe) / fe for fe in expected)
+        assert rel < 6e-3, f"peak {fpk / 1e9:.4f} GHz matches no cavity mode (rel {rel:.4f})"
+    # the lowest mode must be TM110
+    assert abs(fp[0] - fm(1, 1, 0)) / fm(1, 1, 0) < 4e-3
+
+
+@pytest.mark.parametrize("boundary,limit_db", [("PML_8", -60.0), ("MUR", -25.0)])
+def test_absorbing_boundaries_drain_the_box(boundary, limit_db):
+    F, nf, port = scenes.dipole(boundary, cells=(32, 32, 36), nrts=2500, end=10 ** (limit_db / 10.0))
+    F.Run(scenes.tmp_sim_path("abc"), cleanup=True)
+    assert F.results["stop_reason"] == "EndCriteria", f"{boundary}: energy did not fall below {limit_db} dB"
+
+
+def test_dipole_pattern_directivity_and_power_balance():
+    f0 = 3e9
+    F, nf, port = scenes.dipole("PML_8", cells=(40, 40, 48), f0=f0, fc=1.5e9, nrts=3000, end=1e-6)
+    path = scenes.tmp_sim_path("dip")
+    F.Run(path, cleanup=True)
+    theta = np.arange(0.0, 181.0, 5.0)
+    res = nf.CalcNF2FF(path, f0, theta, np.array([0.0, 90.0]))
+    e = res.E_norm[0]
+    # short dipole: |E| ~ sin(theta), no E_phi, omnidirectional in phi, D = 1.5 (1.64 for a half-wave one)
+    pat = e[:, 0] / e[:, 0].max()
+    assert np.abs(pat - np.sin(np.deg2rad(theta))).max() < 0.04
+    assert np.abs(res.E_phi[0]).max() < 1e-2 * np.abs(res.E_theta[0]).max()
+    assert np.abs(e[:, 0] - e[:, 1]).max() < 1e-2 * e.max()
+    assert 1.45 < res.Dmax[0] < 1.62, f"Dmax {res.Dmax[0]}"
+    # power balance of a lossless antenna: accepted port power == radiated power through the Huygens box
+    port.CalcPort(path, np.array([f0]))
+    assert port.P_acc[0] > 0
+    assert abs(res.Prad[0] - port.P_acc[0]) / port.P_acc[0] < 0.03, (res.Prad[0], port.P_acc[0])
+    # a short dipole is badly matched to 50 ohm
+    s11 = np.abs(port.uf_ref / port.uf_inc)[0]
+    assert 0.9 < s11 < 1.0
+    # incident power of a matched source: |U_inc|^2 / (2 R)
+    assert np.isclose(port.P_inc[0], np.abs(port.uf_inc[0]) ** 2 / (2 * 50.0), rtol=1e-12)
+
+
+def test_running_dft_matches_host_dft_of_the_series():
+    F, nf, port = scenes.dipole("MUR", cells=(24, 24, 28), nrts=1200, end=1e-9)
+    path = scenes.tmp_sim_path("dft")
+    F.Run(path, cleanup=True)
+    res = F.results
+    pf = res["probe_freqs"]
+    for name, pr in res["probes"].items():
+        host = dft_time2freq(pr["t"], pr["val"], pf)
+        dev = 2.0 * (pr["t"][1] - pr["t"][0]) * pr["dft"]
+        assert np.abs(host - dev).max() < 1e-9 * np.abs(host).max()
