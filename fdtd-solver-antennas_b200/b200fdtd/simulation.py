@@ -182,6 +182,8 @@ class Simulation:
         dist = torch.distributed
         E = self.engine
         f = E.curr if field == 1 else E.volt
+        if isinstance(f, np.ndarray):                # host-array engines (CPU test doubles): a view sharing the memory
+            f = torch.from_numpy(f)
         ops, bufs = [], []
         up, dn = self.rank + 1, self.rank - 1
         cs = slice(0, 3) if all_comps else slice(0, 2)

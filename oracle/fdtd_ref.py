@@ -63,7 +63,8 @@ def lib():
     global _LIB
     if _LIB is None:
         so = os.path.join(_HERE, "libfdtd_ref.so")
-        if not os.path.exists(so):
+        src = os.path.join(_HERE, "fdtd_ref.c")
+        if not os.path.exists(so) or (os.path.exists(src) and os.path.getmtime(so) < os.path.getmtime(src)):
             build()
         L = C.CDLL(so)
         for name in ("ref_update_e", "ref_update_h", "ref_excite", "ref_step", "ref_probes", "ref_nf2ff"):

@@ -1,0 +1,69 @@
+"""z-slab decomposition: 2 ranks over gloo on the CPU reproduce the single-slab run.
+
+Uses the oracle engine as the per-rank engine (CPU box has no GPU); the host logic under test — slab ranges,
+per-slab operator build, index remapping, halo exchange order, result reduction — is the product's.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _worker(rank, world, port, boundary, q):
+    sys.path[:0] = [os.path.dirname(HERE), HERE, os.path.join(os.path.dirname(HERE), "fdtd-solver-antennas_b200")]
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import scenes
+        scenes.use_oracle_engine(threads=1)
+        F, nf, prt = scenes.dipole(boundary, cells=(20, 20, 30), nrts=300, end=1e-12)
+        F.Run(scenes.tmp_sim_path(f"slab{rank}"), cleanup=True)
+        res = F.results
+        if rank == 0:
+            q.put(dict(ut=res["probes"]["port_ut_1"]["val"], it=res["probes"]["port_it_1"]["val"],
+                       acc=[a.copy() for a in res["nf2ff"]["acc"]], dt=res["dt"], ts=res["timesteps"]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("boundary", ["PML_8", "MUR"])
+@pytest.mark.parametrize("world", [2, 3])
+def test_slabs_equal_single(boundary, world):
+    import scenes
+    scenes.use_oracle_engine(threads=1)
+    F, nf, prt = scenes.dipole(boundary, cells=(20, 20, 30), nrts=300, end=1e-12)
+    F.Run(scenes.tmp_sim_path("slab_single"), cleanup=True, distributed=False)
+    ref = F.results
+    scenes.use_cuda_engine()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + world
+    procs = [ctx.Process(target=_worker, args=(r, world, port, boundary, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = None
+    for _ in range(600):
+        if not q.empty():
+            got = q.get()
+            break
+        if any(p.exitcode not in (None, 0) for p in procs):
+            break
+        procs[0].join(timeout=0.5)
+    for p in procs:
+        p.join(timeout=60)
+        if p.is_alive():
+            p.kill()
+    assert got is not None and all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    assert got["dt"] == ref["dt"] and got["ts"] == ref["timesteps"]
+    for key, name in (("ut", "port_ut_1"), ("it", "port_it_1")):
+        a, b = got[key], ref["probes"][name]["val"]
+        assert np.abs(a - b).max() <= 1e-12 * np.abs(b).max(), key
+    for a, b in zip(got["acc"], ref["nf2ff"]["acc"]):
+        assert np.abs(a - b).max() <= 1e-12 * max(np.abs(b).max(), 1e-300)

@@ -1,0 +1,69 @@
+"""End-to-end parity, CUDA engine vs CPU oracle, through the drop-in API on identical meshes and excitations.
+
+North-star tolerances (BASELINE.json): S11 within 0.2 dB over band, resonant frequency within 0.1 %, far-field
+gain within 0.1 dBi (fp32).  Both engines consume the same operator, so the fields are in fact bit-identical;
+the outputs differ only by fp32-vs-fp64 accumulation in the probe sums and running DFTs.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import replay
+import scenes
+
+pytestmark = pytest.mark.gpu
+
+S11_TOL_DB = 0.2
+FRES_TOL = 1e-3
+GAIN_TOL_DB = 0.1
+
+
+def _run_both(build, nrts, tag):
+    out = {}
+    for eng in ("oracle", "cuda"):
+        (scenes.use_oracle_engine(threads=os.cpu_count() or 4) if eng == "oracle" else scenes.use_cuda_engine())
+        F, nf, port, theta, phi, center = build()
+        F.SetNumberOfTimeSteps(nrts)
+        path = scenes.tmp_sim_path(f"{tag}_{eng}")
+        F.Run(path, cleanup=True)
+        f0 = F.exc[1]
+        f, s11, zin = replay.s11_db(port, path, f0)
+        dbi, dmax = replay.reference_postprocess(nf, path, f0, theta, phi, center)
+        E = F.sim.engine
+        volt = E.volt.cpu().numpy() if hasattr(E.volt, "cpu") else E.volt.copy()
+        out[eng] = dict(f=f, s11=s11, zin=zin, dbi=dbi, dmax=dmax, ts=F.sim.timesteps, volt=volt, stop=F.sim.stop_reason)
+    scenes.use_cuda_engine()
+    return out
+
+
+def _check(out):
+    o, c = out["oracle"], out["cuda"]
+    assert o["ts"] == c["ts"], "engines stopped at different time steps"
+    assert np.array_equal(o["volt"].view(np.uint32), c["volt"].view(np.uint32)), "final E field is not bit-identical"
+    assert np.abs(o["s11"] - c["s11"]).max() <= S11_TOL_DB, f"S11 differs by {np.abs(o['s11'] - c['s11']).max()} dB"
+    fo, fc = o["f"][np.argmin(o["s11"])], c["f"][np.argmin(c["s11"])]
+    assert abs(fo - fc) <= FRES_TOL * fo
+    assert abs(10 * np.log10(o["dmax"]) - 10 * np.log10(c["dmax"])) <= GAIN_TOL_DB
+    sel = o["dbi"] > o["dbi"].max() - 30.0
+    assert np.abs(o["dbi"][sel] - c["dbi"][sel]).max() <= GAIN_TOL_DB
+    assert np.abs(o["zin"] - c["zin"]).max() <= 1e-3 * np.abs(o["zin"]).max()
+
+
+def test_dipole_pml():
+    def build():
+        F, nf, port = scenes.dipole("PML_8", cells=(40, 40, 48), nrts=3000, end=1e-6)
+        return F, nf, port, np.arange(0.0, 181.0, 5.0), np.arange(0.0, 361.0, 45.0), np.zeros(3)
+    out = _run_both(build, 3000, "dip")
+    _check(out)
+    assert 1.45 < out["cuda"]["dmax"] < 1.62
+
+
+@pytest.mark.parametrize("case,nrts", [("trace_single_mur_q1", 6000), ("trace_single_pml8_q3", 3000), ("trace_multi2_mur_q2", 1200)])
+def test_reference_scenes(case, nrts):
+    """the reference's own scenes (recorded call traces of the unmodified prepare functions), both engines"""
+    def build():
+        R = replay.replay(case)
+        return R["FDTD"], R["nf"], R["FDTD"].ports[0], R["theta"][::5], R["phi"][::9], R["nf_center"]
+    out = _run_both(build, nrts, case)
+    _check(out)

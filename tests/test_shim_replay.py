@@ -1,0 +1,103 @@
+"""The shim accepts the reference's exact call sequences (recorded fixtures) and, where the reference tree is
+present, the UNMODIFIED reference prepare functions themselves."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import refload
+import replay
+
+GOLDEN = replay.GOLDEN
+CASES = ["trace_single_pml8_q3", "trace_single_mur_q1", "trace_single_mur_q2_posy", "trace_multi2_mur_q2"]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_replay_builds_a_valid_scene(case):
+    R = replay.replay(case)
+    F = R["FDTD"]
+    S = F._setup()
+    n = [len(l) for l in S.lines]
+    assert all(m > 20 for m in n)
+    for l in S.lines:
+        d = np.diff(l)
+        assert (d > 0).all()
+    assert len(F.ports) >= 1 and len(F.nf2ff_boxes) == 1
+    assert len(S.lumped) == len(F.ports) and len(S.excitations) == len(F.ports)
+    assert len(S.probes) == 2 * len(F.ports)
+    assert len(S.metals) >= 3
+    # every port coordinate sits exactly on mesh lines (edges2grid / explicit AddLine in the reference)
+    unit = F.GetCSX().GetGrid().GetDeltaUnit()
+    for p in F.ports:
+        for a in range(3):
+            for v in (p.start[a], p.stop[a]):
+                assert np.min(np.abs(S.lines[a] - v * unit)) < 1e-12
+
+
+def test_closed_form_pins_in_the_single_patch_trace():
+    """patch/feed geometry in the recorded calls equals the reference's closed-form design values (App. B)"""
+    cf = json.load(open(os.path.join(GOLDEN, "closed_form.json")))
+    assert abs(cf["patch_length_m"] * 1e3 - 29.138326) < 1e-5
+    assert abs(cf["patch_width_m"] * 1e3 - 37.583886) < 1e-5
+    assert abs(cf["eps_eff"] - 3.992370) < 1e-6
+    assert abs(cf["feed_width_m"] * 1e3 - 3.114396) < 1e-5
+    assert abs(cf["kappa"] - 0.0117218) < 1e-6
+    R = replay.replay("trace_single_pml8_q3")
+    csx = R["FDTD"].GetCSX()
+    patch = csx.GetPropertiesByName("patch")[0].primitives[0]
+    assert np.allclose(patch.stop - patch.start, [cf["patch_width_m"] * 1e3, cf["patch_length_m"] * 1e3, 0.0], rtol=1e-12)
+    feed = csx.GetPropertiesByName("feed_line")[0].primitives[0]
+    assert np.isclose(feed.stop[1] - feed.start[1], cf["feed_width_m"] * 1e3, rtol=1e-12)
+    sub = csx.GetPropertiesByName("substrate")[0]
+    assert np.isclose(sub.props["kappa"], cf["kappa"], rtol=1e-12) and sub.props["epsilon"] == 4.3
+    S = R["FDTD"]._setup()
+    assert S.bc == [3] * 6 and S.pml_cells == [8] * 6 and S.nrts == 30000 and S.end_criteria == 1e-4
+    assert S.f0 == 2.45e9 and S.fc == 1.225e9
+    assert len(R["theta"]) == 91 and len(R["phi"]) == 73
+
+
+@pytest.mark.skipif(not refload.available(), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("boundary,quality", [("PML_8", 3), ("MUR", 1)])
+def test_unmodified_reference_prepare_runs_on_the_shim(boundary, quality):
+    m = refload.load()
+    P = m["models"].PatchAntennaParams.from_user_units(frequency_ghz=2.45, er=4.3, h_mm=1.6, loss_tangent=0.02, metal="copper")
+    prep = m["solver_fdtd_openems_microstrip_3d"].prepare_openems_microstrip_patch_3d(
+        P, dll_dir=refload.DLL_DIR, boundary=boundary, mesh_quality=quality)
+    assert prep.ok, prep.message
+    case = "trace_single_pml8_q3" if boundary == "PML_8" else "trace_single_mur_q1"
+    R = replay.replay(case)
+    Sa, Sb = prep.FDTD._setup(), R["FDTD"]._setup()
+    for la, lb in zip(Sa.lines, Sb.lines):
+        assert np.array_equal(la, lb)
+    assert Sa.bc == Sb.bc and len(Sa.metals) == len(Sb.metals)
+    assert np.array_equal(prep.theta, R["theta"]) and np.array_equal(prep.phi, R["phi"])
+
+
+@pytest.mark.skipif(not refload.available(), reason="reference tree not present (GPU box)")
+def test_unmodified_reference_multi_prepare_runs_on_the_shim():
+    from dataclasses import dataclass
+    m = refload.load()
+    P = m["models"].PatchAntennaParams.from_user_units(frequency_ghz=2.45, er=4.3, h_mm=1.6, loss_tangent=0.02, metal="copper")
+    FD = m["solver_fdtd_openems_microstrip"].FeedDirection
+
+    @dataclass
+    class PI:
+        name: str
+        params: object
+        center_x_m: float = 0.0
+        center_y_m: float = 0.0
+        center_z_m: float = 0.0
+        rot_x_deg: float = 0.0
+        rot_y_deg: float = 0.0
+        rot_z_deg: float = 0.0
+        feed_direction: object = None
+    patches = [PI("P1", P, center_x_m=-0.035, feed_direction=FD.NEG_X), PI("P2", P, center_x_m=0.035, rot_z_deg=90.0, feed_direction=FD.NEG_X)]
+    prep = m["solver_fdtd_openems_microstrip_multi_3d"].prepare_openems_microstrip_multi_3d(
+        patches, dll_dir=refload.DLL_DIR, boundary="MUR", mesh_quality=2, theta_step_deg=5.0, phi_step_deg=15.0)
+    assert prep.ok, prep.message
+    R = replay.replay("trace_multi2_mur_q2")
+    Sa, Sb = prep.FDTD._setup(), R["FDTD"]._setup()
+    for la, lb in zip(Sa.lines, Sb.lines):
+        assert np.array_equal(la, lb)
+    assert len(prep.FDTD.ports) == 2
