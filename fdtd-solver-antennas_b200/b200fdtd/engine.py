@@ -103,7 +103,7 @@ class Engine:
         keep = []
         for b, B in enumerate(boxes):
             shp = (3, int(B["bz"]), int(B["by"]), int(B["bx"]))
-            d = {n: self._dev(np.asarray(B[n], np.float32).reshape(shp)) for n in ("vv", "vvfo", "vvfn", "ii", "iifo", "iifn")}
+            d = {n: self._dev(B[n]).reshape(shp).contiguous() for n in ("vv", "vvfo", "vvfn", "ii", "iifo", "iifn")}
             d["flux_v"] = torch.zeros(shp, dtype=torch.float32, device=self.device)
             d["flux_i"] = torch.zeros(shp, dtype=torch.float32, device=self.device)
             keep.append(d)

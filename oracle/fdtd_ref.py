@@ -86,6 +86,13 @@ def _p(a, t):
     return a.ctypes.data_as(t)
 
 
+def _host(a, dt=np.float32):
+    """numpy view/copy of a numpy array or a (possibly CUDA) torch tensor"""
+    if hasattr(a, "detach"):
+        a = a.detach().cpu().numpy()
+    return np.asarray(a, dt)
+
+
 def lin(nz, ny, px, c, k, j, i):
     """linear index of (component c, local plane k, row j, column i) — include/b200fdtd.h"""
     return ((c * (nz + 2) + (k + 1)) * ny + j) * px + i
@@ -119,7 +126,7 @@ class RefEngine:
 
     def set_coeffs(self, vv, vi, ii, iv):
         for dst, src in ((self.vv, vv), (self.vi, vi), (self.ii, ii), (self.iv, iv)):
-            dst[...] = np.asarray(src, np.float32).reshape(self.shape)
+            dst[...] = _host(src).reshape(self.shape)
 
     def set_excitation(self, idx, amp, delay, signal):
         k = self._keep
@@ -147,7 +154,7 @@ class RefEngine:
         keep = []
         for b, B in enumerate(boxes):
             shp = (3, B["bz"], B["by"], B["bx"])
-            d = {n: np.ascontiguousarray(np.asarray(B[n], np.float32).reshape(shp)) for n in ("vv", "vvfo", "vvfn", "ii", "iifo", "iifn")}
+            d = {n: np.ascontiguousarray(_host(B[n]).reshape(shp)) for n in ("vv", "vvfo", "vvfn", "ii", "iifo", "iifn")}
             d["flux_v"] = np.zeros(shp, np.float32); d["flux_i"] = np.zeros(shp, np.float32)
             keep.append(d)
             for n in ("x0", "y0", "z0", "bx", "by", "bz"):
