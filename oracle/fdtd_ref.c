@@ -144,6 +144,7 @@ void ref_excite(ref_engine* e)
 void ref_mur(ref_engine* e, int phase)
 {
     float* v = e->volt;
+#pragma omp parallel for schedule(static) num_threads(e->threads > 0 ? e->threads : 1)
     for (int64_t n = 0; n < e->n_mur; ++n) {
         if (phase == 0)      e->mur_tmp[n] = fmaf(-e->mur_coeff[n], v[e->mur_dst[n]], v[e->mur_src[n]]);
         else if (phase == 1) e->mur_tmp[n] = fmaf(e->mur_coeff[n], v[e->mur_src[n]], e->mur_tmp[n]);
@@ -163,11 +164,12 @@ void ref_pml(ref_engine* e, int which, int post)
         const float* a = which == 0 ? B->vv : B->ii;
         const float* fo = which == 0 ? B->vvfo : B->iifo;
         const float* fn = which == 0 ? B->vvfn : B->iifn;
-        int64_t l = 0;
+#pragma omp parallel for collapse(2) schedule(static) num_threads(e->threads > 0 ? e->threads : 1)
         for (int c = 0; c < 3; ++c)
             for (int z = 0; z < B->bz; ++z)
                 for (int y = 0; y < B->by; ++y)
-                    for (int x = 0; x < B->bx; ++x, ++l) {
+                    for (int x = 0; x < B->bx; ++x) {
+                        const int64_t l = (((int64_t)c * B->bz + z) * B->by + y) * B->bx + x;
                         const int64_t q = c * cs + (int64_t)(B->z0 + z + 1) * sz + (int64_t)(B->y0 + y) * px + (B->x0 + x);
                         if (!post) {
                             const float fl = flux[l];
