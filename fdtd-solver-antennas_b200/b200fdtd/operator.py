@@ -259,13 +259,15 @@ class OperatorBuilder:
             mid = (self.pml_lo[a] if lo else 0, self.n[a] - 1 - self.pml_hi[a] if hi else self.n[a])
             return lo, hi, mid
         (xl, xh, xm), (yl, yh, ym), (zl, zh, zm) = rng(0), rng(1), rng(2)
+        # z-slabs take whole planes, y-slabs whole x-rows of the remaining planes (both are fused into the volume
+        # kernels, csrc/b200fdtd.cu RowParams); x-slabs are the narrow rest for the separate pre/post kernel
         boxes = []
-        for r in (xl, xh):
-            if r: boxes.append((r, (0, ny), (0, nz)))
-        for r in (yl, yh):
-            if r: boxes.append((xm, r, (0, nz)))
         for r in (zl, zh):
-            if r: boxes.append((xm, ym, r))
+            if r: boxes.append(((0, nx), (0, ny), r))
+        for r in (yl, yh):
+            if r: boxes.append(((0, nx), r, zm))
+        for r in (xl, xh):
+            if r: boxes.append((r, ym, zm))
         return [b for b in boxes if all(q[1] > q[0] for q in b)]
 
     # ------------------------------------------------------------------ EC blocks

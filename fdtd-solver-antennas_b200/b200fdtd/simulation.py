@@ -117,6 +117,12 @@ class Simulation:
                 continue
             co = B.pml_coefficients((ri, rj, (k0, k1)), dt)
             box = dict(x0=ri[0], y0=rj[0], z0=k0 - self.K0, bx=ri[1] - ri[0], by=rj[1] - rj[0], bz=k1 - k0)
+            if ri[0] == 0 and ri[1] == nx and self.px > nx:
+                # whole x-rows: pad to the row pitch so the volume kernels can fuse this slab (RowParams)
+                co = {n: torch.nn.functional.pad(t, (0, self.px - nx)) for n, t in co.items()}
+                box["bx"] = self.px
+            elif ri[0] == 0 and ri[1] == nx:
+                box["bx"] = self.px
             box.update(co)
             self.pml_cells += box["bx"] * box["by"] * box["bz"]
             boxes.append(box)

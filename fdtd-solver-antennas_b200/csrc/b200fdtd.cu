@@ -54,6 +54,15 @@ struct PmlBoxDev {
 #define MAX_PML_BOXES 8
 struct PmlTable { int n; long long total; PmlBoxDev b[MAX_PML_BOXES]; };
 
+// launch plan of the volume kernels: PML boxes spanning whole x-rows are fused into the volume launches
+struct FusedBox { int y0, by, z0, bz; float *flux_v, *flux_i; const float *vv, *vvfo, *vvfn, *ii, *iifo, *iifn; };
+struct VolumePlan {
+    bool valid = false;
+    int nseg = 0; int seg0[3], seg1[3];          // plane ranges of the plain launches (complement of fused z-slabs)
+    int nskip = 0; int sj0[2], sj1[2];           // rows of fused y-slabs
+    int nfused = 0; FusedBox fb[4];
+};
+
 struct FaceDev {
     int normal, plane, a0, a1, b0, b1;
     float* acc;
@@ -67,6 +76,8 @@ struct b200fdtd_ctx {
     long long sz = 0, cs = 0;      // plane stride, component stride (floats)
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t side = nullptr;           // runs the fused PML slab launches concurrently with the plain launch
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     float *volt = nullptr, *curr = nullptr;
     const float *vv = nullptr, *vi = nullptr, *ii = nullptr, *iv = nullptr;
     int kz = 16, ty = 4, variant = 0;
@@ -78,8 +89,10 @@ struct b200fdtd_ctx {
     float* exc_sig = nullptr; int exc_siglen = 0;
     // mur
     int64_t n_mur = 0; int64_t *mur_dst = nullptr, *mur_src = nullptr; float *mur_coeff = nullptr, *mur_tmp = nullptr;
-    // pml
+    // pml: all boxes as given, the boxes left to the separate pre/post passes, and the fused launch plan
+    PmlTable pml_all{};
     PmlTable pml{};
+    VolumePlan plan{};
     // probes
     int n_probes = 0; int* pr_kind = nullptr; int64_t* pr_off = nullptr; int64_t* pr_idx = nullptr; float* pr_w = nullptr;
     int interval = 0; int max_samples = 0; float* pr_series = nullptr; int pr_nfreq = 0; double* pr_freqs = nullptr;
@@ -136,17 +149,57 @@ __device__ __forceinline__ float4 upd4(float4 ca, float4 f, float4 cb, float4 a,
     return r;
 }
 
+// Row selection of one volume launch and, for launches over a fused PML slab, the slab arrays.
+// A PML box that spans whole x-rows (x0 = 0, bx = px) is not swept by the separate pre/post passes: the
+// volume kernel does  pre -> update -> post  on the values it already holds in registers (same arithmetic,
+// same order per cell as the separate passes; App. A4), so volt/curr are read and written once.
+struct RowParams {
+    int j0, j1;                     // rows handled by this launch
+    int sj0a, sj1a, sj0b, sj1b;     // rows that belong to fused y-slabs (skipped by the plain launch; empty ranges if none)
+    float* flux;                    // fused slab arrays [3][bz][by][px] (PML launches only)
+    const float* a; const float* fo; const float* fn;
+    int y0, z0, by, bz;
+};
+
+__device__ __forceinline__ float4 pml_pre4(float4 a, float4 fo, float4 fl, float4 e) {
+    // h = a*e - fo*flux   (the field itself becomes the old flux)
+    float4 h;
+    h.x = __fmaf_rn(a.x, e.x, -__fmul_rn(fo.x, fl.x));
+    h.y = __fmaf_rn(a.y, e.y, -__fmul_rn(fo.y, fl.y));
+    h.z = __fmaf_rn(a.z, e.z, -__fmul_rn(fo.z, fl.z));
+    h.w = __fmaf_rn(a.w, e.w, -__fmul_rn(fo.w, fl.w));
+    return h;
+}
+__device__ __forceinline__ float4 pml_post4(float4 fn, float4 F, float4 h) {
+    return make_float4(__fmaf_rn(fn.x, F.x, h.x), __fmaf_rn(fn.y, F.y, h.y), __fmaf_rn(fn.z, F.z, h.z), __fmaf_rn(fn.w, F.w, h.w));
+}
+
+// one component of a fused PML row: pre, update, post.  f4 holds the field on entry and the new field on exit.
+#define PML_COMP(f4, ca4, cb4, A, B, C, D, lofs)                                              \
+    do {                                                                                      \
+        float4 fl_ = zero4(), a_ = zero4(), fo_ = zero4(), fn_ = zero4();                     \
+        if (act) { fl_ = ld4_stream(r.flux + (lofs)); a_ = ld4_ro(r.a + (lofs));              \
+                   fo_ = ld4_ro(r.fo + (lofs)); fn_ = ld4_ro(r.fn + (lofs)); }                 \
+        const float4 h_ = pml_pre4(a_, fo_, fl_, f4);                                         \
+        const float4 F_ = upd4(ca4, fl_, cb4, A, B, C, D);                                    \
+        if (act) st4(r.flux + (lofs), F_);                                                    \
+        f4 = pml_post4(fn_, F_, h_);                                                          \
+    } while (0)
+
 // E update: volt_n = vv_n volt_n + vi_n curl_n(curr)   (App. A1)
 //   x: ((Hz - Hz[j-1]) - Hy) + Hy[k-1]
 //   y: ((Hx - Hx[k-1]) - Hz) + Hz[i-1]
 //   z: ((Hy - Hy[i-1]) - Hx) + Hx[j-1]
-template <int TY>
-__global__ void __launch_bounds__(32 * TY) update_e_kernel(const VolParams p)
+template <int TY, bool PML>
+__global__ void __launch_bounds__(32 * TY) update_e_kernel(const VolParams p, const RowParams r)
 {
     const int lane = threadIdx.x;
     const int i0 = (blockIdx.x * 32 + lane) * 4;
-    const int j = blockIdx.y * TY + threadIdx.y;
-    if (j >= p.ny) return;                                  // warp-uniform
+    const int j = r.j0 + blockIdx.y * TY + threadIdx.y;
+    if (j >= r.j1) return;                                  // warp-uniform
+    if (!PML) {
+        if ((j >= r.sj0a && j < r.sj1a) || (j >= r.sj0b && j < r.sj1b)) return;
+    }
     const bool act = i0 < p.px;
     const int kbeg = p.k0 + blockIdx.z * p.kz;
     const int kend = min(kbeg + p.kz, p.k1);
@@ -160,8 +213,13 @@ __global__ void __launch_bounds__(32 * TY) update_e_kernel(const VolParams p)
     base += sz;                                             // plane kbeg
     const bool has_jm = j > 0;
     const bool edge_load = act && lane == 0 && i0 > 0;
+    long long lb = 0, lsz = 0, lcs = 0;
+    if (PML) {
+        lsz = (long long)r.by * p.px; lcs = lsz * r.bz;
+        lb = (long long)(kbeg - r.z0) * lsz + (long long)(j - r.y0) * p.px + i0;
+    }
 
-    for (int k = kbeg; k < kend; ++k, base += sz) {
+    for (int k = kbeg; k < kend; ++k, base += sz, lb += lsz) {
         float4 hx = zero4(), hy = zero4(), hz = zero4(), hz_jm = zero4(), hx_jm = zero4();
         float4 ex = zero4(), ey = zero4(), ez = zero4();
         float4 ax = zero4(), ay = zero4(), az = zero4(), bx = zero4(), by = zero4(), bz = zero4();
@@ -180,9 +238,15 @@ __global__ void __launch_bounds__(32 * TY) update_e_kernel(const VolParams p)
         const float4 hz_im = make_float4(hz_l, hz.x, hz.y, hz.z);
         const float4 hy_im = make_float4(hy_l, hy.x, hy.y, hy.z);
 
-        ex = upd4(ax, ex, bx, hz, hz_jm, hy, hy_km);
-        ey = upd4(ay, ey, by, hx, hx_km, hz, hz_im);
-        ez = upd4(az, ez, bz, hy, hy_im, hx, hx_jm);
+        if (PML) {
+            PML_COMP(ex, ax, bx, hz, hz_jm, hy, hy_km, lb);
+            PML_COMP(ey, ay, by, hx, hx_km, hz, hz_im, lcs + lb);
+            PML_COMP(ez, az, bz, hy, hy_im, hx, hx_jm, 2 * lcs + lb);
+        } else {
+            ex = upd4(ax, ex, bx, hz, hz_jm, hy, hy_km);
+            ey = upd4(ay, ey, by, hx, hx_km, hz, hz_im);
+            ez = upd4(az, ez, bz, hy, hy_im, hx, hx_jm);
+        }
         if (act) {
             st4(f + base, ex); st4(f + cs + base, ey); st4(f + 2 * cs + base, ez);
         }
@@ -194,13 +258,16 @@ __global__ void __launch_bounds__(32 * TY) update_e_kernel(const VolParams p)
 //   x: ((Ez - Ez[j+1]) - Ey) + Ey[k+1]
 //   y: ((Ex - Ex[k+1]) - Ez) + Ez[i+1]
 //   z: ((Ey - Ey[i+1]) - Ex) + Ex[j+1]
-template <int TY>
-__global__ void __launch_bounds__(32 * TY) update_h_kernel(const VolParams p)
+template <int TY, bool PML>
+__global__ void __launch_bounds__(32 * TY) update_h_kernel(const VolParams p, const RowParams r)
 {
     const int lane = threadIdx.x;
     const int i0 = (blockIdx.x * 32 + lane) * 4;
-    const int j = blockIdx.y * TY + threadIdx.y;
-    if (j >= p.ny) return;
+    const int j = r.j0 + blockIdx.y * TY + threadIdx.y;
+    if (j >= r.j1) return;
+    if (!PML) {
+        if ((j >= r.sj0a && j < r.sj1a) || (j >= r.sj0b && j < r.sj1b)) return;
+    }
     const bool act = i0 < p.px;
     const int kbeg = p.k0 + blockIdx.z * p.kz;
     const int kend = min(kbeg + p.kz, p.k1);
@@ -215,8 +282,13 @@ __global__ void __launch_bounds__(32 * TY) update_h_kernel(const VolParams p)
     const bool has_jp = j + 1 < p.ny;
     const bool last = act && (lane == 31 || i0 + 4 >= p.px);
     const bool edge_load = last && (i0 + 4 < p.px);
+    long long lb = 0, lsz = 0, lcs = 0;
+    if (PML) {
+        lsz = (long long)r.by * p.px; lcs = lsz * r.bz;
+        lb = (long long)(kend - 1 - r.z0) * lsz + (long long)(j - r.y0) * p.px + i0;
+    }
 
-    for (int k = kend - 1; k >= kbeg; --k, base -= sz) {
+    for (int k = kend - 1; k >= kbeg; --k, base -= sz, lb -= lsz) {
         float4 ex = zero4(), ey = zero4(), ez = zero4(), ez_jp = zero4(), ex_jp = zero4();
         float4 hx = zero4(), hy = zero4(), hz = zero4();
         float4 ax = zero4(), ay = zero4(), az = zero4(), bx = zero4(), by = zero4(), bz = zero4();
@@ -235,9 +307,15 @@ __global__ void __launch_bounds__(32 * TY) update_h_kernel(const VolParams p)
         const float4 ez_ip = make_float4(ez.y, ez.z, ez.w, ez_r);
         const float4 ey_ip = make_float4(ey.y, ey.z, ey.w, ey_r);
 
-        hx = upd4(ax, hx, bx, ez, ez_jp, ey, ey_kp);
-        hy = upd4(ay, hy, by, ex, ex_kp, ez, ez_ip);
-        hz = upd4(az, hz, bz, ey, ey_ip, ex, ex_jp);
+        if (PML) {
+            PML_COMP(hx, ax, bx, ez, ez_jp, ey, ey_kp, lb);
+            PML_COMP(hy, ay, by, ex, ex_kp, ez, ez_ip, lcs + lb);
+            PML_COMP(hz, az, bz, ey, ey_ip, ex, ex_jp, 2 * lcs + lb);
+        } else {
+            hx = upd4(ax, hx, bx, ez, ez_jp, ey, ey_kp);
+            hy = upd4(ay, hy, by, ex, ex_kp, ez, ez_ip);
+            hz = upd4(az, hz, bz, ey, ey_ip, ex, ex_jp);
+        }
         if (act) {
             st4(f + base, hx); st4(f + cs + base, hy); st4(f + 2 * cs + base, hz);
         }
@@ -245,23 +323,23 @@ __global__ void __launch_bounds__(32 * TY) update_h_kernel(const VolParams p)
     }
 }
 
-static int launch_volume(b200fdtd_ctx* c, int which, int k0, int k1)
+template <bool PML>
+static int launch_volume_one(b200fdtd_ctx* c, int which, int k0, int k1, const RowParams& r, cudaStream_t stream, int kz)
 {
-    if (!c->volt || !c->vv) return fail("fields/coefficients not bound");
-    if (k1 <= k0) return 0;
+    if (k1 <= k0 || r.j1 <= r.j0) return 0;
     VolParams p;
     p.f = which == 0 ? c->volt : c->curr;
     p.g = which == 0 ? c->curr : c->volt;
     p.ca = which == 0 ? c->vv : c->ii;
     p.cb = which == 0 ? c->vi : c->iv;
     p.nx = c->nx; p.ny = c->ny; p.nz = c->nz; p.px = c->px; p.sz = c->sz; p.cs = c->cs;
-    p.kz = c->kz; p.k0 = k0; p.k1 = k1;
+    p.kz = kz; p.k0 = k0; p.k1 = k1;
     const int ty = c->ty;
     dim3 block(32, ty);
-    dim3 grid((c->px + 127) / 128, (c->ny + ty - 1) / ty, (k1 - k0 + c->kz - 1) / c->kz);
+    dim3 grid((c->px + 127) / 128, (r.j1 - r.j0 + ty - 1) / ty, (k1 - k0 + kz - 1) / kz);
     if (grid.y > 65535 || grid.z > 65535) return fail("grid too large for launch (ny/ty=%u, nz/kz=%u)", grid.y, grid.z);
-#define LAUNCH(TYV) do { if (which == 0) update_e_kernel<TYV><<<grid, block, 0, c->stream>>>(p); \
-                         else update_h_kernel<TYV><<<grid, block, 0, c->stream>>>(p); } while (0)
+#define LAUNCH(TYV) do { if (which == 0) update_e_kernel<TYV, PML><<<grid, block, 0, stream>>>(p, r); \
+                         else update_h_kernel<TYV, PML><<<grid, block, 0, stream>>>(p, r); } while (0)
     switch (ty) {
         case 1: LAUNCH(1); break;
         case 2: LAUNCH(2); break;
@@ -272,6 +350,117 @@ static int launch_volume(b200fdtd_ctx* c, int which, int k0, int k1)
     }
 #undef LAUNCH
     CKL();
+    return 0;
+}
+
+// Split the PML boxes into fused slabs (whole x-rows; handled inside the volume launches) and boxes for the
+// separate pre/post kernel.  z-slabs (all rows of some planes) and y-slabs (some rows of all remaining planes) qualify.
+static int build_plan(b200fdtd_ctx* c)
+{
+    VolumePlan P;
+    PmlTable rest; memset(&rest, 0, sizeof(rest));
+    const PmlTable& A = c->pml_all;
+    const bool allow = (c->variant & 1) == 0;
+    int kind[MAX_PML_BOXES];                      // 0 separate, 1 z-slab, 2 y-slab candidate
+    int zlo = 0, zhi = c->nz;                     // complement of the fused z-slabs must stay one contiguous range
+    for (int b = 0; b < A.n; ++b) {
+        const PmlBoxDev& B = A.b[b];
+        kind[b] = 0;
+        if (!allow || B.x0 != 0 || B.bx != c->px) continue;
+        if (((uintptr_t)B.flux_v | (uintptr_t)B.flux_i | (uintptr_t)B.vv | (uintptr_t)B.vvfo | (uintptr_t)B.vvfn |
+             (uintptr_t)B.ii | (uintptr_t)B.iifo | (uintptr_t)B.iifn) & 15) continue;
+        if (B.y0 == 0 && B.by == c->ny) {
+            if (B.z0 == 0 && B.bz < c->nz && B.bz > zlo) { kind[b] = 1; }
+            else if (B.z0 + B.bz == c->nz && B.z0 > 0) { kind[b] = 1; }
+            else if (B.z0 == 0 && B.bz == c->nz) { kind[b] = 1; }      // the whole slab is PML
+        } else kind[b] = 2;
+    }
+    for (int b = 0; b < A.n; ++b) if (kind[b] == 1) {
+        const PmlBoxDev& B = A.b[b];
+        if (B.z0 == 0) zlo = zlo > B.bz ? zlo : B.bz;
+        else zhi = zhi < B.z0 ? zhi : B.z0;
+    }
+    if (zhi < zlo) zhi = zlo;
+    for (int b = 0; b < A.n; ++b) if (kind[b] == 2) {
+        const PmlBoxDev& B = A.b[b];
+        if (!(B.z0 == zlo && B.z0 + B.bz == zhi) || P.nskip >= 2) kind[b] = 0;
+        else { P.sj0[P.nskip] = B.y0; P.sj1[P.nskip] = B.y0 + B.by; P.nskip++; }
+    }
+    for (int b = 0; b < A.n; ++b) {
+        const PmlBoxDev& B = A.b[b];
+        if (kind[b] == 0 || P.nfused >= 4) {
+            PmlBoxDev D = B; D.start = rest.total; rest.b[rest.n++] = D; rest.total += 3LL * B.bx * B.by * B.bz;
+        } else {
+            FusedBox& Fb = P.fb[P.nfused++];
+            Fb.y0 = B.y0; Fb.by = B.by; Fb.z0 = B.z0; Fb.bz = B.bz;
+            Fb.flux_v = B.flux_v; Fb.flux_i = B.flux_i; Fb.vv = B.vv; Fb.vvfo = B.vvfo; Fb.vvfn = B.vvfn;
+            Fb.ii = B.ii; Fb.iifo = B.iifo; Fb.iifn = B.iifn;
+        }
+    }
+    P.nseg = 0;
+    if (zhi > zlo) { P.seg0[0] = zlo; P.seg1[0] = zhi; P.nseg = 1; }
+    P.valid = true;
+    c->plan = P;
+    c->pml = rest;
+    return 0;
+}
+
+// plain (non-PML) volume launches of one half step restricted to planes [k0,k1)
+static int launch_volume_plain(b200fdtd_ctx* c, int which, int k0, int k1, cudaStream_t stream)
+{
+    const VolumePlan& P = c->plan;
+    RowParams r; memset(&r, 0, sizeof(r));
+    r.j0 = 0; r.j1 = c->ny;
+    if (P.nskip > 0) { r.sj0a = P.sj0[0]; r.sj1a = P.sj1[0]; }
+    if (P.nskip > 1) { r.sj0b = P.sj0[1]; r.sj1b = P.sj1[1]; }
+    for (int s = 0; s < P.nseg; ++s) {
+        const int a = k0 > P.seg0[s] ? k0 : P.seg0[s], b = k1 < P.seg1[s] ? k1 : P.seg1[s];
+        if (launch_volume_one<false>(c, which, a, b, r, stream, c->kz)) return 1;
+    }
+    return 0;
+}
+
+// volume launches over the fused PML slabs (pre -> update -> post in registers)
+static int launch_volume_fused(b200fdtd_ctx* c, int which, int k0, int k1, cudaStream_t stream)
+{
+    const VolumePlan& P = c->plan;
+    for (int q = 0; q < P.nfused; ++q) {
+        const FusedBox& B = P.fb[q];
+        RowParams f; memset(&f, 0, sizeof(f));
+        f.j0 = B.y0; f.j1 = B.y0 + B.by; f.y0 = B.y0; f.z0 = B.z0; f.by = B.by; f.bz = B.bz;
+        f.flux = which == 0 ? B.flux_v : B.flux_i;
+        f.a = which == 0 ? B.vv : B.ii; f.fo = which == 0 ? B.vvfo : B.iifo; f.fn = which == 0 ? B.vvfn : B.iifn;
+        const int a = k0 > B.z0 ? k0 : B.z0, b = k1 < B.z0 + B.bz ? k1 : B.z0 + B.bz;
+        if (b <= a) continue;
+        // thin slabs: march fewer planes per CTA so the launch still fills the machine (>= ~8 CTAs per SM)
+        const long long per_chunk = (long long)((c->px + 127) / 128) * ((B.by + c->ty - 1) / c->ty);
+        int kz = c->kz;
+        while (kz > 2 && per_chunk * ((b - a + kz - 1) / kz) < 148LL * 8) kz = (kz + 1) / 2;
+        if (launch_volume_one<true>(c, which, a, b, f, stream, kz)) return 1;
+    }
+    return 0;
+}
+
+// all volume launches of one half step restricted to planes [k0,k1), on the main stream
+static int launch_volume(b200fdtd_ctx* c, int which, int k0, int k1)
+{
+    if (!c->volt || !c->vv) return fail("fields/coefficients not bound");
+    if (!c->plan.valid) if (build_plan(c)) return 1;
+    if (launch_volume_plain(c, which, k0, k1, c->stream)) return 1;
+    return launch_volume_fused(c, which, k0, k1, c->stream);
+}
+
+// fork/join of the side stream that runs the fused PML slab launches next to the plain launch
+static int fork_side(b200fdtd_ctx* c)
+{
+    CK(cudaEventRecord(c->ev_fork, c->stream));
+    CK(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+    return 0;
+}
+static int join_side(b200fdtd_ctx* c)
+{
+    CK(cudaEventRecord(c->ev_join, c->side));
+    CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
     return 0;
 }
 
@@ -308,38 +497,35 @@ __global__ void mur_kernel(float* __restrict__ volt, const int64_t* __restrict__
     }
 }
 
-// K4 PML_8 (App. A4): split-flux UPML, pre and post passes over the slab boxes.
+// K4 PML_8 (App. A4): split-flux UPML, pre and post passes over one slab box (the boxes that are not fused
+// into the volume kernels: the narrow x-slabs).  blockIdx = (row chunk, z, component); threadIdx = (x, row).
 //   pre : h = a*f - fo*flux ; f = flux ; flux = h
 //   post: h = flux ; flux = f ; f = h + fn*flux
-__global__ void pml_kernel(float* __restrict__ field, const PmlTable* __restrict__ tab, int which, int post,
-                           int ny, int px, long long sz, long long cs)
+__global__ void pml_kernel(float* __restrict__ field, const PmlBoxDev B, int which, int post,
+                           int px, long long sz, long long cs)
 {
-    const long long n = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (n >= tab->total) return;
-    int b = 0;
-    while (b + 1 < tab->n && n >= tab->b[b + 1].start) ++b;
-    const PmlBoxDev& B = tab->b[b];
-    long long r = n - B.start;
-    const int x = (int)(r % B.bx); r /= B.bx;
-    const int y = (int)(r % B.by); r /= B.by;
-    const int z = (int)(r % B.bz); r /= B.bz;
-    const int comp = (int)r;
-    const long long q = comp * cs + (long long)(B.z0 + z + 1) * sz + (long long)(B.y0 + y) * px + (B.x0 + x);
-    const long long l = n - B.start;
-    float* flux = which == 0 ? B.flux_v : B.flux_i;
-    if (!post) {
-        const float* a = which == 0 ? B.vv : B.ii;
-        const float* fo = which == 0 ? B.vvfo : B.iifo;
-        const float fl = flux[l];
-        const float h = __fmaf_rn(a[l], field[q], -__fmul_rn(fo[l], fl));
-        field[q] = fl;
-        flux[l] = h;
-    } else {
-        const float* fn = which == 0 ? B.vvfn : B.iifn;
-        const float h = flux[l];
-        const float v = field[q];
-        flux[l] = v;
-        field[q] = __fmaf_rn(fn[l], v, h);
+    const int y = blockIdx.x * blockDim.y + threadIdx.y;
+    if (y >= B.by) return;
+    const int z = blockIdx.y, comp = blockIdx.z;
+    const long long lrow = (((long long)comp * B.bz + z) * B.by + y) * B.bx;
+    const long long grow = comp * cs + (long long)(B.z0 + z + 1) * sz + (long long)(B.y0 + y) * px + B.x0;
+    float* __restrict__ flux = which == 0 ? B.flux_v : B.flux_i;
+    const float* __restrict__ a = which == 0 ? B.vv : B.ii;
+    const float* __restrict__ fo = which == 0 ? B.vvfo : B.iifo;
+    const float* __restrict__ fn = which == 0 ? B.vvfn : B.iifn;
+    for (int x = threadIdx.x; x < B.bx; x += blockDim.x) {
+        const long long l = lrow + x, q = grow + x;
+        if (!post) {
+            const float fl = flux[l];
+            const float h = __fmaf_rn(a[l], field[q], -__fmul_rn(fo[l], fl));
+            field[q] = fl;
+            flux[l] = h;
+        } else {
+            const float h = flux[l];
+            const float v = field[q];
+            flux[l] = v;
+            field[q] = __fmaf_rn(fn[l], v, h);
+        }
     }
 }
 
@@ -552,6 +738,9 @@ extern "C" int b200fdtd_create(b200fdtd_ctx** out, int device, int nx, int ny, i
     c->sz = (long long)ny * px; c->cs = (long long)(nz + 2) * c->sz;
     c->stream = (cudaStream_t)stream;                       // NULL = the default stream (torch's default stream)
     c->own_stream = false;
+    CK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     CK(cudaMalloc((void**)&c->d_ts, sizeof(int)));
     CK(cudaMemsetAsync(c->d_ts, 0, sizeof(int), c->stream));
     c->n_partials = 148 * 8;
@@ -574,6 +763,9 @@ extern "C" int b200fdtd_destroy(b200fdtd_ctx* c)
     cudaFree(c->nf_freqs);
     for (int a = 0; a < 3; ++a) { cudaFree(c->inv_len[a]); cudaFree(c->inv_dual[a]); }
     cudaFree(c->d_pml); cudaFree(c->d_faces);
+    if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
     return 0;
@@ -601,6 +793,7 @@ extern "C" int b200fdtd_set_tuning(b200fdtd_ctx* c, int kz, int ty, int variant)
     if (kz < 1) return fail("kz must be >= 1");
     if (!(ty == 1 || ty == 2 || ty == 4 || ty == 8 || ty == 16)) return fail("ty must be 1,2,4,8 or 16");
     c->kz = kz; c->ty = ty; c->variant = variant; drop_graph(c);
+    c->plan.valid = false;
     return 0;
 }
 
@@ -650,7 +843,7 @@ extern "C" int b200fdtd_set_pml(b200fdtd_ctx* c, int nboxes, const b200fdtd_pml_
     for (int b = 0; b < nboxes; ++b) {
         const b200fdtd_pml_box& B = boxes[b];
         if (B.bx <= 0 || B.by <= 0 || B.bz <= 0 || B.x0 < 0 || B.y0 < 0 || B.z0 < 0 ||
-            B.x0 + B.bx > c->nx || B.y0 + B.by > c->ny || B.z0 + B.bz > c->nz)
+            B.x0 + B.bx > c->px || B.y0 + B.by > c->ny || B.z0 + B.bz > c->nz)
             return fail("PML box %d outside the grid", b);
         if (!B.flux_v || !B.flux_i || !B.vv || !B.vvfo || !B.vvfn || !B.ii || !B.iifo || !B.iifn) return fail("PML box %d has NULL arrays", b);
         PmlBoxDev& D = t.b[b];
@@ -659,11 +852,9 @@ extern "C" int b200fdtd_set_pml(b200fdtd_ctx* c, int nboxes, const b200fdtd_pml_
         start += 3LL * B.bx * B.by * B.bz;
     }
     t.total = start;
-    c->pml = t;
-    if (!c->d_pml) CK(cudaMalloc((void**)&c->d_pml, sizeof(PmlTable)));
-    CK(cudaMemcpyAsync(c->d_pml, &t, sizeof(PmlTable), cudaMemcpyHostToDevice, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    return 0;
+    c->pml_all = t;
+    c->plan.valid = false;
+    return build_plan(c);
 }
 
 extern "C" int b200fdtd_set_probes(b200fdtd_ctx* c, int nprobes, const int32_t* kind, const int64_t* offset,
@@ -753,12 +944,15 @@ extern "C" int b200fdtd_set_timestep(b200fdtd_ctx* c, int64_t ts)
 // ---- one step, expressed as launches with a device-side step offset -----------------
 static int launch_pml(b200fdtd_ctx* c, int which, int post)
 {
-    if (c->pml.n == 0 || c->pml.total == 0) return 0;
-    const int threads = 256;
-    const long long blocks = (c->pml.total + threads - 1) / threads;
-    pml_kernel<<<(unsigned)blocks, threads, 0, c->stream>>>(which == 0 ? c->volt : c->curr, c->d_pml, which, post,
-                                                          c->ny, c->px, c->sz, c->cs);
-    CKL();
+    for (int b = 0; b < c->pml.n; ++b) {
+        const PmlBoxDev& B = c->pml.b[b];
+        const int tx = B.bx <= 8 ? 8 : (B.bx <= 16 ? 16 : 32);
+        const int ty = 256 / tx;
+        if (B.bz > 65535) return fail("PML box too tall for one launch");
+        dim3 block(tx, ty), grid((B.by + ty - 1) / ty, B.bz, 3);
+        pml_kernel<<<grid, block, 0, c->stream>>>(which == 0 ? c->volt : c->curr, B, which, post, c->px, c->sz, c->cs);
+        CKL();
+    }
     return 0;
 }
 static int launch_mur(b200fdtd_ctx* c, int phase)
@@ -807,10 +1001,15 @@ static int launch_ts_add(b200fdtd_ctx* c, int n)
 // E half step with device step offset `off` (host knows ts + off)
 static int e_half(b200fdtd_ctx* c, int off)
 {
+    if (!c->plan.valid) if (build_plan(c)) return 1;
+    const bool side = c->plan.nfused > 0 && (c->variant & 2) == 0;
+    if (launch_mur(c, 0)) return 1;              // Mur sees the true field, before any PML pass swaps in the flux
+    if (side) { if (fork_side(c)) return 1; if (launch_volume_fused(c, 0, 0, c->nz, c->side)) return 1; }
     if (launch_pml(c, 0, 0)) return 1;
-    if (launch_mur(c, 0)) return 1;
-    if (launch_volume(c, 0, 0, c->nz)) return 1;
+    if (launch_volume_plain(c, 0, 0, c->nz, c->stream)) return 1;
+    if (!side) if (launch_volume_fused(c, 0, 0, c->nz, c->stream)) return 1;
     if (launch_pml(c, 0, 1)) return 1;
+    if (side) if (join_side(c)) return 1;
     if (launch_mur(c, 1)) return 1;
     if (launch_excite(c, off)) return 1;
     if (launch_mur(c, 2)) return 1;
@@ -818,9 +1017,14 @@ static int e_half(b200fdtd_ctx* c, int off)
 }
 static int h_half(b200fdtd_ctx* c)
 {
+    if (!c->plan.valid) if (build_plan(c)) return 1;
+    const bool side = c->plan.nfused > 0 && (c->variant & 2) == 0;
+    if (side) { if (fork_side(c)) return 1; if (launch_volume_fused(c, 1, 0, c->nz, c->side)) return 1; }
     if (launch_pml(c, 1, 0)) return 1;
-    if (launch_volume(c, 1, 0, c->nz)) return 1;
+    if (launch_volume_plain(c, 1, 0, c->nz, c->stream)) return 1;
+    if (!side) if (launch_volume_fused(c, 1, 0, c->nz, c->stream)) return 1;
     if (launch_pml(c, 1, 1)) return 1;
+    if (side) if (join_side(c)) return 1;
     return 0;
 }
 
@@ -869,6 +1073,7 @@ extern "C" int b200fdtd_run(b200fdtd_ctx* c, int64_t nsteps, int use_graph)
     if (nsteps < 0) return fail("nsteps < 0");
     if (!c->volt || !c->vv) return fail("fields/coefficients not bound");
     CK(cudaSetDevice(c->device));
+    if (!c->plan.valid) if (build_plan(c)) return 1;        // never inside a stream capture
     if (!use_graph || c->stream == nullptr) return run_eager(c, nsteps);   // the NULL stream cannot be captured
     const int iv = sample_interval(c);
     const int chunk = iv > 0 ? iv : 16;

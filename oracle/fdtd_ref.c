@@ -268,8 +268,8 @@ double ref_energy(const ref_engine* e)
 /* one full time step in openEMS order (App. A1): pre-E ext, E, post-E ext, apply, pre-H, H, post-H, ++ts, sample */
 void ref_step(ref_engine* e)
 {
-    ref_pml(e, 0, 0);
     ref_mur(e, 0);
+    ref_pml(e, 0, 0);
     ref_update_e(e);
     ref_pml(e, 0, 1);
     ref_mur(e, 1);
@@ -291,7 +291,7 @@ void ref_run(ref_engine* e, int64_t nsteps) { for (int64_t s = 0; s < nsteps; ++
 void ref_half_step(ref_engine* e, int phase)
 {
     if (phase == 0) {
-        ref_pml(e, 0, 0); ref_mur(e, 0); ref_update_e(e); ref_pml(e, 0, 1); ref_mur(e, 1); ref_excite(e); ref_mur(e, 2);
+        ref_mur(e, 0); ref_pml(e, 0, 0); ref_update_e(e); ref_pml(e, 0, 1); ref_mur(e, 1); ref_excite(e); ref_mur(e, 2);
     } else if (phase == 1) {
         ref_pml(e, 1, 0); ref_update_h(e); ref_pml(e, 1, 1);
         e->ts += 1;

@@ -7,7 +7,7 @@ def lin(nz, ny, px, c, k, j, i):
 
 
 def make_problem(nx=37, ny=29, nz=23, px=40, seed=0, with_pml=True, with_mur=True, with_exc=True,
-                 with_probes=True, with_nf2ff=True, interval=3, nfreq=3):
+                 with_probes=True, with_nf2ff=True, interval=3, nfreq=3, fused_pml=False):
     rng = np.random.default_rng(seed)
     shape = (3, nz + 2, ny, px)
     P = {"nx": nx, "ny": ny, "nz": nz, "px": px, "shape": shape, "interval": interval}
@@ -62,12 +62,20 @@ def make_problem(nx=37, ny=29, nz=23, px=40, seed=0, with_pml=True, with_mur=Tru
                         coeff=rng.uniform(-0.5, 0.5, len(dst)).astype(np.float32))
     if with_pml:
         boxes = []
-        for (x0, y0, z0, bx, by, bz) in ((0, 0, 0, 5, ny, nz), (nx - 6, 0, 0, 6, ny, nz), (5, 0, 0, nx - 11, 4, nz),
-                                         (5, 4, nz - 5, nx - 11, ny - 4, 5)):
+        if fused_pml:
+            # z-slabs over whole planes, y-slabs over whole rows of the planes in between (fused into the volume kernels),
+            # plus narrow x-slabs for the separate pass
+            layout = ((0, 0, 0, px, ny, 3), (0, 0, nz - 4, px, ny, 4), (0, 0, 3, px, 4, nz - 7), (0, ny - 5, 3, px, 5, nz - 7),
+                      (0, 4, 3, 5, ny - 9, nz - 7), (nx - 6, 4, 3, 6, ny - 9, nz - 7))
+        else:
+            layout = ((0, 0, 0, 5, ny, nz), (nx - 6, 0, 0, 6, ny, nz), (5, 0, 0, nx - 11, 4, nz), (5, 4, nz - 5, nx - 11, ny - 4, 5))
+        for (x0, y0, z0, bx, by, bz) in layout:
             shp = (3, bz, by, bx)
             B = dict(x0=x0, y0=y0, z0=z0, bx=bx, by=by, bz=bz)
             for name in ("vv", "vvfo", "vvfn", "ii", "iifo", "iifn"):
                 B[name] = rng.uniform(0.6, 1.0, shp).astype(np.float32)
+                if x0 + bx > nx:
+                    B[name][..., nx - x0:] = 0.0              # pad columns of full-row slabs
             boxes.append(B)
         P["pml"] = boxes
     if with_probes:
