@@ -164,12 +164,25 @@ class Engine:
         check(self.L.b200fdtd_half_step(self.h, int(phase)))
         self._post()
 
+    def half_step_part(self, phase, part):
+        """no stream joins: the caller orders work on self.stream itself (z-slab overlap, simulation._step_multi)"""
+        check(self.L.b200fdtd_half_step_part(self.h, int(phase), int(part)))
+
+    def half_step_raw(self, phase):
+        check(self.L.b200fdtd_half_step(self.h, int(phase)))
+
     def update_only(self, which, join=True):
         if join:
             self._pre()
         check(self.L.b200fdtd_update_only(self.h, int(which)))
         if join:
             self._post()
+
+    def plan_info(self):
+        """(plain_cells, fused_pml_cells, separate_pml_cells) of the volume launch plan (pad columns included)"""
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        check(self.L.b200fdtd_plan_info(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
 
     def energy(self):
         self._pre()

@@ -183,50 +183,66 @@ class Simulation:
         return out
 
     # ------------------------------------------------------------------ halo exchange (z-slabs)
-    def _exchange(self, field, comps, direction, all_comps=False):
-        """direction +1: my top owned plane -> upper neighbour's lower ghost; -1: my bottom plane -> lower neighbour's upper ghost"""
+    # Data dependence: the E update of my plane 0 reads (Hx,Hy) of the lower neighbour's top plane;
+    # the H update of my top plane reads (Ex,Ey) of the upper neighbour's plane 0.  Planes are sent straight out of /
+    # received straight into the field arrays (each component plane is contiguous: no staging copies).  The NCCL
+    # transfers run on the process group's stream while the interior launch of the next half step runs on the
+    # engine stream; only the one boundary plane waits for them (b200fdtd_half_step_part).
+    def _views(self):
+        if getattr(self, "_tv", None) is None:
+            E = self.engine
+            self._tv = torch.from_numpy(E.volt) if isinstance(E.volt, np.ndarray) else E.volt
+            self._tc = torch.from_numpy(E.curr) if isinstance(E.curr, np.ndarray) else E.curr
+            self._gpu = self._tv.is_cuda
+            self._pend_e, self._pend_h = [], []
+        return self._tv, self._tc
+
+    def _exchange_async(self, f, direction, ncomp):
+        """direction +1: my top owned plane -> upper neighbour's lower ghost; -1: my plane 0 -> lower neighbour's upper ghost"""
         dist = torch.distributed
-        E = self.engine
-        f = E.curr if field == 1 else E.volt
-        if isinstance(f, np.ndarray):                # host-array engines (CPU test doubles): a view sharing the memory
-            f = torch.from_numpy(f)
-        ops, bufs = [], []
+        ops = []
         up, dn = self.rank + 1, self.rank - 1
-        cs = slice(0, 3) if all_comps else slice(0, 2)
         if direction > 0:
             if up < self.world:
-                send = f[cs, self.nz].contiguous(); bufs.append(send)
-                ops.append(dist.P2POp(dist.isend, send, up, self.group))
+                ops += [dist.P2POp(dist.isend, f[c, self.nz], up, self.group) for c in range(ncomp)]
             if dn >= 0:
-                recv = torch.empty_like(f[cs, 0]); bufs.append(recv)
-                ops.append(dist.P2POp(dist.irecv, recv, dn, self.group))
+                ops += [dist.P2POp(dist.irecv, f[c, 0], dn, self.group) for c in range(ncomp)]
         else:
             if dn >= 0:
-                send = f[cs, 1].contiguous(); bufs.append(send)
-                ops.append(dist.P2POp(dist.isend, send, dn, self.group))
+                ops += [dist.P2POp(dist.isend, f[c, 1], dn, self.group) for c in range(ncomp)]
             if up < self.world:
-                recv = torch.empty_like(f[cs, self.nz + 1]); bufs.append(recv)
-                ops.append(dist.P2POp(dist.irecv, recv, up, self.group))
-        if not ops:
-            return
-        for r in dist.batch_isend_irecv(ops):
-            r.wait()
-        if direction > 0 and dn >= 0:
-            f[cs, 0].copy_(recv)
-        if direction < 0 and up < self.world:
-            f[cs, self.nz + 1].copy_(recv)
+                ops += [dist.P2POp(dist.irecv, f[c, self.nz + 1], up, self.group) for c in range(ncomp)]
+        return dist.batch_isend_irecv(ops) if ops else []
+
+    @staticmethod
+    def _wait(works):
+        for w in works:
+            w.wait()            # NCCL: the current (engine) stream waits on the device; gloo: host wait
 
     def _step_multi(self, n):
+        import contextlib
         E = self.engine
-        for _ in range(n):
-            E.half_step(0)
-            self._exchange(0, None, -1)              # E bottom plane -> lower neighbour (read by its H update)
-            ts_next = E.ts + 1
-            if self.local_faces is not None and self.faces and (ts_next % self.interval) == 0:
-                self._exchange(0, None, +1, all_comps=True)   # E top plane -> upper neighbour's lower ghost (NF2FF node interpolation)
-            E.half_step(1)
-            self._exchange(1, None, +1)              # H top plane -> upper neighbour (read by its E update)
-            E.half_step(2)                           # sampling, after the halo
+        volt, curr = self._views()
+        ctx = torch.cuda.stream(E.stream) if self._gpu else contextlib.nullcontext()
+        sampling = bool(self.faces) or bool(self.probe_names)
+        with ctx:
+            for _ in range(n):
+                E.half_step_part(0, 0)                       # E: pre passes + planes [1,nz)      (overlaps the H halo)
+                self._wait(self._pend_h)
+                E.half_step_part(0, 1)                       # E: plane 0 + post passes
+                self._pend_e = self._exchange_async(volt, -1, 2)
+                E.half_step_part(1, 0)                       # H: pre passes + planes [0,nz-1)    (overlaps the E halo)
+                self._wait(self._pend_e)
+                E.half_step_part(1, 1)                       # H: top plane + post passes, ++ts
+                self._pend_h = self._exchange_async(curr, +1, 2)
+                if sampling and (E.ts % self.interval) == 0:
+                    self._wait(self._pend_h); self._pend_h = []
+                    if self.faces:                           # NF2FF node interpolation reads E of plane K0-1 too
+                        self._wait(self._exchange_async(volt, +1, 3))
+                    E.half_step_raw(2)
+            self._wait(self._pend_h); self._pend_h = []
+        if self._gpu:
+            torch.cuda.current_stream(E.device).wait_stream(E.stream)
 
     # ------------------------------------------------------------------ time loop
     def energy(self):

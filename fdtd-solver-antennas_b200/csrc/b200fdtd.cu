@@ -1117,12 +1117,65 @@ extern "C" int b200fdtd_half_step(b200fdtd_ctx* c, int phase)
     return fail("phase must be 0, 1 or 2");
 }
 
+// z-slab overlap: each half step in two parts so a halo exchange can hide behind the interior launch.
+//   phase 0 (E): part 0 = pre passes + planes [1,nz)   | part 1 = plane 0 (needs the lower ghost H) + post passes
+//   phase 1 (H): part 0 = pre passes + planes [0,nz-1) | part 1 = plane nz-1 (needs the upper ghost E) + post, ++ts
+extern "C" int b200fdtd_half_step_part(b200fdtd_ctx* c, int phase, int part)
+{
+    if (!c) return fail("NULL ctx");
+    if (!c->volt || !c->vv) return fail("fields/coefficients not bound");
+    if ((phase != 0 && phase != 1) || (part != 0 && part != 1)) return fail("phase and part must be 0 or 1");
+    CK(cudaSetDevice(c->device));
+    if (!c->plan.valid) if (build_plan(c)) return 1;
+    const int nz = c->nz;
+    if (phase == 0) {
+        if (part == 0) {
+            if (launch_mur(c, 0)) return 1;
+            if (launch_pml(c, 0, 0)) return 1;
+            return launch_volume(c, 0, 1, nz);
+        }
+        if (launch_volume(c, 0, 0, 1)) return 1;
+        if (launch_pml(c, 0, 1)) return 1;
+        if (launch_mur(c, 1)) return 1;
+        if (launch_excite(c, 0)) return 1;
+        return launch_mur(c, 2);
+    }
+    if (part == 0) {
+        if (launch_pml(c, 1, 0)) return 1;
+        return launch_volume(c, 1, 0, nz - 1);
+    }
+    if (launch_volume(c, 1, nz - 1, nz)) return 1;
+    if (launch_pml(c, 1, 1)) return 1;
+    if (launch_ts_add(c, 1)) return 1;
+    c->ts += 1;
+    return 0;
+}
+
 extern "C" int b200fdtd_update_only(b200fdtd_ctx* c, int which)
 {
     if (!c) return fail("NULL ctx");
-    if (which != 0 && which != 1) return fail("which must be 0 or 1");
+    if (which < 0 || which > 3) return fail("which must be 0..3");
     CK(cudaSetDevice(c->device));
-    return launch_volume(c, which, 0, c->nz);
+    if (which < 2) return launch_volume(c, which, 0, c->nz);
+    // 2/3: only the plain (non-PML) launch of the E/H update — the kernel the roofline is quoted on
+    if (!c->volt || !c->vv) return fail("fields/coefficients not bound");
+    if (!c->plan.valid) if (build_plan(c)) return 1;
+    return launch_volume_plain(c, which - 2, 0, c->nz, c->stream);
+}
+
+extern "C" int b200fdtd_plan_info(b200fdtd_ctx* c, int64_t* plain_cells, int64_t* fused_cells, int64_t* separate_cells)
+{
+    if (!c || !plain_cells || !fused_cells || !separate_cells) return fail("NULL argument");
+    if (!c->plan.valid) if (build_plan(c)) return 1;
+    const VolumePlan& P = c->plan;
+    int64_t skip = 0, fused = 0, sep = 0, planes = 0;
+    for (int s = 0; s < P.nskip; ++s) skip += P.sj1[s] - P.sj0[s];
+    for (int s = 0; s < P.nseg; ++s) planes += P.seg1[s] - P.seg0[s];
+    for (int q = 0; q < P.nfused; ++q) fused += (int64_t)c->px * P.fb[q].by * P.fb[q].bz;
+    for (int b = 0; b < c->pml.n; ++b) sep += (int64_t)c->pml.b[b].bx * c->pml.b[b].by * c->pml.b[b].bz;
+    *plain_cells = (int64_t)c->px * (c->ny - skip) * planes;       // cells (incl. pad columns) swept by the plain launch
+    *fused_cells = fused; *separate_cells = sep;
+    return 0;
 }
 
 extern "C" int b200fdtd_energy(b200fdtd_ctx* c, double* energy)

@@ -128,8 +128,16 @@ int b200fdtd_run(b200fdtd_ctx* ctx, int64_t nsteps, int use_graph);
  *   phase 2: probe / NF2FF sampling if the new step count is a multiple of the interval
  *            (after the H halo so slab-boundary nodes see their neighbour's new values) */
 int b200fdtd_half_step(b200fdtd_ctx* ctx, int phase);
-/* only the volume kernels (bench / roofline): which = 0 E update, 1 H update */
+/* the same half steps cut in two so the halo exchange hides behind the interior launch:
+ *   phase 0: part 0 = pre passes + planes [1,nz),   part 1 = plane 0 (reads the lower ghost H) + post passes
+ *   phase 1: part 0 = pre passes + planes [0,nz-1), part 1 = plane nz-1 (reads the upper ghost E) + post, ++ts */
+int b200fdtd_half_step_part(b200fdtd_ctx* ctx, int phase, int part);
+/* only the volume kernels (bench / roofline): which = 0 E update, 1 H update (plain + fused PML slab launches);
+ * 2 / 3 = only the plain launch of the E / H update (rows outside the fused PML slabs) */
 int b200fdtd_update_only(b200fdtd_ctx* ctx, int which);
+/* how the volume is split: cells (incl. pad columns) swept by the plain launch, by the fused PML slab launches, and
+ * by the separate PML pre/post kernel */
+int b200fdtd_plan_info(b200fdtd_ctx* ctx, int64_t* plain_cells, int64_t* fused_cells, int64_t* separate_cells);
 /* openEMS CalcFastEnergy: 0.5*eps0*sum(volt^2) + 0.5*mu0*sum(curr^2) over owned planes
  * (synchronises the stream) */
 int b200fdtd_energy(b200fdtd_ctx* ctx, double* energy);

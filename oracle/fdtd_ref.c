@@ -303,6 +303,14 @@ void ref_half_step(ref_engine* e, int phase)
     }
 }
 
+/* the z-slab overlap protocol of the product cuts each half step in two (include/b200fdtd.h half_step_part).
+ * The oracle keeps whole passes: part 0 does nothing, part 1 does the whole half step, which is equivalent
+ * because the halo a part-1 launch needs has arrived by then. */
+void ref_half_step_part(ref_engine* e, int phase, int part)
+{
+    if (part == 1) ref_half_step(e, phase);
+}
+
 /* App. A6 radiation integrals: out[ndir][4][2] = N_theta, N_phi, L_theta, L_phi (double) */
 void ref_farfield(int64_t npts, const double* pos, const double* J, const double* M, double k,
                   int ndir, const double* theta, const double* phi, double* out)

@@ -73,6 +73,7 @@ def lib():
         L.ref_mur.argtypes = [C.POINTER(_Engine), C.c_int]
         L.ref_pml.argtypes = [C.POINTER(_Engine), C.c_int, C.c_int]
         L.ref_half_step.argtypes = [C.POINTER(_Engine), C.c_int]
+        L.ref_half_step_part.argtypes = [C.POINTER(_Engine), C.c_int, C.c_int]
         L.ref_run.argtypes = [C.POINTER(_Engine), C.c_int64]
         L.ref_energy.argtypes = [C.POINTER(_Engine)]
         L.ref_energy.restype = C.c_double
@@ -216,6 +217,12 @@ class RefEngine:
 
     def half_step(self, phase):
         lib().ref_half_step(C.byref(self.e), int(phase))
+
+    def half_step_part(self, phase, part):
+        lib().ref_half_step_part(C.byref(self.e), int(phase), int(part))
+
+    def half_step_raw(self, phase):
+        self.half_step(phase)
 
     def update_only(self, which):
         (lib().ref_update_e if which == 0 else lib().ref_update_h)(C.byref(self.e))
