@@ -290,10 +290,11 @@ def run_b200(args):
             traffic = None
     line = {
         "metric": "FDTD Mcell-updates/s", "value": round(value, 1), "unit": "Mcell/s", "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": round(ms / K, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "ms_per_step": round(ms / K, 5), "higher_is_better": True, "scaling": "weak" if args.workload == "patch100m" else "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": "patch100m" if args.workload == "patch100m" else f"cube{args.n}",
-                   "scene": "2.45 GHz FR-4 patch (reference recipe), PML_8, Gaussian 1-4 GHz, lumped port, V/I probes + DFT, NF2FF DFT",
+                   "scene": ("2.45 GHz FR-4 patch (reference recipe), PML_8, Gaussian 1-4 GHz, lumped port, V/I probes + DFT, NF2FF DFT"
+                             if args.workload == "patch100m" else "uniform vacuum cube, Mur on 6 faces, centre soft source, one V probe (config 5)"),
                    "grid": [sim.nx, sim.ny, sim.nz_glob], "cells": cells, "cells_per_gpu": local_cells, "pml_cells_rank0": sim.pml_cells,
                    "timestep_s": sim.dt, "sample_interval": sim.interval, "parallelism": f"z-slab x{world}",
                    "l2_note": "working set 72 B/cell >> 126 MB L2 (inputs larger than L2, no flush needed)",
