@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="patch100m", choices=["patch100m", "cube"])
     ap.add_argument("--cells", type=float, default=100e6, help="target cells PER GPU for the patch workload")
-    ap.add_argument("--n", type=int, default=512, help="cube edge (workload cube)")
+    ap.add_argument("--cube-n", dest="n", type=int, default=512, help="cube edge (workload cube)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-cells", type=float, default=12.5e6, help="cells of the CPU-baseline sample of the same scene")
     return ap.parse_args()
