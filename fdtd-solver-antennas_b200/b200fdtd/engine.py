@@ -85,6 +85,22 @@ class Engine:
         check(self.L.b200fdtd_bind_coeffs(self.h, self.vv.data_ptr(), self.vi.data_ptr(),
                                           self.ii.data_ptr(), self.iv.data_ptr()))
 
+    def set_row_compression(self, which, xvecs, meta):
+        """which 0 = E pass (vv, vi), 1 = H pass (ii, iv); xvecs float32 [nvec, px]; meta uint8 [nz+2, ny, 32].
+        Returns (row-slots compressed, row-slots demoted by the device-side verification)."""
+        if xvecs is None or len(xvecs) == 0:
+            check(self.L.b200fdtd_set_row_compression(self.h, int(which), 0, None, None, None, None))
+            return 0, 0
+        xv = self._dev(xvecs).reshape(-1, self.px).contiguous()
+        mt = meta if isinstance(meta, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(meta, np.uint8))
+        mt = mt.to(self.device).contiguous()
+        assert mt.dtype == torch.uint8 and mt.numel() == (self.nz + 2) * self.ny * 32
+        self._keep[f"cmp{which}"] = (xv, mt)
+        nc, nd = C.c_int64(), C.c_int64()
+        check(self.L.b200fdtd_set_row_compression(self.h, int(which), xv.shape[0], xv.data_ptr(), mt.data_ptr(),
+                                                  C.byref(nc), C.byref(nd)))
+        return nc.value, nd.value
+
     def set_tuning(self, kz=16, ty=4, variant=0):
         check(self.L.b200fdtd_set_tuning(self.h, int(kz), int(ty), int(variant)))
 

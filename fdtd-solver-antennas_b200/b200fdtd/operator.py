@@ -93,6 +93,76 @@ def _snap(lines, v):
     return int(np.argmin(np.abs(lines - v)))
 
 
+class RowFactor:
+    """Row compression of one pass (E: vv,vi / H: ii,iv), host side of b200fdtd_set_row_compression.
+
+    On a rectilinear mesh most coefficient rows are scale(j,k) * xvec[i] for a handful of x-vectors.  For such rows the
+    float32 coefficients are DEFINED as fl32(fl32(scale) * fl32(xvec[i])) (instead of rounding the float64 value
+    directly; the two differ by at most one unit in the last place), so that the CUDA kernels can rebuild the row
+    from 32 bytes of metadata and a cached x-vector and still be bit-identical to a run from the full arrays."""
+    TOL = 1e-9
+    MAX_VECS = 250
+
+    def __init__(self, nx, px, nzp, ny, dev):
+        self.nx, self.px, self.dev = nx, px, dev
+        self.vec32 = []                                   # shared table of this pass
+        self.slots = [[] for _ in range(6)]               # per slot: list of (global id, xref float64 [nx])
+        self.meta_f = torch.zeros((nzp, ny, 8), dtype=torch.float32, device=dev)
+        self.meta_u8 = self.meta_f.view(torch.uint8)      # [nzp, ny, 32]
+        self.meta_u8[:, :, 24:30] = 255
+        self.rows_total = 0
+        self.rows_compressed = 0
+
+    def _match(self, arr, amax, gid, xref, ids, sc, unmatched):
+        s = (arr @ xref) / (xref @ xref)
+        resid = (arr - s.unsqueeze(-1) * xref).abs().amax(-1)
+        ok = unmatched & (resid <= self.TOL * amax)
+        ids[ok] = gid
+        sc[ok] = s[ok]
+        unmatched &= ~ok
+
+    def factor(self, arr, slot, plane0):
+        """arr float64 [nk, ny, nx] -> float32 [nk, ny, nx]; records (scale, id) of the rows in meta[plane0:plane0+nk]"""
+        nk, ny, nx = arr.shape
+        amax = arr.abs().amax(-1)
+        ids = torch.full((nk, ny), 255, dtype=torch.int64, device=self.dev)
+        sc = torch.zeros((nk, ny), dtype=torch.float64, device=self.dev)
+        unmatched = torch.ones((nk, ny), dtype=torch.bool, device=self.dev)
+        for gid, xref in self.slots[slot]:
+            self._match(arr, amax, gid, xref, ids, sc, unmatched)
+        for _ in range(3):                                # learn new x-vectors from rows nothing matched yet
+            cand = unmatched & (amax > 0)
+            if not bool(cand.any()) or len(self.vec32) >= self.MAX_VECS:
+                break
+            idx = cand.nonzero()
+            kk, jj = idx[len(idx) // 2].tolist()
+            xref = arr[kk, jj] / amax[kk, jj]
+            gid = len(self.vec32)
+            v32 = torch.zeros(self.px, dtype=torch.float32, device=self.dev)
+            v32[:nx] = xref.to(torch.float32)
+            self.vec32.append(v32)
+            self.slots[slot].append((gid, xref.clone()))
+            self._match(arr, amax, gid, xref, ids, sc, unmatched)
+        out = arr.to(torch.float32)
+        sc32 = sc.to(torch.float32)
+        if len(self.vec32):
+            table = torch.stack(self.vec32)[:, :nx]       # [nvec, nx] float32
+            m = ids != 255
+            if bool(m.any()):
+                prod = sc32.unsqueeze(-1) * table[ids.clamp(max=len(self.vec32) - 1)]    # float32 multiply, IEEE rn
+                out = torch.where(m.unsqueeze(-1), prod, out)
+        self.meta_f[plane0:plane0 + nk, :, slot] = sc32
+        self.meta_u8[plane0:plane0 + nk, :, 24 + slot] = ids.to(torch.uint8)
+        self.rows_total += nk * ny
+        self.rows_compressed += int((ids != 255).sum())
+        return out
+
+    def tables(self):
+        if not self.vec32:
+            return None, None
+        return torch.stack(self.vec32).contiguous(), self.meta_u8.contiguous()
+
+
 class OperatorBuilder:
     """Scene -> coefficient blocks and narrow-band index lists in GLOBAL grid indices."""
 
@@ -420,12 +490,19 @@ class OperatorBuilder:
         return 2.0 / math.sqrt(worst)
 
     # ------------------------------------------------------------------ coefficients
-    def coefficients(self, k0, k1, px, dt, chunk=32):
-        """vv, vi, ii, iv as float32 [3][k1-k0+2][ny][px] (ghost planes and pad columns zero) for node planes [k0,k1)"""
+    def coefficients(self, k0, k1, px, dt, chunk=32, compress=True):
+        """vv, vi, ii, iv as float32 [3][k1-k0+2][ny][px] (ghost planes and pad columns zero) for node planes [k0,k1).
+        With compress=True the row compression tables of both passes are left in self.row_compression."""
         nx, ny, nz = self.n
         shape = (3, k1 - k0 + 2, ny, px)
         vv = torch.zeros(shape, dtype=torch.float32, device=self.dev)
         vi, ii, iv = torch.zeros_like(vv), torch.zeros_like(vv), torch.zeros_like(vv)
+        fE = RowFactor(nx, px, shape[1], ny, self.dev) if compress else None
+        fH = RowFactor(nx, px, shape[1], ny, self.dev) if compress else None
+
+        def put(dst, comp, sl, arr64, fac, slot):
+            dst[comp, sl, :, :nx] = fac.factor(arr64, slot, sl.start) if fac is not None else arr64.to(torch.float32)
+
         k = k0
         while k < k1:
             ke = min(k + chunk, k1)
@@ -444,17 +521,21 @@ class OperatorBuilder:
                 pec = self._pec_mask(comp, rng)
                 ok = ok & ~pec
                 z = torch.zeros_like(C)
-                vv[comp, dst, :, :nx] = torch.where(ok, (1.0 - x) / (1.0 + x), z).to(torch.float32)
-                vi[comp, dst, :, :nx] = torch.where(ok, (dt / Cs) / (1.0 + x), z).to(torch.float32)
+                put(vv, comp, dst, torch.where(ok, (1.0 - x) / (1.0 + x), z), fE, comp)
+                put(vi, comp, dst, torch.where(ok, (dt / Cs) / (1.0 + x), z), fE, 3 + comp)
                 invL = ec["invL"][comp]
                 okh = invL > 0
                 y = torch.zeros_like(invL)
                 rH = self._rates(comp, rng, ec, 1)
                 if rH[nP] is not None:
                     y = y + 0.5 * dt * rH[nP]
-                ii[comp, dst, :, :nx] = torch.where(okh, (1.0 - y) / (1.0 + y), z).to(torch.float32)
-                iv[comp, dst, :, :nx] = torch.where(okh, dt * invL / (1.0 + y), z).to(torch.float32)
+                put(ii, comp, dst, torch.where(okh, (1.0 - y) / (1.0 + y), z), fH, comp)
+                put(iv, comp, dst, torch.where(okh, dt * invL / (1.0 + y), z), fH, 3 + comp)
             k = ke
+        self.row_compression = None
+        if compress:
+            self.row_compression = {0: fE.tables(), 1: fH.tables()}
+            self.row_compression_stats = {0: (fE.rows_compressed, fE.rows_total), 1: (fH.rows_compressed, fH.rows_total)}
         return vv, vi, ii, iv
 
     def pml_coefficients(self, box, dt):

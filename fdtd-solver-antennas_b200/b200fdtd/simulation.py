@@ -89,6 +89,12 @@ class Simulation:
         vv, vi, ii, iv = B.coefficients(self.K0, self.K1, self.px, dt)
         E.set_coeffs(vv, vi, ii, iv)
         del vv, vi, ii, iv
+        self.compression = {}
+        if B.row_compression is not None and hasattr(E, "set_row_compression"):
+            for which in (0, 1):
+                xv, meta = B.row_compression[which]
+                if xv is not None:
+                    self.compression[which] = E.set_row_compression(which, xv, meta) + (int(xv.shape[0]),)
         lin = lambda c, k, j, i: ((c * (self.nz + 2) + (k - self.K0 + 1)) * ny + j) * self.px + i   # noqa: E731
         own = lambda k: (k >= self.K0) & (k < self.K1)                                                  # noqa: E731
         # excitation

@@ -81,6 +81,8 @@ struct b200fdtd_ctx {
     float *volt = nullptr, *curr = nullptr;
     const float *vv = nullptr, *vi = nullptr, *ii = nullptr, *iv = nullptr;
     int kz = 16, ty = 4, variant = 0;
+    const float* cmp_xv[2] = {nullptr, nullptr};          // row compression tables of the E and H pass (caller-owned)
+    const unsigned char* cmp_meta[2] = {nullptr, nullptr};
     // step counter
     int64_t ts = 0;
     int* d_ts = nullptr;
@@ -127,7 +129,41 @@ struct VolParams {
     long long sz, cs;
     int kz;                         // planes marched per CTA
     int k0, k1;                     // plane range [k0,k1) handled by this launch
+    const float* __restrict__ xv;   // row compression: table of x-vectors [nvec][px]
+    const unsigned char* __restrict__ meta;   // per row (k,j): 6 scales + 6 vector ids (32 B), see RowMeta
 };
+
+// Row compression of the operator (the openEMS "compressed operator" idea, applied per x-row): on a rectilinear mesh
+// a coefficient row is very often  scale(j,k) * xvec[i]  with one of a handful of x-vectors (all vacuum rows, PML rows,
+// boundary rows).  Such rows are not streamed from HBM: the kernel reads the 32-byte row record and the (L1-resident)
+// x-vector and multiplies.  The full arrays stay bound and hold exactly fl32(scale*xvec) for every compressed row
+// (checked on the device by verify_rows_kernel, which demotes any row that does not match bit for bit), so results are
+// identical with and without compression and identical to the oracle, which reads the full arrays.
+struct RowMeta { float sc[6]; unsigned char id[6]; unsigned char pad[2]; };   // slots: ca_x, ca_y, ca_z, cb_x, cb_y, cb_z
+#define ROW_FULL 255u
+
+__device__ __forceinline__ float4 coef4(unsigned id, float sc, const float* full, const float* __restrict__ xv, int i0, int px)
+{
+    if (id != ROW_FULL) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(xv + (size_t)id * px + i0));
+        return make_float4(__fmul_rn(sc, v.x), __fmul_rn(sc, v.y), __fmul_rn(sc, v.z), __fmul_rn(sc, v.w));
+    }
+    return __ldcs(reinterpret_cast<const float4*>(full));
+}
+
+#define LOAD_COEFFS_CMP()                                                                                   \
+    do {                                                                                                    \
+        const float4* m_ = reinterpret_cast<const float4*>(p.meta + ((long long)(k + 1) * p.ny + j) * 32);  \
+        const float4 m0_ = __ldg(m_), m1_ = __ldg(m_ + 1);                                                  \
+        const unsigned w0_ = __float_as_uint(m1_.z), w1_ = __float_as_uint(m1_.w);                          \
+        ax = coef4(w0_ & 255u, m0_.x, p.ca + base, p.xv, i0, p.px);                                         \
+        ay = coef4((w0_ >> 8) & 255u, m0_.y, p.ca + cs + base, p.xv, i0, p.px);                             \
+        az = coef4((w0_ >> 16) & 255u, m0_.z, p.ca + 2 * cs + base, p.xv, i0, p.px);                        \
+        bx = coef4(w0_ >> 24, m0_.w, p.cb + base, p.xv, i0, p.px);                                          \
+        by = coef4(w1_ & 255u, m1_.x, p.cb + cs + base, p.xv, i0, p.px);                                    \
+        bz = coef4((w1_ >> 8) & 255u, m1_.y, p.cb + 2 * cs + base, p.xv, i0, p.px);                         \
+    } while (0)
+
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ float4 ld4_stream(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
@@ -190,7 +226,7 @@ __device__ __forceinline__ float4 pml_post4(float4 fn, float4 F, float4 h) {
 //   x: ((Hz - Hz[j-1]) - Hy) + Hy[k-1]
 //   y: ((Hx - Hx[k-1]) - Hz) + Hz[i-1]
 //   z: ((Hy - Hy[i-1]) - Hx) + Hx[j-1]
-template <int TY, bool PML>
+template <int TY, bool PML, bool CMP>
 __global__ void __launch_bounds__(32 * TY) update_e_kernel(const VolParams p, const RowParams r)
 {
     const int lane = threadIdx.x;
@@ -228,8 +264,11 @@ __global__ void __launch_bounds__(32 * TY) update_e_kernel(const VolParams p, co
             hx = ld4(g + base); hy = ld4(g + cs + base); hz = ld4(g + 2 * cs + base);
             if (has_jm) { hz_jm = ld4(g + 2 * cs + base - p.px); hx_jm = ld4(g + base - p.px); }
             ex = ld4_stream(f + base); ey = ld4_stream(f + cs + base); ez = ld4_stream(f + 2 * cs + base);
-            ax = ld4_ro(p.ca + base); ay = ld4_ro(p.ca + cs + base); az = ld4_ro(p.ca + 2 * cs + base);
-            bx = ld4_ro(p.cb + base); by = ld4_ro(p.cb + cs + base); bz = ld4_ro(p.cb + 2 * cs + base);
+            if (CMP) LOAD_COEFFS_CMP();
+            else {
+                ax = ld4_ro(p.ca + base); ay = ld4_ro(p.ca + cs + base); az = ld4_ro(p.ca + 2 * cs + base);
+                bx = ld4_ro(p.cb + base); by = ld4_ro(p.cb + cs + base); bz = ld4_ro(p.cb + 2 * cs + base);
+            }
         }
         if (edge_load) { hz_e = g[2 * cs + base - 1]; hy_e = g[cs + base - 1]; }
         float hz_l = __shfl_up_sync(0xffffffffu, hz.w, 1);
@@ -258,7 +297,7 @@ __global__ void __launch_bounds__(32 * TY) update_e_kernel(const VolParams p, co
 //   x: ((Ez - Ez[j+1]) - Ey) + Ey[k+1]
 //   y: ((Ex - Ex[k+1]) - Ez) + Ez[i+1]
 //   z: ((Ey - Ey[i+1]) - Ex) + Ex[j+1]
-template <int TY, bool PML>
+template <int TY, bool PML, bool CMP>
 __global__ void __launch_bounds__(32 * TY) update_h_kernel(const VolParams p, const RowParams r)
 {
     const int lane = threadIdx.x;
@@ -297,8 +336,11 @@ __global__ void __launch_bounds__(32 * TY) update_h_kernel(const VolParams p, co
             ex = ld4(g + base); ey = ld4(g + cs + base); ez = ld4(g + 2 * cs + base);
             if (has_jp) { ez_jp = ld4(g + 2 * cs + base + p.px); ex_jp = ld4(g + base + p.px); }
             hx = ld4_stream(f + base); hy = ld4_stream(f + cs + base); hz = ld4_stream(f + 2 * cs + base);
-            ax = ld4_ro(p.ca + base); ay = ld4_ro(p.ca + cs + base); az = ld4_ro(p.ca + 2 * cs + base);
-            bx = ld4_ro(p.cb + base); by = ld4_ro(p.cb + cs + base); bz = ld4_ro(p.cb + 2 * cs + base);
+            if (CMP) LOAD_COEFFS_CMP();
+            else {
+                ax = ld4_ro(p.ca + base); ay = ld4_ro(p.ca + cs + base); az = ld4_ro(p.ca + 2 * cs + base);
+                bx = ld4_ro(p.cb + base); by = ld4_ro(p.cb + cs + base); bz = ld4_ro(p.cb + 2 * cs + base);
+            }
         }
         if (edge_load) { ez_e = g[2 * cs + base + 4]; ey_e = g[cs + base + 4]; }
         float ez_r = __shfl_down_sync(0xffffffffu, ez.x, 1);
@@ -338,8 +380,13 @@ static int launch_volume_one(b200fdtd_ctx* c, int which, int k0, int k1, const R
     dim3 block(32, ty);
     dim3 grid((c->px + 127) / 128, (r.j1 - r.j0 + ty - 1) / ty, (k1 - k0 + kz - 1) / kz);
     if (grid.y > 65535 || grid.z > 65535) return fail("grid too large for launch (ny/ty=%u, nz/kz=%u)", grid.y, grid.z);
-#define LAUNCH(TYV) do { if (which == 0) update_e_kernel<TYV, PML><<<grid, block, 0, stream>>>(p, r); \
-                         else update_h_kernel<TYV, PML><<<grid, block, 0, stream>>>(p, r); } while (0)
+    const bool cmp = c->cmp_meta[which] != nullptr && (c->variant & 4) == 0;
+    p.xv = c->cmp_xv[which]; p.meta = c->cmp_meta[which];
+#define LAUNCH(TYV) do { \
+        if (which == 0) { if (cmp) update_e_kernel<TYV, PML, true><<<grid, block, 0, stream>>>(p, r); \
+                          else update_e_kernel<TYV, PML, false><<<grid, block, 0, stream>>>(p, r); } \
+        else { if (cmp) update_h_kernel<TYV, PML, true><<<grid, block, 0, stream>>>(p, r); \
+               else update_h_kernel<TYV, PML, false><<<grid, block, 0, stream>>>(p, r); } } while (0)
     switch (ty) {
         case 1: LAUNCH(1); break;
         case 2: LAUNCH(2); break;
@@ -784,6 +831,7 @@ extern "C" int b200fdtd_bind_coeffs(b200fdtd_ctx* c, const float* vv, const floa
     if (!c || !vv || !vi || !ii || !iv) return fail("NULL argument");
     if (((uintptr_t)vv | (uintptr_t)vi | (uintptr_t)ii | (uintptr_t)iv) & 15) return fail("coefficient pointers must be 16-byte aligned");
     c->vv = vv; c->vi = vi; c->ii = ii; c->iv = iv; drop_graph(c);
+    c->cmp_xv[0] = c->cmp_xv[1] = nullptr; c->cmp_meta[0] = c->cmp_meta[1] = nullptr;   // new arrays: compression must be set again
     return 0;
 }
 
@@ -794,6 +842,67 @@ extern "C" int b200fdtd_set_tuning(b200fdtd_ctx* c, int kz, int ty, int variant)
     if (!(ty == 1 || ty == 2 || ty == 4 || ty == 8 || ty == 16)) return fail("ty must be 1,2,4,8 or 16");
     c->kz = kz; c->ty = ty; c->variant = variant; drop_graph(c);
     c->plan.valid = false;
+    return 0;
+}
+
+// one warp per (row, slot): a compressed row must reproduce the full array bit for bit, else it is demoted to ROW_FULL
+__global__ void __launch_bounds__(256) verify_rows_kernel(unsigned char* __restrict__ meta, const float* __restrict__ xv, int nvec,
+        const float* __restrict__ ca, const float* __restrict__ cb, int ny, int nz, int px, long long sz, long long cs,
+        unsigned long long* __restrict__ counts /* [0] demoted, [1] compressed row-slots */)
+{
+    const long long w = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const long long nrows = (long long)nz * ny;
+    if (w >= nrows * 6) return;
+    const int slot = (int)(w % 6);
+    const long long row = w / 6;
+    const int k = (int)(row / ny), j = (int)(row % ny);
+    RowMeta* M = reinterpret_cast<RowMeta*>(meta + ((long long)(k + 1) * ny + j) * 32);
+    const unsigned id = M->id[slot];
+    if (id == ROW_FULL) return;
+    bool ok = id < (unsigned)nvec;
+    if (ok) {
+        const float sc = M->sc[slot];
+        const float* full = (slot < 3 ? ca : cb) + (long long)(slot % 3) * cs + (long long)(k + 1) * sz + (long long)j * px;
+        const float* v = xv + (size_t)id * px;
+        for (int i = lane; i < px; i += 32)
+            if (__float_as_uint(__fmul_rn(sc, v[i])) != __float_as_uint(full[i])) ok = false;
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    if (lane == 0) {
+        if (!ok) { M->id[slot] = (unsigned char)ROW_FULL; atomicAdd(&counts[0], 1ULL); }
+        else atomicAdd(&counts[1], 1ULL);
+    }
+}
+
+extern "C" int b200fdtd_set_row_compression(b200fdtd_ctx* c, int which, int nvec, const float* xvecs, void* meta,
+                                             int64_t* n_compressed, int64_t* n_demoted)
+{
+    if (!c) return fail("NULL ctx");
+    if (which != 0 && which != 1) return fail("which must be 0 (E pass) or 1 (H pass)");
+    CK(cudaSetDevice(c->device));
+    drop_graph(c);
+    if (nvec == 0 || !xvecs || !meta) { c->cmp_xv[which] = nullptr; c->cmp_meta[which] = nullptr; return 0; }
+    if (!c->vv) return fail("bind the coefficients before setting their row compression");
+    if (nvec < 0 || nvec > 255) return fail("nvec=%d out of range (1..255)", nvec);
+    if (((uintptr_t)xvecs | (uintptr_t)meta) & 15) return fail("compression tables must be 16-byte aligned");
+    unsigned long long* d_counts = nullptr;
+    CK(cudaMalloc((void**)&d_counts, 2 * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(d_counts, 0, 2 * sizeof(unsigned long long), c->stream));
+    const long long warps = (long long)c->nz * c->ny * 6;
+    const long long blocks = (warps * 32 + 255) / 256;
+    verify_rows_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>((unsigned char*)meta, xvecs, nvec,
+        which == 0 ? c->vv : c->ii, which == 0 ? c->vi : c->iv, c->ny, c->nz, c->px, c->sz, c->cs, d_counts);
+    g_launches.fetch_add(1);
+    cudaError_t e = cudaGetLastError();
+    unsigned long long h[2] = {0, 0};
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, d_counts, sizeof(h), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_counts);
+    if (e != cudaSuccess) return fail("row compression verification failed: %s", cudaGetErrorString(e));
+    if (n_demoted) *n_demoted = (int64_t)h[0];
+    if (n_compressed) *n_compressed = (int64_t)h[1];
+    c->cmp_xv[which] = xvecs; c->cmp_meta[which] = (const unsigned char*)meta;
     return 0;
 }
 

@@ -54,8 +54,17 @@ int b200fdtd_bind_fields(b200fdtd_ctx* ctx, float* volt, float* curr);
 /* vv,vi,ii,iv [3][nz+2][ny][px] (dev, read-only): the openEMS operator (App. A2) */
 int b200fdtd_bind_coeffs(b200fdtd_ctx* ctx, const float* vv, const float* vi,
                          const float* ii, const float* iv);
+/* Row compression of the operator (optional, lossless).  For the E pass (which = 0: vv, vi) or the H pass
+ * (which = 1: ii, iv): xvecs = dev [nvec][px] table of x-vectors; meta = dev, writable, [(nz+2)*ny] records of 32 bytes
+ *   { float scale[6]; uint8 vec_id[6]; uint8 pad[2]; }   slots: ca_x, ca_y, ca_z, cb_x, cb_y, cb_z  (ca = vv|ii, cb = vi|iv)
+ * vec_id 255 = row is streamed from the full array.  A row with vec_id < nvec claims full[i] == fl32(scale*xvec[i]);
+ * the library verifies every claim on the device and demotes rows that do not match bit for bit, so results never
+ * depend on the compression.  The full arrays must stay bound.  nvec = 0 switches compression off. */
+int b200fdtd_set_row_compression(b200fdtd_ctx* ctx, int which, int nvec, const float* xvecs, void* meta,
+                                 int64_t* n_compressed /*host out, may be NULL*/, int64_t* n_demoted /*host out, may be NULL*/);
 /* tuning knobs of the volume kernels: planes marched per CTA (kz), rows per CTA (ty in {2,4,8}),
- * variant (0 = register z-march) */
+ * variant bits: 1 = PML slabs by the separate pre/post kernel instead of fused rows, 2 = no side stream,
+ * 4 = ignore the row compression */
 int b200fdtd_set_tuning(b200fdtd_ctx* ctx, int kz, int ty, int variant);
 
 /* ---- excitation (openEMS Engine_Ext_Excitation::Apply2Voltages; AddLumpedPort's

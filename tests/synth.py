@@ -7,7 +7,7 @@ def lin(nz, ny, px, c, k, j, i):
 
 
 def make_problem(nx=37, ny=29, nz=23, px=40, seed=0, with_pml=True, with_mur=True, with_exc=True,
-                 with_probes=True, with_nf2ff=True, interval=3, nfreq=3, fused_pml=False):
+                 with_probes=True, with_nf2ff=True, interval=3, nfreq=3, fused_pml=False, compress=False):
     rng = np.random.default_rng(seed)
     shape = (3, nz + 2, ny, px)
     P = {"nx": nx, "ny": ny, "nz": nz, "px": px, "shape": shape, "interval": interval}
@@ -23,6 +23,52 @@ def make_problem(nx=37, ny=29, nz=23, px=40, seed=0, with_pml=True, with_mur=Tru
     # H components on the top index planes do not exist
     for a in (ii, iv):
         a[:, :, ny - 1, :] = 0; a[:, :, :, nx - 1:] = 0
+    if compress:
+        # row compression (b200fdtd_set_row_compression): ~70 % of the rows become scale*xvec exactly; a few records
+        # make false claims and must be demoted by the device-side verification
+        P["cmp"] = {}
+        for which, (ca, cb) in enumerate(((vv, vi), (ii, iv))):
+            nvec = 5
+            xv = np.zeros((nvec, px), np.float32)
+            xv[:, :nx] = rng.uniform(0.5, 1.0, (nvec, nx)).astype(np.float32)
+            xv[0, :nx] = 1.0
+            if which == 1:
+                xv[:, nx - 1:] = 0.0
+            meta_f = np.zeros((nz + 2, ny, 8), np.float32)
+            meta = meta_f.view(np.uint8)
+            meta[:, :, 24:30] = 255
+            wrong = 0
+            for slot in range(6):
+                arr = (ca, cb)[slot // 3][slot % 3]
+                for k in range(nz):
+                    for j in range(ny):
+                        u = rng.random()
+                        if u < 0.7:
+                            vid = int(rng.integers(0, nvec)); scv = np.float32(rng.uniform(0.05, 1.0))
+                            arr[k + 1, j, :] = scv * xv[vid]          # float32 product
+                            meta_f[k + 1, j, slot] = scv; meta[k + 1, j, 24 + slot] = vid
+                        elif u < 0.73:
+                            vid = int(rng.integers(0, nvec)); scv = np.float32(rng.uniform(0.05, 1.0))
+                            meta_f[k + 1, j, slot] = scv; meta[k + 1, j, 24 + slot] = vid   # false claim: row left as is
+                            wrong += 1
+            P["cmp"][which] = dict(xvecs=xv, meta=meta.copy(), wrong=wrong)
+        pec = pec & (rng.random(shape) < 0.0)              # keep compressed rows intact (no random PEC on top)
+        for a in (ii, iv):
+            a[:, :, ny - 1, :] = 0; a[:, :, :, nx - 1:] = 0
+        # a false claim may have become true by the zeroing above only if the whole row is zero: recount exactly
+        for which, (ca, cb) in enumerate(((vv, vi), (ii, iv))):
+            c = P["cmp"][which]; mf = c["meta"].view(np.float32); wrong = 0; good = 0
+            for slot in range(6):
+                arr = (ca, cb)[slot // 3][slot % 3]
+                ids = c["meta"][:, :, 24 + slot]
+                for k in range(nz):
+                    for j in range(ny):
+                        vid = ids[k + 1, j]
+                        if vid == 255:
+                            continue
+                        ok = np.array_equal((mf[k + 1, j, slot] * c["xvecs"][vid]).view(np.uint32), arr[k + 1, j].view(np.uint32))
+                        wrong += (not ok); good += ok
+            c["wrong"], c["good"] = wrong, good
     P.update(vv=vv, vi=vi, ii=ii, iv=iv)
     volt = rng.standard_normal(shape).astype(np.float32); volt[..., nx:] = 0
     curr = rng.standard_normal(shape).astype(np.float32); curr[..., nx:] = 0
@@ -102,6 +148,8 @@ def make_problem(nx=37, ny=29, nz=23, px=40, seed=0, with_pml=True, with_mur=Tru
 def apply(E, P, np_fields=True):
     """Load problem P into an engine E (oracle RefEngine or CUDA Engine; same method names)."""
     E.set_coeffs(P["vv"], P["vi"], P["ii"], P["iv"])
+    if "cmp" in P and hasattr(E, "set_row_compression"):
+        E.cmp_counts = {w: E.set_row_compression(w, c["xvecs"], c["meta"].copy()) for w, c in P["cmp"].items()}
     if np_fields:
         E.volt[...] = P["volt0"]; E.curr[...] = P["curr0"]
     else:

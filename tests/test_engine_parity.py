@@ -74,6 +74,28 @@ def test_full_step_all_extensions(use_graph, fused, variant):
     assert abs(e_g - e_r) <= 1e-6 * abs(e_r)
 
 
+@pytest.mark.parametrize("fused", [False, True])
+@pytest.mark.parametrize("tune", [(16, 4, 0), (3, 8, 0), (5, 2, 4)])
+def test_row_compression_is_lossless(fused, tune):
+    """compressed rows (scale*xvec) give bit-identical fields; false claims are demoted by the device-side check;
+    variant 4 ignores the tables"""
+    P = synth.make_problem(37, 29, 23, 40, seed=9, fused_pml=fused, compress=True)
+    R, G = _engines(P)
+    for w in (0, 1):
+        good, demoted = G.cmp_counts[w]
+        assert demoted == P["cmp"][w]["wrong"] and good == P["cmp"][w]["good"], (w, G.cmp_counts[w], P["cmp"][w]["wrong"])
+        assert good > 1000
+    G.set_tuning(kz=tune[0], ty=tune[1], variant=tune[2])
+    if not fused:          # update_only on fused slabs includes their PML pre/post, which the bare oracle update does not
+        for it in range(2):
+            R.update_only(0); G.update_only(0)
+            _assert_fields_equal(R, G, f"after E update {it}")
+            R.update_only(1); G.update_only(1)
+            _assert_fields_equal(R, G, f"after H update {it}")
+    R.run(11); G.run(11, use_graph=True)
+    _assert_fields_equal(R, G, "after 11 full steps with row compression")
+
+
 def test_half_steps_equal_run():
     P = synth.make_problem(33, 17, 11, 64, seed=5)
     R, G = _engines(P)
