@@ -44,6 +44,9 @@ def parse():
     ap.add_argument("--cells", type=float, default=100e6, help="target cells PER GPU for the patch workload")
     ap.add_argument("--cube-n", dest="n", type=int, default=512, help="cube edge (workload cube)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kz", type=int, default=0, help="tuning experiment: planes marched per CTA")
+    ap.add_argument("--ty", type=int, default=0, help="tuning experiment: rows per CTA")
+    ap.add_argument("--variant", type=int, default=0, help="tuning experiment: engine variant bits")
     ap.add_argument("--cpu-cells", type=float, default=12.5e6, help="cells of the CPU-baseline sample of the same scene")
     return ap.parse_args()
 
@@ -191,6 +194,8 @@ def run_b200(args):
     sim.prepare()
     build_s = time.time() - t0
     E = sim.engine
+    if args.kz or args.ty or args.variant:
+        E.set_tuning(kz=args.kz or 16, ty=args.ty or 4, variant=args.variant)
     cells = sim.cells
     local_cells = sim.nx * sim.ny * sim.nz
 

@@ -45,7 +45,7 @@ def _default_engine_factory(nx, ny, nz, px, device):
 
 class Simulation:
     def __init__(self, setup: Setup, device=0, rank=0, world=1, group=None, engine_factory=None,
-                 build_device=None, px_align=32, log=None, nf2ff_freqs=None, probe_freqs=None):
+                 build_device=None, px_align=32, log=None, nf2ff_freqs=None, probe_freqs=None, align_x_slabs=False):
         self.setup = setup
         self.rank, self.world, self.group = int(rank), int(world), group
         self.device = device
@@ -55,6 +55,7 @@ class Simulation:
             build_device = torch.device("cuda", device) if torch.cuda.is_available() else torch.device("cpu")
         self.build_device = build_device
         self.px_align = px_align
+        self.align_x_slabs = bool(align_x_slabs)
         self.nf2ff_freqs = None if nf2ff_freqs is None else np.atleast_1d(np.asarray(nf2ff_freqs, np.float64))
         self.probe_freqs = None if probe_freqs is None else np.atleast_1d(np.asarray(probe_freqs, np.float64))
         self.engine = None
@@ -121,13 +122,27 @@ class Simulation:
             k0, k1 = max(rk[0], self.K0), min(rk[1], self.K1)
             if k1 <= k0:
                 continue
+            full_rows = ri[0] == 0 and ri[1] == nx
+            if not full_rows and self.align_x_slabs:
+                # narrow x-slab widened to float4-aligned columns (the extra columns get the identity coefficients
+                # a = fo = fn = 1 that the formulas give outside the PML) so the x-edge launches can fold it in.
+                # Off by default: measured on patch100m the 160-register x-edge kernel costs more than the separate
+                # pre/post passes it replaces (2.42 vs 1.88 ms/step), see DESIGN.md.
+                ri = (0, min(nx, _round_up(ri[1], 4))) if ri[0] == 0 else ((ri[0] // 4) * 4, nx)
             co = B.pml_coefficients((ri, rj, (k0, k1)), dt)
             box = dict(x0=ri[0], y0=rj[0], z0=k0 - self.K0, bx=ri[1] - ri[0], by=rj[1] - rj[0], bz=k1 - k0)
-            if ri[0] == 0 and ri[1] == nx and self.px > nx:
+            if not full_rows and ri[1] == nx and self.px > nx:
+                co = {n: torch.nn.functional.pad(t, (0, self.px - nx)) for n, t in co.items()}
+                box["bx"] = self.px - ri[0]
+            elif not full_rows and ri[0] == 0 and box["bx"] % 4:
+                pad = _round_up(box["bx"], 4) - box["bx"]
+                co = {n: torch.nn.functional.pad(t, (0, pad)) for n, t in co.items()}
+                box["bx"] += pad
+            if full_rows and self.px > nx:
                 # whole x-rows: pad to the row pitch so the volume kernels can fuse this slab (RowParams)
                 co = {n: torch.nn.functional.pad(t, (0, self.px - nx)) for n, t in co.items()}
                 box["bx"] = self.px
-            elif ri[0] == 0 and ri[1] == nx:
+            elif full_rows:
                 box["bx"] = self.px
             box.update(co)
             self.pml_cells += box["bx"] * box["by"] * box["bz"]

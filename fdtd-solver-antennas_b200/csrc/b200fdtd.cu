@@ -61,6 +61,10 @@ struct VolumePlan {
     int nseg = 0; int seg0[3], seg1[3];          // plane ranges of the plain launches (complement of fused z-slabs)
     int nskip = 0; int sj0[2], sj1[2];           // rows of fused y-slabs
     int nfused = 0; FusedBox fb[4];
+    // narrow x-slabs folded into "x-edge" launches of the plain rows
+    bool xedge = false; int has_lo = 0, has_hi = 0; FusedBox xlo{}, xhi{}; int xw0 = 0, xx1 = 0, xw1 = 0;
+    int nxc = 0, xc[3] = {0, 0, 0};              // x-chunks swept by the x-edge launch
+    int plain_c0 = 0, plain_nc = 0;              // x-chunks swept by the plain launch
 };
 
 struct FaceDev {
@@ -195,6 +199,11 @@ struct RowParams {
     float* flux;                    // fused slab arrays [3][bz][by][px] (PML launches only)
     const float* a; const float* fo; const float* fn;
     int y0, z0, by, bz;
+    // x-chunk selection: plain launches sweep chunks [xc_off, xc_off+gridDim.x); x-edge launches (MODE 2) sweep the
+    // listed chunks, whose lanes inside the narrow x-slabs do the PML pre/update/post and all other lanes the plain update
+    int xc_off, xc0, xc1, xc2;
+    float* xflux0; const float* xa0; const float* xfo0; const float* xfn0; int xw0;            // low x-slab: columns [0, xw0)
+    float* xflux1; const float* xa1; const float* xfo1; const float* xfn1; int xx1, xw1;       // high x-slab: columns [xx1, xx1+xw1)
 };
 
 __device__ __forceinline__ float4 pml_pre4(float4 a, float4 fo, float4 fl, float4 e) {
@@ -222,18 +231,33 @@ __device__ __forceinline__ float4 pml_post4(float4 fn, float4 F, float4 h) {
         f4 = pml_post4(fn_, F_, h_);                                                          \
     } while (0)
 
+// the same with explicit slab pointers and a per-lane predicate (x-edge launches)
+#define PML_COMP_X(f4, ca4, cb4, A, B, C, D, lofs)                                            \
+    do {                                                                                      \
+        if (inx) {                                                                            \
+            const float4 fl_ = ld4_stream(xflux + (lofs)), a_ = ld4_ro(xa + (lofs));          \
+            const float4 fo_ = ld4_ro(xfo + (lofs)), fn_ = ld4_ro(xfn + (lofs));              \
+            const float4 h_ = pml_pre4(a_, fo_, fl_, f4);                                     \
+            const float4 F_ = upd4(ca4, fl_, cb4, A, B, C, D);                                \
+            st4(xflux + (lofs), F_);                                                          \
+            f4 = pml_post4(fn_, F_, h_);                                                      \
+        } else f4 = upd4(ca4, f4, cb4, A, B, C, D);                                           \
+    } while (0)
+
 // E update: volt_n = vv_n volt_n + vi_n curl_n(curr)   (App. A1)
 //   x: ((Hz - Hz[j-1]) - Hy) + Hy[k-1]
 //   y: ((Hx - Hx[k-1]) - Hz) + Hz[i-1]
 //   z: ((Hy - Hy[i-1]) - Hx) + Hx[j-1]
-template <int TY, bool PML, bool CMP>
-__global__ void __launch_bounds__(32 * TY) update_e_kernel(const VolParams p, const RowParams r)
+template <int TY, int MODE, bool CMP>      // MODE 0 plain rows, 1 fused PML rows, 2 plain rows whose x-edge lanes are PML
+__global__ void __launch_bounds__(32 * TY, MODE ? 1 : (24 / TY > 0 ? 24 / TY : 1)) update_e_kernel(const VolParams p, const RowParams r)
 {
+    constexpr bool PML = MODE == 1;
     const int lane = threadIdx.x;
-    const int i0 = (blockIdx.x * 32 + lane) * 4;
+    const int chunk = MODE == 2 ? (blockIdx.x == 0 ? r.xc0 : (blockIdx.x == 1 ? r.xc1 : r.xc2)) : (int)blockIdx.x + r.xc_off;
+    const int i0 = (chunk * 32 + lane) * 4;
     const int j = r.j0 + blockIdx.y * TY + threadIdx.y;
     if (j >= r.j1) return;                                  // warp-uniform
-    if (!PML) {
+    if (MODE != 1) {
         if ((j >= r.sj0a && j < r.sj1a) || (j >= r.sj0b && j < r.sj1b)) return;
     }
     const bool act = i0 < p.px;
@@ -253,6 +277,16 @@ __global__ void __launch_bounds__(32 * TY) update_e_kernel(const VolParams p, co
     if (PML) {
         lsz = (long long)r.by * p.px; lcs = lsz * r.bz;
         lb = (long long)(kbeg - r.z0) * lsz + (long long)(j - r.y0) * p.px + i0;
+    }
+    bool inx = false;
+    float* xflux = nullptr; const float* xa = nullptr; const float* xfo = nullptr; const float* xfn = nullptr;
+    if (MODE == 2) {
+        const bool inlo = act && i0 < r.xw0, inhi = act && r.xw1 > 0 && i0 >= r.xx1;
+        inx = inlo || inhi;
+        const int w = inlo ? r.xw0 : r.xw1, x0 = inlo ? 0 : r.xx1;
+        xflux = inlo ? r.xflux0 : r.xflux1; xa = inlo ? r.xa0 : r.xa1; xfo = inlo ? r.xfo0 : r.xfo1; xfn = inlo ? r.xfn0 : r.xfn1;
+        lsz = (long long)r.by * w; lcs = lsz * r.bz;
+        lb = (long long)(kbeg - r.z0) * lsz + (long long)(j - r.y0) * w + (i0 - x0);
     }
 
     for (int k = kbeg; k < kend; ++k, base += sz, lb += lsz) {
@@ -281,6 +315,10 @@ __global__ void __launch_bounds__(32 * TY) update_e_kernel(const VolParams p, co
             PML_COMP(ex, ax, bx, hz, hz_jm, hy, hy_km, lb);
             PML_COMP(ey, ay, by, hx, hx_km, hz, hz_im, lcs + lb);
             PML_COMP(ez, az, bz, hy, hy_im, hx, hx_jm, 2 * lcs + lb);
+        } else if (MODE == 2) {
+            PML_COMP_X(ex, ax, bx, hz, hz_jm, hy, hy_km, lb);
+            PML_COMP_X(ey, ay, by, hx, hx_km, hz, hz_im, lcs + lb);
+            PML_COMP_X(ez, az, bz, hy, hy_im, hx, hx_jm, 2 * lcs + lb);
         } else {
             ex = upd4(ax, ex, bx, hz, hz_jm, hy, hy_km);
             ey = upd4(ay, ey, by, hx, hx_km, hz, hz_im);
@@ -297,14 +335,16 @@ __global__ void __launch_bounds__(32 * TY) update_e_kernel(const VolParams p, co
 //   x: ((Ez - Ez[j+1]) - Ey) + Ey[k+1]
 //   y: ((Ex - Ex[k+1]) - Ez) + Ez[i+1]
 //   z: ((Ey - Ey[i+1]) - Ex) + Ex[j+1]
-template <int TY, bool PML, bool CMP>
-__global__ void __launch_bounds__(32 * TY) update_h_kernel(const VolParams p, const RowParams r)
+template <int TY, int MODE, bool CMP>
+__global__ void __launch_bounds__(32 * TY, MODE ? 1 : (24 / TY > 0 ? 24 / TY : 1)) update_h_kernel(const VolParams p, const RowParams r)
 {
+    constexpr bool PML = MODE == 1;
     const int lane = threadIdx.x;
-    const int i0 = (blockIdx.x * 32 + lane) * 4;
+    const int chunk = MODE == 2 ? (blockIdx.x == 0 ? r.xc0 : (blockIdx.x == 1 ? r.xc1 : r.xc2)) : (int)blockIdx.x + r.xc_off;
+    const int i0 = (chunk * 32 + lane) * 4;
     const int j = r.j0 + blockIdx.y * TY + threadIdx.y;
     if (j >= r.j1) return;
-    if (!PML) {
+    if (MODE != 1) {
         if ((j >= r.sj0a && j < r.sj1a) || (j >= r.sj0b && j < r.sj1b)) return;
     }
     const bool act = i0 < p.px;
@@ -325,6 +365,16 @@ __global__ void __launch_bounds__(32 * TY) update_h_kernel(const VolParams p, co
     if (PML) {
         lsz = (long long)r.by * p.px; lcs = lsz * r.bz;
         lb = (long long)(kend - 1 - r.z0) * lsz + (long long)(j - r.y0) * p.px + i0;
+    }
+    bool inx = false;
+    float* xflux = nullptr; const float* xa = nullptr; const float* xfo = nullptr; const float* xfn = nullptr;
+    if (MODE == 2) {
+        const bool inlo = act && i0 < r.xw0, inhi = act && r.xw1 > 0 && i0 >= r.xx1;
+        inx = inlo || inhi;
+        const int w = inlo ? r.xw0 : r.xw1, x0 = inlo ? 0 : r.xx1;
+        xflux = inlo ? r.xflux0 : r.xflux1; xa = inlo ? r.xa0 : r.xa1; xfo = inlo ? r.xfo0 : r.xfo1; xfn = inlo ? r.xfn0 : r.xfn1;
+        lsz = (long long)r.by * w; lcs = lsz * r.bz;
+        lb = (long long)(kend - 1 - r.z0) * lsz + (long long)(j - r.y0) * w + (i0 - x0);
     }
 
     for (int k = kend - 1; k >= kbeg; --k, base -= sz, lb -= lsz) {
@@ -353,6 +403,10 @@ __global__ void __launch_bounds__(32 * TY) update_h_kernel(const VolParams p, co
             PML_COMP(hx, ax, bx, ez, ez_jp, ey, ey_kp, lb);
             PML_COMP(hy, ay, by, ex, ex_kp, ez, ez_ip, lcs + lb);
             PML_COMP(hz, az, bz, ey, ey_ip, ex, ex_jp, 2 * lcs + lb);
+        } else if (MODE == 2) {
+            PML_COMP_X(hx, ax, bx, ez, ez_jp, ey, ey_kp, lb);
+            PML_COMP_X(hy, ay, by, ex, ex_kp, ez, ez_ip, lcs + lb);
+            PML_COMP_X(hz, az, bz, ey, ey_ip, ex, ex_jp, 2 * lcs + lb);
         } else {
             hx = upd4(ax, hx, bx, ez, ez_jp, ey, ey_kp);
             hy = upd4(ay, hy, by, ex, ex_kp, ez, ez_ip);
@@ -365,10 +419,10 @@ __global__ void __launch_bounds__(32 * TY) update_h_kernel(const VolParams p, co
     }
 }
 
-template <bool PML>
-static int launch_volume_one(b200fdtd_ctx* c, int which, int k0, int k1, const RowParams& r, cudaStream_t stream, int kz)
+template <int MODE>
+static int launch_volume_one(b200fdtd_ctx* c, int which, int k0, int k1, const RowParams& r, cudaStream_t stream, int kz, int nchunks)
 {
-    if (k1 <= k0 || r.j1 <= r.j0) return 0;
+    if (k1 <= k0 || r.j1 <= r.j0 || nchunks <= 0) return 0;
     VolParams p;
     p.f = which == 0 ? c->volt : c->curr;
     p.g = which == 0 ? c->curr : c->volt;
@@ -378,15 +432,15 @@ static int launch_volume_one(b200fdtd_ctx* c, int which, int k0, int k1, const R
     p.kz = kz; p.k0 = k0; p.k1 = k1;
     const int ty = c->ty;
     dim3 block(32, ty);
-    dim3 grid((c->px + 127) / 128, (r.j1 - r.j0 + ty - 1) / ty, (k1 - k0 + kz - 1) / kz);
+    dim3 grid(nchunks, (r.j1 - r.j0 + ty - 1) / ty, (k1 - k0 + kz - 1) / kz);
     if (grid.y > 65535 || grid.z > 65535) return fail("grid too large for launch (ny/ty=%u, nz/kz=%u)", grid.y, grid.z);
     const bool cmp = c->cmp_meta[which] != nullptr && (c->variant & 4) == 0;
     p.xv = c->cmp_xv[which]; p.meta = c->cmp_meta[which];
 #define LAUNCH(TYV) do { \
-        if (which == 0) { if (cmp) update_e_kernel<TYV, PML, true><<<grid, block, 0, stream>>>(p, r); \
-                          else update_e_kernel<TYV, PML, false><<<grid, block, 0, stream>>>(p, r); } \
-        else { if (cmp) update_h_kernel<TYV, PML, true><<<grid, block, 0, stream>>>(p, r); \
-               else update_h_kernel<TYV, PML, false><<<grid, block, 0, stream>>>(p, r); } } while (0)
+        if (which == 0) { if (cmp) update_e_kernel<TYV, MODE, true><<<grid, block, 0, stream>>>(p, r); \
+                          else update_e_kernel<TYV, MODE, false><<<grid, block, 0, stream>>>(p, r); } \
+        else { if (cmp) update_h_kernel<TYV, MODE, true><<<grid, block, 0, stream>>>(p, r); \
+               else update_h_kernel<TYV, MODE, false><<<grid, block, 0, stream>>>(p, r); } } while (0)
     switch (ty) {
         case 1: LAUNCH(1); break;
         case 2: LAUNCH(2); break;
@@ -433,8 +487,47 @@ static int build_plan(b200fdtd_ctx* c)
         if (!(B.z0 == zlo && B.z0 + B.bz == zhi) || P.nskip >= 2) kind[b] = 0;
         else { P.sj0[P.nskip] = B.y0; P.sj1[P.nskip] = B.y0 + B.by; P.nskip++; }
     }
+    // narrow x-slabs: columns [0,w) or [x0,px), multiples of 4, spanning exactly the plain rows and planes
+    const int nchunks = (c->px + 127) / 128;
+    P.plain_c0 = 0; P.plain_nc = nchunks;
+    if (allow && (c->variant & 8) == 0) {
+        int ym0 = 0, ym1 = c->ny;
+        for (int q = 0; q < P.nskip; ++q) { if (P.sj0[q] == 0) ym0 = P.sj1[q]; else ym1 = P.sj0[q]; }
+        for (int b = 0; b < A.n; ++b) {
+            const PmlBoxDev& B = A.b[b];
+            if (kind[b] != 0) continue;
+            const bool shape = (B.x0 % 4 == 0) && (B.bx % 4 == 0) && B.y0 == ym0 && B.y0 + B.by == ym1 && B.z0 == zlo && B.z0 + B.bz == zhi;
+            const bool aligned = !(((uintptr_t)B.flux_v | (uintptr_t)B.flux_i | (uintptr_t)B.vv | (uintptr_t)B.vvfo | (uintptr_t)B.vvfn |
+                                    (uintptr_t)B.ii | (uintptr_t)B.iifo | (uintptr_t)B.iifn) & 15);
+            if (!shape || !aligned) continue;
+            FusedBox Fb; Fb.y0 = B.y0; Fb.by = B.by; Fb.z0 = B.z0; Fb.bz = B.bz;
+            Fb.flux_v = B.flux_v; Fb.flux_i = B.flux_i; Fb.vv = B.vv; Fb.vvfo = B.vvfo; Fb.vvfn = B.vvfn; Fb.ii = B.ii; Fb.iifo = B.iifo; Fb.iifn = B.iifn;
+            if (B.x0 == 0 && !P.has_lo && B.bx <= 128) { P.has_lo = 1; P.xlo = Fb; P.xw0 = B.bx; kind[b] = 3; }
+            else if (B.x0 > 0 && B.x0 + B.bx == c->px && !P.has_hi && B.bx <= 128 && (!P.has_lo || B.x0 >= P.xw0)) { P.has_hi = 1; P.xhi = Fb; P.xx1 = B.x0; P.xw1 = B.bx; kind[b] = 3; }
+        }
+        if (P.has_lo || P.has_hi) {
+            P.xedge = true;
+            bool edge[1 << 12]; const int nc = nchunks < (1 << 12) ? nchunks : (1 << 12);
+            for (int q = 0; q < nc; ++q) edge[q] = false;
+            if (P.has_lo) edge[0] = true;
+            if (P.has_hi) for (int q = P.xx1 / 128; q < nc; ++q) edge[q] = true;
+            P.nxc = 0; int first_plain = -1, last_plain = -1;
+            for (int q = 0; q < nc; ++q) {
+                if (edge[q]) { if (P.nxc < 3) P.xc[P.nxc] = q; P.nxc++; }
+                else { if (first_plain < 0) first_plain = q; last_plain = q; }
+            }
+            if (P.nxc > 3 || nchunks > (1 << 12)) {          // cannot happen for slabs <= 128 columns; keep the separate path
+                P.xedge = false; P.has_lo = P.has_hi = 0;
+                for (int b = 0; b < A.n; ++b) if (kind[b] == 3) kind[b] = 0;
+            } else {
+                P.plain_c0 = first_plain < 0 ? 0 : first_plain;
+                P.plain_nc = first_plain < 0 ? 0 : last_plain - first_plain + 1;
+            }
+        }
+    }
     for (int b = 0; b < A.n; ++b) {
         const PmlBoxDev& B = A.b[b];
+        if (kind[b] == 3) continue;
         if (kind[b] == 0 || P.nfused >= 4) {
             PmlBoxDev D = B; D.start = rest.total; rest.b[rest.n++] = D; rest.total += 3LL * B.bx * B.by * B.bz;
         } else {
@@ -460,9 +553,22 @@ static int launch_volume_plain(b200fdtd_ctx* c, int which, int k0, int k1, cudaS
     r.j0 = 0; r.j1 = c->ny;
     if (P.nskip > 0) { r.sj0a = P.sj0[0]; r.sj1a = P.sj1[0]; }
     if (P.nskip > 1) { r.sj0b = P.sj0[1]; r.sj1b = P.sj1[1]; }
+    r.xc_off = P.plain_c0;
     for (int s = 0; s < P.nseg; ++s) {
         const int a = k0 > P.seg0[s] ? k0 : P.seg0[s], b = k1 < P.seg1[s] ? k1 : P.seg1[s];
-        if (launch_volume_one<false>(c, which, a, b, r, stream, c->kz)) return 1;
+        if (launch_volume_one<0>(c, which, a, b, r, stream, c->kz, P.plain_nc)) return 1;
+        if (P.xedge) {
+            RowParams e = r;
+            e.xc0 = P.xc[0]; e.xc1 = P.xc[1]; e.xc2 = P.xc[2];
+            const FusedBox& L = P.xlo; const FusedBox& H = P.xhi;
+            const FusedBox& any = P.has_lo ? L : H;
+            e.y0 = any.y0; e.z0 = any.z0; e.by = any.by; e.bz = any.bz;
+            if (P.has_lo) { e.xflux0 = which == 0 ? L.flux_v : L.flux_i; e.xa0 = which == 0 ? L.vv : L.ii;
+                            e.xfo0 = which == 0 ? L.vvfo : L.iifo; e.xfn0 = which == 0 ? L.vvfn : L.iifn; e.xw0 = P.xw0; }
+            if (P.has_hi) { e.xflux1 = which == 0 ? H.flux_v : H.flux_i; e.xa1 = which == 0 ? H.vv : H.ii;
+                            e.xfo1 = which == 0 ? H.vvfo : H.iifo; e.xfn1 = which == 0 ? H.vvfn : H.iifn; e.xx1 = P.xx1; e.xw1 = P.xw1; }
+            if (launch_volume_one<2>(c, which, a, b, e, stream, c->kz, P.nxc)) return 1;
+        }
     }
     return 0;
 }
@@ -483,7 +589,7 @@ static int launch_volume_fused(b200fdtd_ctx* c, int which, int k0, int k1, cudaS
         const long long per_chunk = (long long)((c->px + 127) / 128) * ((B.by + c->ty - 1) / c->ty);
         int kz = c->kz;
         while (kz > 2 && per_chunk * ((b - a + kz - 1) / kz) < 148LL * 8) kz = (kz + 1) / 2;
-        if (launch_volume_one<true>(c, which, a, b, f, stream, kz)) return 1;
+        if (launch_volume_one<1>(c, which, a, b, f, stream, kz, (c->px + 127) / 128)) return 1;
     }
     return 0;
 }
@@ -1281,6 +1387,8 @@ extern "C" int b200fdtd_plan_info(b200fdtd_ctx* c, int64_t* plain_cells, int64_t
     for (int s = 0; s < P.nskip; ++s) skip += P.sj1[s] - P.sj0[s];
     for (int s = 0; s < P.nseg; ++s) planes += P.seg1[s] - P.seg0[s];
     for (int q = 0; q < P.nfused; ++q) fused += (int64_t)c->px * P.fb[q].by * P.fb[q].bz;
+    if (P.has_lo) fused += (int64_t)P.xw0 * P.xlo.by * P.xlo.bz;
+    if (P.has_hi) fused += (int64_t)P.xw1 * P.xhi.by * P.xhi.bz;
     for (int b = 0; b < c->pml.n; ++b) sep += (int64_t)c->pml.b[b].bx * c->pml.b[b].by * c->pml.b[b].bz;
     *plain_cells = (int64_t)c->px * (c->ny - skip) * planes;       // cells (incl. pad columns) swept by the plain launch
     *fused_cells = fused; *separate_cells = sep;

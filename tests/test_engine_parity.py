@@ -47,11 +47,12 @@ def test_volume_kernels_bit_exact(shape, tune):
 
 
 @pytest.mark.parametrize("use_graph", [False, True])
-@pytest.mark.parametrize("fused,variant", [(False, 0), (True, 0), (True, 1), (True, 2)])
+@pytest.mark.parametrize("fused,variant", [(False, 0), (True, 0), (True, 1), (True, 2), (True, 8)])
 def test_full_step_all_extensions(use_graph, fused, variant):
     """fused=True lays the PML out as whole-row slabs: variant 0 folds them into the volume kernels,
     variant 1 forces the separate pre/post passes, variant 2 keeps the fused launches on the main stream
-    (no side-stream fork); all must equal the oracle bit for bit"""
+    (no side-stream fork), variant 8 leaves the narrow x-slabs to the separate kernel (no x-edge launches);
+    all must equal the oracle bit for bit"""
     P = synth.make_problem(37, 29, 23, 40, seed=3, fused_pml=fused)
     R, G = _engines(P)
     G.set_tuning(kz=5, ty=4, variant=variant)
