@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--kz", type=int, default=0, help="tuning experiment: planes marched per CTA")
     ap.add_argument("--ty", type=int, default=0, help="tuning experiment: rows per CTA")
     ap.add_argument("--variant", type=int, default=0, help="tuning experiment: engine variant bits")
+    ap.add_argument("--no-align-x", action="store_true", help="tuning experiment: minimal (unaligned) x-slab PML boxes")
     ap.add_argument("--cpu-cells", type=float, default=12.5e6, help="cells of the CPU-baseline sample of the same scene")
     return ap.parse_args()
 
@@ -190,7 +191,8 @@ def run_b200(args):
     F, nf, port = build_scene(args, world, args.cells)
     S = F._setup()
     t0 = time.time()
-    sim = Simulation(S, device=local, rank=rank, world=world, nf2ff_freqs=F.nf2ff_freqs, probe_freqs=S.probe_freqs)
+    sim = Simulation(S, device=local, rank=rank, world=world, nf2ff_freqs=F.nf2ff_freqs, probe_freqs=S.probe_freqs,
+                     align_x_slabs=not args.no_align_x)
     sim.prepare()
     build_s = time.time() - t0
     E = sim.engine

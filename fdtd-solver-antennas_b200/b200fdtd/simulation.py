@@ -45,7 +45,7 @@ def _default_engine_factory(nx, ny, nz, px, device):
 
 class Simulation:
     def __init__(self, setup: Setup, device=0, rank=0, world=1, group=None, engine_factory=None,
-                 build_device=None, px_align=32, log=None, nf2ff_freqs=None, probe_freqs=None, align_x_slabs=False):
+                 build_device=None, px_align=32, log=None, nf2ff_freqs=None, probe_freqs=None, align_x_slabs=True):
         self.setup = setup
         self.rank, self.world, self.group = int(rank), int(world), group
         self.device = device
@@ -125,25 +125,19 @@ class Simulation:
             full_rows = ri[0] == 0 and ri[1] == nx
             if not full_rows and self.align_x_slabs:
                 # narrow x-slab widened to float4-aligned columns (the extra columns get the identity coefficients
-                # a = fo = fn = 1 that the formulas give outside the PML) so the x-edge launches can fold it in.
-                # Off by default: measured on patch100m the 160-register x-edge kernel costs more than the separate
-                # pre/post passes it replaces (2.42 vs 1.88 ms/step), see DESIGN.md.
+                # a = fo = fn = 1 that the formulas give outside the PML) so a narrow-slab launch of the volume kernel
+                # (csrc/b200fdtd.cu MODE 2) can own these columns instead of separate pre/post passes
                 ri = (0, min(nx, _round_up(ri[1], 4))) if ri[0] == 0 else ((ri[0] // 4) * 4, nx)
             co = B.pml_coefficients((ri, rj, (k0, k1)), dt)
             box = dict(x0=ri[0], y0=rj[0], z0=k0 - self.K0, bx=ri[1] - ri[0], by=rj[1] - rj[0], bz=k1 - k0)
-            if not full_rows and ri[1] == nx and self.px > nx:
-                co = {n: torch.nn.functional.pad(t, (0, self.px - nx)) for n, t in co.items()}
-                box["bx"] = self.px - ri[0]
-            elif not full_rows and ri[0] == 0 and box["bx"] % 4:
-                pad = _round_up(box["bx"], 4) - box["bx"]
+            if full_rows:
+                if self.px > nx:       # whole x-rows: pad to the row pitch so the volume kernels can fuse this slab (RowParams)
+                    co = {n: torch.nn.functional.pad(t, (0, self.px - nx)) for n, t in co.items()}
+                box["bx"] = self.px
+            elif self.align_x_slabs and box["bx"] % 4:
+                pad = _round_up(box["bx"], 4) - box["bx"]          # pad columns of the grid (i >= nx) or identity columns
                 co = {n: torch.nn.functional.pad(t, (0, pad)) for n, t in co.items()}
                 box["bx"] += pad
-            if full_rows and self.px > nx:
-                # whole x-rows: pad to the row pitch so the volume kernels can fuse this slab (RowParams)
-                co = {n: torch.nn.functional.pad(t, (0, self.px - nx)) for n, t in co.items()}
-                box["bx"] = self.px
-            elif full_rows:
-                box["bx"] = self.px
             box.update(co)
             self.pml_cells += box["bx"] * box["by"] * box["bz"]
             boxes.append(box)

@@ -63,8 +63,6 @@ struct VolumePlan {
     int nfused = 0; FusedBox fb[4];
     // narrow x-slabs folded into "x-edge" launches of the plain rows
     bool xedge = false; int has_lo = 0, has_hi = 0; FusedBox xlo{}, xhi{}; int xw0 = 0, xx1 = 0, xw1 = 0;
-    int nxc = 0, xc[3] = {0, 0, 0};              // x-chunks swept by the x-edge launch
-    int plain_c0 = 0, plain_nc = 0;              // x-chunks swept by the plain launch
 };
 
 struct FaceDev {
@@ -199,11 +197,11 @@ struct RowParams {
     float* flux;                    // fused slab arrays [3][bz][by][px] (PML launches only)
     const float* a; const float* fo; const float* fn;
     int y0, z0, by, bz;
-    // x-chunk selection: plain launches sweep chunks [xc_off, xc_off+gridDim.x); x-edge launches (MODE 2) sweep the
-    // listed chunks, whose lanes inside the narrow x-slabs do the PML pre/update/post and all other lanes the plain update
-    int xc_off, xc0, xc1, xc2;
-    float* xflux0; const float* xa0; const float* xfo0; const float* xfn0; int xw0;            // low x-slab: columns [0, xw0)
-    float* xflux1; const float* xa1; const float* xfo1; const float* xfn1; int xx1, xw1;       // high x-slab: columns [xx1, xx1+xw1)
+    // narrow x-slabs (columns [0,xw0) and [xx1,xx1+xw1), multiples of 4): the plain launch (MODE 0) does not store
+    // these columns; a narrow launch (MODE 2, blockIdx.x = slab) owns them: a warp covers xs float4 columns of 32/xs
+    // rows and does the PML pre/update/post like the fused row launch
+    float* xflux0; const float* xa0; const float* xfo0; const float* xfn0; int xw0, xs0;
+    float* xflux1; const float* xa1; const float* xfo1; const float* xfn1; int xx1, xw1, xs1;
 };
 
 __device__ __forceinline__ float4 pml_pre4(float4 a, float4 fo, float4 fl, float4 e) {
@@ -253,14 +251,29 @@ __global__ void __launch_bounds__(32 * TY, MODE ? 1 : (24 / TY > 0 ? 24 / TY : 1
 {
     constexpr bool PML = MODE == 1;
     const int lane = threadIdx.x;
-    const int chunk = MODE == 2 ? (blockIdx.x == 0 ? r.xc0 : (blockIdx.x == 1 ? r.xc1 : r.xc2)) : (int)blockIdx.x + r.xc_off;
-    const int i0 = (chunk * 32 + lane) * 4;
-    const int j = r.j0 + blockIdx.y * TY + threadIdx.y;
-    if (j >= r.j1) return;                                  // warp-uniform
-    if (MODE != 1) {
-        if ((j >= r.sj0a && j < r.sj1a) || (j >= r.sj0b && j < r.sj1b)) return;
+    int i0, j;
+    bool act;
+    // narrow-slab launch state (MODE 2)
+    const bool hi_slab = MODE == 2 && (blockIdx.x == 1 || r.xw0 == 0);
+    const int xw = hi_slab ? r.xw1 : r.xw0, xx0 = hi_slab ? r.xx1 : 0;
+    if (MODE == 2) {
+        const int xs = hi_slab ? r.xs1 : r.xs0;             // float4 slots per row (power of two), 32/xs rows per warp
+        const int c4 = lane & (xs - 1);
+        j = r.j0 + (blockIdx.y * TY + threadIdx.y) * (32 / xs) + lane / xs;
+        i0 = xx0 + c4 * 4;
+        if (j >= r.j1 || c4 * 4 >= xw) return;              // per lane (no warp collectives in this mode)
+        act = true;
+    } else {
+        i0 = (blockIdx.x * 32 + lane) * 4;
+        j = r.j0 + blockIdx.y * TY + threadIdx.y;
+        if (j >= r.j1) return;                              // warp-uniform
+        if (MODE == 0) {
+            if ((j >= r.sj0a && j < r.sj1a) || (j >= r.sj0b && j < r.sj1b)) return;
+        }
+        act = i0 < p.px;
     }
-    const bool act = i0 < p.px;
+    // plain launch: columns owned by a narrow-slab launch are computed but not stored
+    const bool own = MODE != 0 || !(i0 < r.xw0 || (i0 >= r.xx1 && i0 < r.xx1 + r.xw1));
     const int kbeg = p.k0 + blockIdx.z * p.kz;
     const int kend = min(kbeg + p.kz, p.k1);
     const long long cs = p.cs, sz = p.sz;
@@ -278,15 +291,12 @@ __global__ void __launch_bounds__(32 * TY, MODE ? 1 : (24 / TY > 0 ? 24 / TY : 1
         lsz = (long long)r.by * p.px; lcs = lsz * r.bz;
         lb = (long long)(kbeg - r.z0) * lsz + (long long)(j - r.y0) * p.px + i0;
     }
-    bool inx = false;
+    const bool inx = true;
     float* xflux = nullptr; const float* xa = nullptr; const float* xfo = nullptr; const float* xfn = nullptr;
     if (MODE == 2) {
-        const bool inlo = act && i0 < r.xw0, inhi = act && r.xw1 > 0 && i0 >= r.xx1;
-        inx = inlo || inhi;
-        const int w = inlo ? r.xw0 : r.xw1, x0 = inlo ? 0 : r.xx1;
-        xflux = inlo ? r.xflux0 : r.xflux1; xa = inlo ? r.xa0 : r.xa1; xfo = inlo ? r.xfo0 : r.xfo1; xfn = inlo ? r.xfn0 : r.xfn1;
-        lsz = (long long)r.by * w; lcs = lsz * r.bz;
-        lb = (long long)(kbeg - r.z0) * lsz + (long long)(j - r.y0) * w + (i0 - x0);
+        xflux = hi_slab ? r.xflux1 : r.xflux0; xa = hi_slab ? r.xa1 : r.xa0; xfo = hi_slab ? r.xfo1 : r.xfo0; xfn = hi_slab ? r.xfn1 : r.xfn0;
+        lsz = (long long)r.by * xw; lcs = lsz * r.bz;
+        lb = (long long)(kbeg - r.z0) * lsz + (long long)(j - r.y0) * xw + (i0 - xx0);
     }
 
     for (int k = kbeg; k < kend; ++k, base += sz, lb += lsz) {
@@ -304,10 +314,15 @@ __global__ void __launch_bounds__(32 * TY, MODE ? 1 : (24 / TY > 0 ? 24 / TY : 1
                 bx = ld4_ro(p.cb + base); by = ld4_ro(p.cb + cs + base); bz = ld4_ro(p.cb + 2 * cs + base);
             }
         }
-        if (edge_load) { hz_e = g[2 * cs + base - 1]; hy_e = g[cs + base - 1]; }
-        float hz_l = __shfl_up_sync(0xffffffffu, hz.w, 1);
-        float hy_l = __shfl_up_sync(0xffffffffu, hy.w, 1);
-        if (lane == 0) { hz_l = hz_e; hy_l = hy_e; }
+        float hz_l, hy_l;
+        if (MODE == 2) {
+            hz_l = i0 > 0 ? g[2 * cs + base - 1] : 0.f; hy_l = i0 > 0 ? g[cs + base - 1] : 0.f;
+        } else {
+            if (edge_load) { hz_e = g[2 * cs + base - 1]; hy_e = g[cs + base - 1]; }
+            hz_l = __shfl_up_sync(0xffffffffu, hz.w, 1);
+            hy_l = __shfl_up_sync(0xffffffffu, hy.w, 1);
+            if (lane == 0) { hz_l = hz_e; hy_l = hy_e; }
+        }
         const float4 hz_im = make_float4(hz_l, hz.x, hz.y, hz.z);
         const float4 hy_im = make_float4(hy_l, hy.x, hy.y, hy.z);
 
@@ -324,7 +339,7 @@ __global__ void __launch_bounds__(32 * TY, MODE ? 1 : (24 / TY > 0 ? 24 / TY : 1
             ey = upd4(ay, ey, by, hx, hx_km, hz, hz_im);
             ez = upd4(az, ez, bz, hy, hy_im, hx, hx_jm);
         }
-        if (act) {
+        if (act && own) {
             st4(f + base, ex); st4(f + cs + base, ey); st4(f + 2 * cs + base, ez);
         }
         hx_km = hx; hy_km = hy;
@@ -340,14 +355,29 @@ __global__ void __launch_bounds__(32 * TY, MODE ? 1 : (24 / TY > 0 ? 24 / TY : 1
 {
     constexpr bool PML = MODE == 1;
     const int lane = threadIdx.x;
-    const int chunk = MODE == 2 ? (blockIdx.x == 0 ? r.xc0 : (blockIdx.x == 1 ? r.xc1 : r.xc2)) : (int)blockIdx.x + r.xc_off;
-    const int i0 = (chunk * 32 + lane) * 4;
-    const int j = r.j0 + blockIdx.y * TY + threadIdx.y;
-    if (j >= r.j1) return;
-    if (MODE != 1) {
-        if ((j >= r.sj0a && j < r.sj1a) || (j >= r.sj0b && j < r.sj1b)) return;
+    int i0, j;
+    bool act;
+    // narrow-slab launch state (MODE 2)
+    const bool hi_slab = MODE == 2 && (blockIdx.x == 1 || r.xw0 == 0);
+    const int xw = hi_slab ? r.xw1 : r.xw0, xx0 = hi_slab ? r.xx1 : 0;
+    if (MODE == 2) {
+        const int xs = hi_slab ? r.xs1 : r.xs0;             // float4 slots per row (power of two), 32/xs rows per warp
+        const int c4 = lane & (xs - 1);
+        j = r.j0 + (blockIdx.y * TY + threadIdx.y) * (32 / xs) + lane / xs;
+        i0 = xx0 + c4 * 4;
+        if (j >= r.j1 || c4 * 4 >= xw) return;              // per lane (no warp collectives in this mode)
+        act = true;
+    } else {
+        i0 = (blockIdx.x * 32 + lane) * 4;
+        j = r.j0 + blockIdx.y * TY + threadIdx.y;
+        if (j >= r.j1) return;                              // warp-uniform
+        if (MODE == 0) {
+            if ((j >= r.sj0a && j < r.sj1a) || (j >= r.sj0b && j < r.sj1b)) return;
+        }
+        act = i0 < p.px;
     }
-    const bool act = i0 < p.px;
+    // plain launch: columns owned by a narrow-slab launch are computed but not stored
+    const bool own = MODE != 0 || !(i0 < r.xw0 || (i0 >= r.xx1 && i0 < r.xx1 + r.xw1));
     const int kbeg = p.k0 + blockIdx.z * p.kz;
     const int kend = min(kbeg + p.kz, p.k1);
     const long long cs = p.cs, sz = p.sz;
@@ -366,15 +396,12 @@ __global__ void __launch_bounds__(32 * TY, MODE ? 1 : (24 / TY > 0 ? 24 / TY : 1
         lsz = (long long)r.by * p.px; lcs = lsz * r.bz;
         lb = (long long)(kend - 1 - r.z0) * lsz + (long long)(j - r.y0) * p.px + i0;
     }
-    bool inx = false;
+    const bool inx = true;
     float* xflux = nullptr; const float* xa = nullptr; const float* xfo = nullptr; const float* xfn = nullptr;
     if (MODE == 2) {
-        const bool inlo = act && i0 < r.xw0, inhi = act && r.xw1 > 0 && i0 >= r.xx1;
-        inx = inlo || inhi;
-        const int w = inlo ? r.xw0 : r.xw1, x0 = inlo ? 0 : r.xx1;
-        xflux = inlo ? r.xflux0 : r.xflux1; xa = inlo ? r.xa0 : r.xa1; xfo = inlo ? r.xfo0 : r.xfo1; xfn = inlo ? r.xfn0 : r.xfn1;
-        lsz = (long long)r.by * w; lcs = lsz * r.bz;
-        lb = (long long)(kend - 1 - r.z0) * lsz + (long long)(j - r.y0) * w + (i0 - x0);
+        xflux = hi_slab ? r.xflux1 : r.xflux0; xa = hi_slab ? r.xa1 : r.xa0; xfo = hi_slab ? r.xfo1 : r.xfo0; xfn = hi_slab ? r.xfn1 : r.xfn0;
+        lsz = (long long)r.by * xw; lcs = lsz * r.bz;
+        lb = (long long)(kend - 1 - r.z0) * lsz + (long long)(j - r.y0) * xw + (i0 - xx0);
     }
 
     for (int k = kend - 1; k >= kbeg; --k, base -= sz, lb -= lsz) {
@@ -392,10 +419,15 @@ __global__ void __launch_bounds__(32 * TY, MODE ? 1 : (24 / TY > 0 ? 24 / TY : 1
                 bx = ld4_ro(p.cb + base); by = ld4_ro(p.cb + cs + base); bz = ld4_ro(p.cb + 2 * cs + base);
             }
         }
-        if (edge_load) { ez_e = g[2 * cs + base + 4]; ey_e = g[cs + base + 4]; }
-        float ez_r = __shfl_down_sync(0xffffffffu, ez.x, 1);
-        float ey_r = __shfl_down_sync(0xffffffffu, ey.x, 1);
-        if (last || !act) { ez_r = ez_e; ey_r = ey_e; }
+        float ez_r, ey_r;
+        if (MODE == 2) {
+            ez_r = i0 + 4 < p.px ? g[2 * cs + base + 4] : 0.f; ey_r = i0 + 4 < p.px ? g[cs + base + 4] : 0.f;
+        } else {
+            if (edge_load) { ez_e = g[2 * cs + base + 4]; ey_e = g[cs + base + 4]; }
+            ez_r = __shfl_down_sync(0xffffffffu, ez.x, 1);
+            ey_r = __shfl_down_sync(0xffffffffu, ey.x, 1);
+            if (last || !act) { ez_r = ez_e; ey_r = ey_e; }
+        }
         const float4 ez_ip = make_float4(ez.y, ez.z, ez.w, ez_r);
         const float4 ey_ip = make_float4(ey.y, ey.z, ey.w, ey_r);
 
@@ -412,7 +444,7 @@ __global__ void __launch_bounds__(32 * TY, MODE ? 1 : (24 / TY > 0 ? 24 / TY : 1
             hy = upd4(ay, hy, by, ex, ex_kp, ez, ez_ip);
             hz = upd4(az, hz, bz, ey, ey_ip, ex, ex_jp);
         }
-        if (act) {
+        if (act && own) {
             st4(f + base, hx); st4(f + cs + base, hy); st4(f + 2 * cs + base, hz);
         }
         ex_kp = ex; ey_kp = ey;
@@ -420,7 +452,7 @@ __global__ void __launch_bounds__(32 * TY, MODE ? 1 : (24 / TY > 0 ? 24 / TY : 1
 }
 
 template <int MODE>
-static int launch_volume_one(b200fdtd_ctx* c, int which, int k0, int k1, const RowParams& r, cudaStream_t stream, int kz, int nchunks)
+static int launch_volume_one(b200fdtd_ctx* c, int which, int k0, int k1, const RowParams& r, cudaStream_t stream, int kz, int nchunks, int grid_y = 0)
 {
     if (k1 <= k0 || r.j1 <= r.j0 || nchunks <= 0) return 0;
     VolParams p;
@@ -432,7 +464,7 @@ static int launch_volume_one(b200fdtd_ctx* c, int which, int k0, int k1, const R
     p.kz = kz; p.k0 = k0; p.k1 = k1;
     const int ty = c->ty;
     dim3 block(32, ty);
-    dim3 grid(nchunks, (r.j1 - r.j0 + ty - 1) / ty, (k1 - k0 + kz - 1) / kz);
+    dim3 grid(nchunks, grid_y > 0 ? grid_y : (r.j1 - r.j0 + ty - 1) / ty, (k1 - k0 + kz - 1) / kz);
     if (grid.y > 65535 || grid.z > 65535) return fail("grid too large for launch (ny/ty=%u, nz/kz=%u)", grid.y, grid.z);
     const bool cmp = c->cmp_meta[which] != nullptr && (c->variant & 4) == 0;
     p.xv = c->cmp_xv[which]; p.meta = c->cmp_meta[which];
@@ -487,43 +519,24 @@ static int build_plan(b200fdtd_ctx* c)
         if (!(B.z0 == zlo && B.z0 + B.bz == zhi) || P.nskip >= 2) kind[b] = 0;
         else { P.sj0[P.nskip] = B.y0; P.sj1[P.nskip] = B.y0 + B.by; P.nskip++; }
     }
-    // narrow x-slabs: columns [0,w) or [x0,px), multiples of 4, spanning exactly the plain rows and planes
-    const int nchunks = (c->px + 127) / 128;
-    P.plain_c0 = 0; P.plain_nc = nchunks;
+    // narrow x-slabs: float4-aligned column ranges [0,w) and [x0,x0+w), w <= 32, spanning exactly the plain rows and planes
     if (allow && (c->variant & 8) == 0) {
         int ym0 = 0, ym1 = c->ny;
         for (int q = 0; q < P.nskip; ++q) { if (P.sj0[q] == 0) ym0 = P.sj1[q]; else ym1 = P.sj0[q]; }
         for (int b = 0; b < A.n; ++b) {
             const PmlBoxDev& B = A.b[b];
             if (kind[b] != 0) continue;
-            const bool shape = (B.x0 % 4 == 0) && (B.bx % 4 == 0) && B.y0 == ym0 && B.y0 + B.by == ym1 && B.z0 == zlo && B.z0 + B.bz == zhi;
+            const bool shape = (B.x0 % 4 == 0) && (B.bx % 4 == 0) && B.bx <= 32 && B.x0 + B.bx <= c->px &&
+                               B.y0 == ym0 && B.y0 + B.by == ym1 && B.z0 == zlo && B.z0 + B.bz == zhi;
             const bool aligned = !(((uintptr_t)B.flux_v | (uintptr_t)B.flux_i | (uintptr_t)B.vv | (uintptr_t)B.vvfo | (uintptr_t)B.vvfn |
                                     (uintptr_t)B.ii | (uintptr_t)B.iifo | (uintptr_t)B.iifn) & 15);
             if (!shape || !aligned) continue;
             FusedBox Fb; Fb.y0 = B.y0; Fb.by = B.by; Fb.z0 = B.z0; Fb.bz = B.bz;
             Fb.flux_v = B.flux_v; Fb.flux_i = B.flux_i; Fb.vv = B.vv; Fb.vvfo = B.vvfo; Fb.vvfn = B.vvfn; Fb.ii = B.ii; Fb.iifo = B.iifo; Fb.iifn = B.iifn;
-            if (B.x0 == 0 && !P.has_lo && B.bx <= 128) { P.has_lo = 1; P.xlo = Fb; P.xw0 = B.bx; kind[b] = 3; }
-            else if (B.x0 > 0 && B.x0 + B.bx == c->px && !P.has_hi && B.bx <= 128 && (!P.has_lo || B.x0 >= P.xw0)) { P.has_hi = 1; P.xhi = Fb; P.xx1 = B.x0; P.xw1 = B.bx; kind[b] = 3; }
+            if (B.x0 == 0 && !P.has_lo && (!P.has_hi || B.bx <= P.xx1)) { P.has_lo = 1; P.xlo = Fb; P.xw0 = B.bx; kind[b] = 3; }
+            else if (B.x0 > 0 && !P.has_hi && (!P.has_lo || B.x0 >= P.xw0)) { P.has_hi = 1; P.xhi = Fb; P.xx1 = B.x0; P.xw1 = B.bx; kind[b] = 3; }
         }
-        if (P.has_lo || P.has_hi) {
-            P.xedge = true;
-            bool edge[1 << 12]; const int nc = nchunks < (1 << 12) ? nchunks : (1 << 12);
-            for (int q = 0; q < nc; ++q) edge[q] = false;
-            if (P.has_lo) edge[0] = true;
-            if (P.has_hi) for (int q = P.xx1 / 128; q < nc; ++q) edge[q] = true;
-            P.nxc = 0; int first_plain = -1, last_plain = -1;
-            for (int q = 0; q < nc; ++q) {
-                if (edge[q]) { if (P.nxc < 3) P.xc[P.nxc] = q; P.nxc++; }
-                else { if (first_plain < 0) first_plain = q; last_plain = q; }
-            }
-            if (P.nxc > 3 || nchunks > (1 << 12)) {          // cannot happen for slabs <= 128 columns; keep the separate path
-                P.xedge = false; P.has_lo = P.has_hi = 0;
-                for (int b = 0; b < A.n; ++b) if (kind[b] == 3) kind[b] = 0;
-            } else {
-                P.plain_c0 = first_plain < 0 ? 0 : first_plain;
-                P.plain_nc = first_plain < 0 ? 0 : last_plain - first_plain + 1;
-            }
-        }
+        P.xedge = P.has_lo || P.has_hi;
     }
     for (int b = 0; b < A.n; ++b) {
         const PmlBoxDev& B = A.b[b];
@@ -553,24 +566,45 @@ static int launch_volume_plain(b200fdtd_ctx* c, int which, int k0, int k1, cudaS
     r.j0 = 0; r.j1 = c->ny;
     if (P.nskip > 0) { r.sj0a = P.sj0[0]; r.sj1a = P.sj1[0]; }
     if (P.nskip > 1) { r.sj0b = P.sj0[1]; r.sj1b = P.sj1[1]; }
-    r.xc_off = P.plain_c0;
+    // columns owned by the narrow-slab launches are not stored by the plain launch
+    if (P.has_lo) r.xw0 = P.xw0;
+    if (P.has_hi) { r.xx1 = P.xx1; r.xw1 = P.xw1; } else { r.xx1 = 0; r.xw1 = 0; }
     for (int s = 0; s < P.nseg; ++s) {
         const int a = k0 > P.seg0[s] ? k0 : P.seg0[s], b = k1 < P.seg1[s] ? k1 : P.seg1[s];
-        if (launch_volume_one<0>(c, which, a, b, r, stream, c->kz, P.plain_nc)) return 1;
-        if (P.xedge) {
-            RowParams e = r;
-            e.xc0 = P.xc[0]; e.xc1 = P.xc[1]; e.xc2 = P.xc[2];
-            const FusedBox& L = P.xlo; const FusedBox& H = P.xhi;
-            const FusedBox& any = P.has_lo ? L : H;
-            e.y0 = any.y0; e.z0 = any.z0; e.by = any.by; e.bz = any.bz;
-            if (P.has_lo) { e.xflux0 = which == 0 ? L.flux_v : L.flux_i; e.xa0 = which == 0 ? L.vv : L.ii;
-                            e.xfo0 = which == 0 ? L.vvfo : L.iifo; e.xfn0 = which == 0 ? L.vvfn : L.iifn; e.xw0 = P.xw0; }
-            if (P.has_hi) { e.xflux1 = which == 0 ? H.flux_v : H.flux_i; e.xa1 = which == 0 ? H.vv : H.ii;
-                            e.xfo1 = which == 0 ? H.vvfo : H.iifo; e.xfn1 = which == 0 ? H.vvfn : H.iifn; e.xx1 = P.xx1; e.xw1 = P.xw1; }
-            if (launch_volume_one<2>(c, which, a, b, e, stream, c->kz, P.nxc)) return 1;
-        }
+        if (launch_volume_one<0>(c, which, a, b, r, stream, c->kz, (c->px + 127) / 128)) return 1;
     }
     return 0;
+}
+
+static int slots_for(int w) { int s = 1; while (s * 4 < w) s *= 2; return s; }
+
+// narrow x-slab launches (MODE 2): PML pre/update/post on the slab columns of the plain rows
+static int launch_volume_xslabs(b200fdtd_ctx* c, int which, int k0, int k1, cudaStream_t stream)
+{
+    const VolumePlan& P = c->plan;
+    if (!P.xedge) return 0;
+    RowParams e; memset(&e, 0, sizeof(e));
+    const FusedBox& L = P.xlo; const FusedBox& H = P.xhi;
+    const FusedBox& any = P.has_lo ? L : H;
+    e.j0 = any.y0; e.j1 = any.y0 + any.by;
+    e.y0 = any.y0; e.z0 = any.z0; e.by = any.by; e.bz = any.bz;
+    if (P.has_lo) { e.xflux0 = which == 0 ? L.flux_v : L.flux_i; e.xa0 = which == 0 ? L.vv : L.ii;
+                    e.xfo0 = which == 0 ? L.vvfo : L.iifo; e.xfn0 = which == 0 ? L.vvfn : L.iifn; e.xw0 = P.xw0; e.xs0 = slots_for(P.xw0); }
+    if (P.has_hi) { e.xflux1 = which == 0 ? H.flux_v : H.flux_i; e.xa1 = which == 0 ? H.vv : H.ii;
+                    e.xfo1 = which == 0 ? H.vvfo : H.iifo; e.xfn1 = which == 0 ? H.vvfn : H.iifn; e.xx1 = P.xx1; e.xw1 = P.xw1; e.xs1 = slots_for(P.xw1); }
+    const int a = k0 > any.z0 ? k0 : any.z0, b = k1 < any.z0 + any.bz ? k1 : any.z0 + any.bz;
+    if (b <= a) return 0;
+    // rows per CTA = ty * 32/xs: size the row grid for the slab with the fewest rows per warp
+    const int xs = (P.has_lo && P.has_hi) ? (e.xs0 > e.xs1 ? e.xs0 : e.xs1) : (P.has_lo ? e.xs0 : e.xs1);
+    RowParams g = e;
+    g.j1 = e.j1;                                             // kernel bounds rows by j1; grid.y from the widest slab
+    const int rows_per_cta = c->ty * (32 / xs);
+    const int gy = (any.by + rows_per_cta - 1) / rows_per_cta;
+    int kz = c->kz;
+    while (kz > 2 && (long long)gy * ((b - a + kz - 1) / kz) * (P.has_lo + P.has_hi) < 148LL * 8) kz = (kz + 1) / 2;
+    // launch_volume_one derives grid.y from (j1-j0)/ty: pass an equivalent row count
+    g.j0 = e.j0; 
+    return launch_volume_one<2>(c, which, a, b, g, stream, kz, P.has_lo + P.has_hi, gy);
 }
 
 // volume launches over the fused PML slabs (pre -> update -> post in registers)
@@ -600,6 +634,7 @@ static int launch_volume(b200fdtd_ctx* c, int which, int k0, int k1)
     if (!c->volt || !c->vv) return fail("fields/coefficients not bound");
     if (!c->plan.valid) if (build_plan(c)) return 1;
     if (launch_volume_plain(c, which, k0, k1, c->stream)) return 1;
+    if (launch_volume_xslabs(c, which, k0, k1, c->stream)) return 1;
     return launch_volume_fused(c, which, k0, k1, c->stream);
 }
 
@@ -1217,12 +1252,13 @@ static int launch_ts_add(b200fdtd_ctx* c, int n)
 static int e_half(b200fdtd_ctx* c, int off)
 {
     if (!c->plan.valid) if (build_plan(c)) return 1;
-    const bool side = c->plan.nfused > 0 && (c->variant & 2) == 0;
+    const bool side = (c->plan.nfused > 0 || c->plan.xedge) && (c->variant & 2) == 0;
     if (launch_mur(c, 0)) return 1;              // Mur sees the true field, before any PML pass swaps in the flux
-    if (side) { if (fork_side(c)) return 1; if (launch_volume_fused(c, 0, 0, c->nz, c->side)) return 1; }
+    if (side) { if (fork_side(c)) return 1; if (launch_volume_xslabs(c, 0, 0, c->nz, c->side)) return 1;
+                if (launch_volume_fused(c, 0, 0, c->nz, c->side)) return 1; }
     if (launch_pml(c, 0, 0)) return 1;
     if (launch_volume_plain(c, 0, 0, c->nz, c->stream)) return 1;
-    if (!side) if (launch_volume_fused(c, 0, 0, c->nz, c->stream)) return 1;
+    if (!side) { if (launch_volume_xslabs(c, 0, 0, c->nz, c->stream)) return 1; if (launch_volume_fused(c, 0, 0, c->nz, c->stream)) return 1; }
     if (launch_pml(c, 0, 1)) return 1;
     if (side) if (join_side(c)) return 1;
     if (launch_mur(c, 1)) return 1;
@@ -1233,11 +1269,12 @@ static int e_half(b200fdtd_ctx* c, int off)
 static int h_half(b200fdtd_ctx* c)
 {
     if (!c->plan.valid) if (build_plan(c)) return 1;
-    const bool side = c->plan.nfused > 0 && (c->variant & 2) == 0;
-    if (side) { if (fork_side(c)) return 1; if (launch_volume_fused(c, 1, 0, c->nz, c->side)) return 1; }
+    const bool side = (c->plan.nfused > 0 || c->plan.xedge) && (c->variant & 2) == 0;
+    if (side) { if (fork_side(c)) return 1; if (launch_volume_xslabs(c, 1, 0, c->nz, c->side)) return 1;
+                if (launch_volume_fused(c, 1, 0, c->nz, c->side)) return 1; }
     if (launch_pml(c, 1, 0)) return 1;
     if (launch_volume_plain(c, 1, 0, c->nz, c->stream)) return 1;
-    if (!side) if (launch_volume_fused(c, 1, 0, c->nz, c->stream)) return 1;
+    if (!side) { if (launch_volume_xslabs(c, 1, 0, c->nz, c->stream)) return 1; if (launch_volume_fused(c, 1, 0, c->nz, c->stream)) return 1; }
     if (launch_pml(c, 1, 1)) return 1;
     if (side) if (join_side(c)) return 1;
     return 0;

@@ -73,6 +73,11 @@ def install_mocks():
     pc = types.ModuleType("openEMS.physical_constants")
     pc.C0, pc.EPS0, pc.MUE0, pc.Z0 = C0, EPS0, MUE0, float(np.sqrt(MUE0 / EPS0))
     oe.physical_constants = pc
+    # the legacy backend also does `from openEMS import CSXCAD, nf2ff, ports, utilities, automesh`
+    # (antenna_sim/solver_fdtd_openems.py:117-124)
+    oe.CSXCAD = csx
+    for sub in ("nf2ff", "ports", "utilities", "automesh"):
+        setattr(oe, sub, types.ModuleType("openEMS." + sub))
     saved = {k: sys.modules.get(k) for k in ("CSXCAD", "openEMS", "openEMS.physical_constants")}
     sys.modules["CSXCAD"] = csx; sys.modules["openEMS"] = oe; sys.modules["openEMS.physical_constants"] = pc
     return saved
@@ -124,6 +129,22 @@ def main():
         assert prep.ok, prep.message
         out = dict(case=name, kwargs={k: str(v) for k, v in kw.items()}, log=Rec._log, fdtd=prep.FDTD._id, nf=prep.nf._id,
                    theta=prep.theta.tolist(), phi=prep.phi.tolist(), nf_center=prep.nf_center.tolist())
+        json.dump(out, open(os.path.join(HERE, name + ".json"), "w"))
+        print(name, len(Rec._log), "calls")
+    # sibling callers: tutorial-exact scene, E/H-cut microstrip variant, legacy int-BC backend
+    sib = refload.load(("solver_fdtd_openems",))
+    for name, fn in (("trace_fixed_tutorial", lambda: m["solver_fdtd_openems_fixed"].prepare_openems_patch_fixed(P, dll_dir=refload.DLL_DIR)),
+                     ("trace_microstrip_cuts", lambda: m["solver_fdtd_openems_microstrip"].prepare_openems_microstrip_patch(P, dll_dir=refload.DLL_DIR)),
+                     ("trace_legacy_intbc", lambda: sib["solver_fdtd_openems"].prepare_openems_patch(P, dll_dir=refload.DLL_DIR))):
+        saved = install_mocks()
+        try:
+            prep = fn()
+        finally:
+            restore(saved)
+        assert prep.ok, prep.message
+        out = dict(case=name, log=Rec._log, fdtd=prep.FDTD._id, nf=prep.nf._id,
+                   theta=np.asarray(prep.theta).tolist(), phi=np.asarray(prep.phi).tolist(),
+                   nf_center=(np.asarray(prep.nf_center).tolist() if getattr(prep, "nf_center", None) is not None else [0.0, 0.0, 0.0]))
         json.dump(out, open(os.path.join(HERE, name + ".json"), "w"))
         print(name, len(Rec._log), "calls")
     # multi-patch: 2 elements, quality 4, copper 35 um

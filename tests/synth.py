@@ -112,7 +112,7 @@ def make_problem(nx=37, ny=29, nz=23, px=40, seed=0, with_pml=True, with_mur=Tru
             # z-slabs over whole planes, y-slabs over whole rows of the planes in between (fused into the volume kernels),
             # plus narrow x-slabs for the separate pass
             layout = ((0, 0, 0, px, ny, 3), (0, 0, nz - 4, px, ny, 4), (0, 0, 3, px, 4, nz - 7), (0, ny - 5, 3, px, 5, nz - 7),
-                      (0, 4, 3, 8, ny - 9, nz - 7), ((nx - 6) // 4 * 4, 4, 3, px - (nx - 6) // 4 * 4, ny - 9, nz - 7))
+                      (0, 4, 3, 8, ny - 9, nz - 7), ((nx - 6) // 4 * 4, 4, 3, (nx - (nx - 6) // 4 * 4 + 3) // 4 * 4, ny - 9, nz - 7))
         else:
             layout = ((0, 0, 0, 5, ny, nz), (nx - 6, 0, 0, 6, ny, nz), (5, 0, 0, nx - 11, 4, nz), (5, 4, nz - 5, nx - 11, ny - 4, 5))
         for (x0, y0, z0, bx, by, bz) in layout:

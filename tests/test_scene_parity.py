@@ -59,11 +59,17 @@ def test_dipole_pml():
     assert 1.45 < out["cuda"]["dmax"] < 1.62
 
 
-@pytest.mark.parametrize("case,nrts", [("trace_single_mur_q1", 6000), ("trace_single_pml8_q3", 3000), ("trace_multi2_mur_q2", 1200)])
+@pytest.mark.parametrize("case,nrts", [("trace_single_mur_q1", 6000), ("trace_single_pml8_q3", 3000), ("trace_multi2_mur_q2", 1200),
+                                       ("trace_fixed_tutorial", 3000), ("trace_microstrip_cuts", 2000), ("trace_legacy_intbc", 1500)])
 def test_reference_scenes(case, nrts):
     """the reference's own scenes (recorded call traces of the unmodified prepare functions), both engines"""
     def build():
         R = replay.replay(case)
-        return R["FDTD"], R["nf"], R["FDTD"].ports[0], R["theta"][::5], R["phi"][::9], R["nf_center"]
+        th, ph = R["theta"], R["phi"]
+        if th.max() <= 2 * np.pi + 1e-9 and ph.max() <= 2 * np.pi + 1e-9 and len(th) > 8:
+            th, ph = np.rad2deg(th), np.rad2deg(ph)          # the legacy backend keeps radians (solver_fdtd_openems.py)
+        th = th[::5] if len(th) > 20 else th
+        ph = ph[::9] if len(ph) > 20 else ph
+        return R["FDTD"], R["nf"], R["FDTD"].ports[0], th, ph, R["nf_center"]
     out = _run_both(build, nrts, case)
     _check(out)
