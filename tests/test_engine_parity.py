@@ -142,3 +142,22 @@ def test_errors_are_reported_not_fatal():
         G.run(1)                                 # coefficients not bound
     with pytest.raises(B200FDTDError):
         G.set_excitation([10 ** 12], [1.0], [0], [0.0, 1.0])   # index out of range
+
+
+def test_degenerate_inputs():
+    """no extensions at all, zero steps, a single plane, pitch wider than the grid"""
+    from oracle.fdtd_ref import RefEngine
+    from b200fdtd.engine import Engine
+    for (nx, ny, nz, px) in ((9, 3, 1, 12), (4, 2, 2, 32), (33, 5, 2, 64)):
+        P = synth.make_problem(nx, ny, nz, px, seed=1, with_pml=False, with_mur=False, with_exc=False, with_probes=False, with_nf2ff=False)
+        R, G = _engines(P)
+        G.run(0); R.run(0)
+        _assert_fields_equal(R, G, "zero steps")
+        G.run(5, use_graph=True); R.run(5)
+        _assert_fields_equal(R, G, f"bare grid {nx}x{ny}x{nz}")
+        assert G.ts == 5 and G.num_samples == 0
+    # empty lists are accepted and switch the feature off
+    G = Engine(8, 8, 4, 8)
+    G.set_excitation([], [], [], [0.0])
+    G.set_mur([], [], [])
+    G.set_pml([])

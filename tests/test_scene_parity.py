@@ -73,3 +73,42 @@ def test_reference_scenes(case, nrts):
         return R["FDTD"], R["nf"], R["FDTD"].ports[0], th, ph, R["nf_center"]
     out = _run_both(build, nrts, case)
     _check(out)
+
+
+def test_config4_broadband_multi_frequency():
+    """BASELINE.json configs[3]: broadband 1-6 GHz pulse (f0 3.5 GHz, fc 2.5 GHz), running DFT of the port V/I at 501
+    points and of the NF2FF box at 11 frequencies, all on the device; compared with the oracle's double-precision DFTs"""
+    from b200fdtd import scenes as pscenes
+    nf_freqs = np.linspace(1e9, 6e9, 11)
+    pf = np.linspace(1e9, 6e9, 501)
+    out = {}
+    for eng in ("oracle", "cuda"):
+        (scenes.use_oracle_engine(threads=os.cpu_count() or 4) if eng == "oracle" else scenes.use_cuda_engine())
+        F, nf, port = pscenes.patch_scene(mesh_res_mm=5.0, boundary="PML_8", f0=3.5e9, fc=2.5e9, nrts=2500, end_criteria=1e-9,
+                                          nf2ff_freqs=nf_freqs)
+        F.port_dft_freqs = pf
+        path = scenes.tmp_sim_path(f"cfg4_{eng}")
+        F.Run(path, cleanup=True)
+        port.CalcPort(path, pf)                       # registered grid -> device running DFT on the CUDA engine
+        s11 = 20 * np.log10(np.abs(port.uf_ref / port.uf_inc))
+        theta, phi = np.arange(0.0, 181.0, 10.0), np.array([0.0, 90.0])
+        res = nf.CalcNF2FF(path, nf_freqs, theta, phi, center=[0, 0, 0.8e-3])
+        out[eng] = dict(s11=s11, dmax=np.array(res.Dmax), e=np.array(res.E_norm), used_dft=F.results["probes"]["port_ut_1"]["dft"] is not None)
+    scenes.use_cuda_engine()
+    o, c = out["oracle"], out["cuda"]
+    assert c["used_dft"]
+    assert np.abs(o["s11"] - c["s11"]).max() <= S11_TOL_DB
+    assert np.abs(10 * np.log10(o["dmax"]) - 10 * np.log10(c["dmax"])).max() <= GAIN_TOL_DB
+    for q in range(len(nf_freqs)):
+        eo, ec = o["e"][q], c["e"][q]
+        sel = eo > eo.max() * 10 ** (-30 / 20)
+        assert np.abs(20 * np.log10(ec[sel] / eo[sel])).max() <= GAIN_TOL_DB
+
+
+def test_calcnf2ff_rejects_unregistered_frequency():
+    scenes.use_cuda_engine()
+    F, nf, port = scenes.dipole("MUR", cells=(16, 16, 20), nrts=60, end=1e-12)
+    path = scenes.tmp_sim_path("unreg")
+    F.Run(path, cleanup=True)
+    with pytest.raises(ValueError):
+        nf.CalcNF2FF(path, 7.77e9, np.array([0.0]), np.array([0.0]))
