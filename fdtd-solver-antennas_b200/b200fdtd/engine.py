@@ -97,6 +97,7 @@ class Engine:
         assert mt.dtype == torch.uint8 and mt.numel() == (self.nz + 2) * self.ny * 32
         self._keep[f"cmp{which}"] = (xv, mt)
         nc, nd = C.c_int64(), C.c_int64()
+        self._pre()          # the verification kernel reads the coefficient arrays: order it after whatever filled them
         check(self.L.b200fdtd_set_row_compression(self.h, int(which), xv.shape[0], xv.data_ptr(), mt.data_ptr(),
                                                   C.byref(nc), C.byref(nd)))
         return nc.value, nd.value

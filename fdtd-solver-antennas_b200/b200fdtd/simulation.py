@@ -201,6 +201,61 @@ class Simulation:
         out[a - lo:b - lo] = arr[a:b]
         return out
 
+    # ------------------------------------------------------------------ compressed operator on the host
+    def export_operator(self, pin=True):
+        """Host copy of the operator in its compressed form: per pass the x-vector table, the 32-byte row records and the
+        rows that are not of the form scale*xvec (RowFactor).  ~0.1 % of the 48 B/cell of the full arrays."""
+        E = self.engine
+        out = {}
+        for which, (ca, cb) in enumerate(((E.vv, E.vi), (E.ii, E.iv))):
+            xv, meta = E._keep[f"cmp{which}"]                # device tensors after the device-side verification
+            ids = meta.view(self.nz + 2, self.ny, 32)[..., 24:30]
+            rows, slots = [], []
+            for slot in range(6):
+                arr = (ca, cb)[slot // 3][slot % 3]
+                full = (ids[..., slot] == 255) & (arr.abs().amax(-1) > 0)
+                idx = full.nonzero()
+                slots.append(idx)
+                rows.append(arr[idx[:, 0], idx[:, 1]])
+            H = dict(xvecs=xv.cpu(), meta=meta.cpu(), full_idx=[i.cpu() for i in slots], full_rows=[r.cpu() for r in rows])
+            if pin:
+                H = {k: ([t.pin_memory() for t in v] if isinstance(v, list) else v.pin_memory()) for k, v in H.items()}
+            out[which] = H
+        return out
+
+    @staticmethod
+    def operator_nbytes(op):
+        n = 0
+        for H in op.values():
+            for v in H.values():
+                n += sum(t.numel() * t.element_size() for t in v) if isinstance(v, list) else v.numel() * v.element_size()
+        return n
+
+    def load_operator(self, op):
+        """H2D of a compressed operator, expansion into the bound full arrays on the device, and (re)verification.
+        Returns (row-slots compressed, row-slots demoted) per pass."""
+        E = self.engine
+        dev = E.device
+        res = {}
+        for which, (ca, cb) in enumerate(((E.vv, E.vi), (E.ii, E.iv))):
+            H = op[which]
+            xv = H["xvecs"].to(dev, non_blocking=True)
+            meta = H["meta"].to(dev, non_blocking=True)
+            m = meta.view(self.nz + 2, self.ny, 32)
+            scales = m[..., :24].contiguous().view(torch.float32)       # [nzp, ny, 6]
+            ids = m[..., 24:30]
+            for slot in range(6):
+                arr = (ca, cb)[slot // 3][slot % 3]
+                idl = ids[..., slot].long()
+                comp = idl != 255
+                arr.copy_(torch.where(comp.unsqueeze(-1), scales[..., slot].unsqueeze(-1) * xv[idl.clamp(max=xv.shape[0] - 1)],
+                                      torch.zeros((), dtype=torch.float32, device=dev)))
+                idx = H["full_idx"][slot].to(dev, non_blocking=True)
+                if idx.numel():
+                    arr[idx[:, 0], idx[:, 1]] = H["full_rows"][slot].to(dev, non_blocking=True)
+            res[which] = E.set_row_compression(which, xv, meta)
+        return res
+
     # ------------------------------------------------------------------ halo exchange (z-slabs)
     # Data dependence (SURVEY.md §8e): the E update of my plane 0 reads (Hx,Hy) of the lower neighbour's top plane;
     # the H update of my top plane reads (Ex,Ey) of the upper neighbour's plane 0.  Planes are sent straight out of /
