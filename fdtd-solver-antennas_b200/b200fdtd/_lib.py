@@ -10,7 +10,7 @@ import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.normpath(os.path.join(_PKG, "..", "csrc"))
-SO_PATH = os.path.join(CSRC, "libb200fdtd.so")
+SO_PATH = os.environ.get("B200FDTD_LIB") or os.path.join(CSRC, "libb200fdtd.so")   # override: kernel experiments only
 INCLUDE = os.path.normpath(os.path.join(_PKG, "..", "..", "include"))
 
 c_f = C.POINTER(C.c_float)
@@ -24,7 +24,9 @@ class PmlBox(C.Structure):
     _fields_ = [("x0", C.c_int32), ("y0", C.c_int32), ("z0", C.c_int32),
                 ("bx", C.c_int32), ("by", C.c_int32), ("bz", C.c_int32),
                 ("flux_v", vp), ("flux_i", vp), ("vv", vp), ("vvfo", vp), ("vvfn", vp),
-                ("ii", vp), ("iifo", vp), ("iifn", vp)]
+                ("ii", vp), ("iifo", vp), ("iifn", vp),
+                ("xvecs_v", vp), ("meta_v", vp), ("nvec_v", C.c_int32),
+                ("xvecs_i", vp), ("meta_i", vp), ("nvec_i", C.c_int32)]
 
 
 class Nf2ffFace(C.Structure):
@@ -46,6 +48,7 @@ SYMBOLS = {
     "b200fdtd_set_excitation": (C.c_int, [vp, C.c_int64, c_i64, c_f, c_i32, c_f, C.c_int32]),
     "b200fdtd_set_mur": (C.c_int, [vp, C.c_int64, c_i64, c_i64, c_f]),
     "b200fdtd_set_pml": (C.c_int, [vp, C.c_int, C.POINTER(PmlBox)]),
+    "b200fdtd_pml_compression_info": (C.c_int, [vp, c_i64, c_i64]),
     "b200fdtd_set_probes": (C.c_int, [vp, C.c_int, c_i32, c_i64, c_i64, c_f, C.c_int, C.c_int, vp, C.c_int, c_d, vp, C.c_double]),
     "b200fdtd_set_nf2ff": (C.c_int, [vp, C.c_int, C.POINTER(Nf2ffFace), C.c_int, c_d, C.c_int, C.c_double,
                                      c_f, c_f, c_f, c_f, c_f, c_f]),

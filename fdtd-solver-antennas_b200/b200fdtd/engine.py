@@ -128,9 +128,23 @@ class Engine:
                 setattr(arr[b], n, int(B[n]))
             for n, t in d.items():
                 setattr(arr[b], n, t.data_ptr())
+            for kind in ("v", "i"):                       # optional row compression of the slab coefficients
+                cmp = B.get("cmp_" + kind)
+                if cmp is not None and cmp[0] is not None:
+                    xv = self._dev(cmp[0]).reshape(-1, shp[3]).contiguous()
+                    mt = cmp[1] if isinstance(cmp[1], torch.Tensor) else torch.from_numpy(np.ascontiguousarray(cmp[1], np.uint8))
+                    mt = mt.to(self.device).contiguous()
+                    assert mt.dtype == torch.uint8 and mt.numel() == shp[1] * shp[2] * 48
+                    d["xv_" + kind], d["meta_" + kind] = xv, mt
+                    setattr(arr[b], "xvecs_" + kind, xv.data_ptr()); setattr(arr[b], "meta_" + kind, mt.data_ptr())
+                    setattr(arr[b], "nvec_" + kind, int(xv.shape[0]))
         self._keep["pml"] = keep
         self.pml_arrays = keep
+        self._pre()              # the verification kernels read the slab arrays: order them after whatever filled them
         check(self.L.b200fdtd_set_pml(self.h, len(boxes), arr))
+        a, bb = C.c_int64(), C.c_int64()
+        check(self.L.b200fdtd_pml_compression_info(self.h, C.byref(a), C.byref(bb)))
+        self.pml_compression = (a.value, bb.value)
 
     def set_probes(self, kind, offset, idx, weight, interval, max_samples, freqs, dt):
         kind, offset = _np(kind, np.int32), _np(offset, np.int64)

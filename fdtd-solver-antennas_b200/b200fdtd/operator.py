@@ -100,16 +100,18 @@ class RowFactor:
     float32 coefficients are DEFINED as fl32(fl32(scale) * fl32(xvec[i])) (instead of rounding the float64 value
     directly; the two differ by at most one unit in the last place), so that the CUDA kernels can rebuild the row
     from 32 bytes of metadata and a cached x-vector and still be bit-identical to a run from the full arrays."""
-    TOL = 1e-9
+    TOL = 1e-11
     MAX_VECS = 250
 
-    def __init__(self, nx, px, nzp, ny, dev):
+    def __init__(self, nx, px, nzp, ny, dev, nslots=6, rec_bytes=32):
+        """nslots scales + nslots ids per row record of rec_bytes (operator passes: 6 / 32; PML slabs: 9 / 48)"""
         self.nx, self.px, self.dev = nx, px, dev
+        self.nslots, self.id0 = nslots, 4 * nslots
         self.vec32 = []                                   # shared table of this pass
-        self.slots = [[] for _ in range(6)]               # per slot: list of (global id, xref float64 [nx])
-        self.meta_f = torch.zeros((nzp, ny, 8), dtype=torch.float32, device=dev)
-        self.meta_u8 = self.meta_f.view(torch.uint8)      # [nzp, ny, 32]
-        self.meta_u8[:, :, 24:30] = 255
+        self.slots = [[] for _ in range(nslots)]          # per slot: list of (global id, xref float64 [nx])
+        self.meta_f = torch.zeros((nzp, ny, rec_bytes // 4), dtype=torch.float32, device=dev)
+        self.meta_u8 = self.meta_f.view(torch.uint8)      # [nzp, ny, rec_bytes]
+        self.meta_u8[:, :, self.id0:self.id0 + nslots] = 255
         self.rows_total = 0
         self.rows_compressed = 0
 
@@ -152,7 +154,7 @@ class RowFactor:
                 prod = sc32.unsqueeze(-1) * table[ids.clamp(max=len(self.vec32) - 1)]    # float32 multiply, IEEE rn
                 out = torch.where(m.unsqueeze(-1), prod, out)
         self.meta_f[plane0:plane0 + nk, :, slot] = sc32
-        self.meta_u8[plane0:plane0 + nk, :, 24 + slot] = ids.to(torch.uint8)
+        self.meta_u8[plane0:plane0 + nk, :, self.id0 + slot] = ids.to(torch.uint8)
         self.rows_total += nk * ny
         self.rows_compressed += int((ids != 255).sum())
         return out
@@ -538,24 +540,32 @@ class OperatorBuilder:
             self.row_compression_stats = {0: (fE.rows_compressed, fE.rows_total), 1: (fH.rows_compressed, fH.rows_total)}
         return vv, vi, ii, iv
 
-    def pml_coefficients(self, box, dt):
-        """second-stage UPML coefficients of one box ((i0,i1),(j0,j1),(k0,k1)); float32 [3][bz][by][bx] each"""
+    def pml_coefficients(self, box, dt, pad_to=None, compress=False):
+        """second-stage UPML coefficients of one box ((i0,i1),(j0,j1),(k0,k1)); float32 [3][bz][by][bx] each, bx padded
+        with zero columns to pad_to.  With compress=True the rows are factorised like the operator rows (RowFactor,
+        9 slots: a_xyz, fo_xyz, fn_xyz) and the tables are returned as 'cmp_v' / 'cmp_i' = (xvecs, records)."""
         ec = self.ec_block(box)
+        bx = box[0][1] - box[0][0]; by = box[1][1] - box[1][0]; bz = box[2][1] - box[2][0]
+        bxp = int(pad_to) if pad_to else bx
         names = ("vv", "vvfo", "vvfn", "ii", "iifo", "iifn")
-        out = {n: [] for n in names}
+        out = {n: torch.zeros((3, bz, by, bxp), dtype=torch.float32, device=self.dev) for n in names}
+        fac = [RowFactor(bx, bxp, bz, by, self.dev, nslots=9, rec_bytes=48) if compress else None for _ in range(2)]
         for comp in range(3):
             nPP = (comp + 2) % 3
-            for kind, (a, fo, fn) in ((0, ("vv", "vvfo", "vvfn")), (1, ("ii", "iifo", "iifn"))):
+            for kind, trip in ((0, ("vv", "vvfo", "vvfn")), (1, ("ii", "iifo", "iifn"))):
                 r = self._rates(comp, box, ec, kind)
                 base = ec["C"][comp] if kind == 0 else ec["invL"][comp]
                 zero = torch.zeros_like(base)
                 rn = r[comp] if r[comp] is not None else zero
                 rpp = r[nPP] if r[nPP] is not None else zero
                 den = 2.0 + dt * rpp
-                out[a].append(((2.0 - dt * rpp) / den).to(torch.float32))
-                out[fo].append(((2.0 - dt * rn) / den).to(torch.float32))
-                out[fn].append(((2.0 + dt * rn) / den).to(torch.float32))
-        return {n: torch.stack(v) for n, v in out.items()}
+                vals = ((2.0 - dt * rpp) / den, (2.0 - dt * rn) / den, (2.0 + dt * rn) / den)
+                for q, (name, v64) in enumerate(zip(trip, vals)):
+                    v64 = v64 + zero                                   # broadcast to the full block
+                    out[name][comp, :, :, :bx] = fac[kind].factor(v64, 3 * q + comp, 0) if compress else v64.to(torch.float32)
+        if compress:
+            out["cmp_v"], out["cmp_i"] = fac[0].tables(), fac[1].tables()
+        return out
 
     # ------------------------------------------------------------------ narrow-band lists (global indices)
     def excitation_list(self, dt):

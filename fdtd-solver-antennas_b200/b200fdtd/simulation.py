@@ -45,7 +45,7 @@ def _default_engine_factory(nx, ny, nz, px, device):
 
 class Simulation:
     def __init__(self, setup: Setup, device=0, rank=0, world=1, group=None, engine_factory=None,
-                 build_device=None, px_align=32, log=None, nf2ff_freqs=None, probe_freqs=None, align_x_slabs=True):
+                 build_device=None, px_align=32, log=None, nf2ff_freqs=None, probe_freqs=None, align_x_slabs=True, compress_pml=True):
         self.setup = setup
         self.rank, self.world, self.group = int(rank), int(world), group
         self.device = device
@@ -54,6 +54,7 @@ class Simulation:
         self.build_device = build_device       # None: chosen in prepare() from the slab size
         self.px_align = px_align
         self.align_x_slabs = bool(align_x_slabs)
+        self.compress_pml = bool(compress_pml)
         self.nf2ff_freqs = None if nf2ff_freqs is None else np.atleast_1d(np.asarray(nf2ff_freqs, np.float64))
         self.probe_freqs = None if probe_freqs is None else np.atleast_1d(np.asarray(probe_freqs, np.float64))
         self.engine = None
@@ -132,16 +133,16 @@ class Simulation:
                 # a = fo = fn = 1 that the formulas give outside the PML) so a narrow-slab launch of the volume kernel
                 # (csrc/b200fdtd.cu MODE 2) can own these columns instead of separate pre/post passes
                 ri = (0, min(nx, _round_up(ri[1], 4))) if ri[0] == 0 else ((ri[0] // 4) * 4, nx)
-            co = B.pml_coefficients((ri, rj, (k0, k1)), dt)
-            box = dict(x0=ri[0], y0=rj[0], z0=k0 - self.K0, bx=ri[1] - ri[0], by=rj[1] - rj[0], bz=k1 - k0)
+            bx = ri[1] - ri[0]
             if full_rows:
-                if self.px > nx:       # whole x-rows: pad to the row pitch so the volume kernels can fuse this slab (RowParams)
-                    co = {n: torch.nn.functional.pad(t, (0, self.px - nx)) for n, t in co.items()}
-                box["bx"] = self.px
-            elif self.align_x_slabs and box["bx"] % 4:
-                pad = _round_up(box["bx"], 4) - box["bx"]          # pad columns of the grid (i >= nx) or identity columns
-                co = {n: torch.nn.functional.pad(t, (0, pad)) for n, t in co.items()}
-                box["bx"] += pad
+                bxp = self.px              # whole x-rows: padded to the row pitch so the volume kernels can fuse this slab
+            elif self.align_x_slabs:
+                bxp = _round_up(bx, 4)     # pad columns of the grid (i >= nx) or identity columns
+            else:
+                bxp = bx
+            fusable = full_rows or self.align_x_slabs
+            co = B.pml_coefficients((ri, rj, (k0, k1)), dt, pad_to=bxp, compress=fusable and self.compress_pml)
+            box = dict(x0=ri[0], y0=rj[0], z0=k0 - self.K0, bx=bxp, by=rj[1] - rj[0], bz=k1 - k0)
             box.update(co)
             self.pml_cells += box["bx"] * box["by"] * box["bz"]
             boxes.append(box)

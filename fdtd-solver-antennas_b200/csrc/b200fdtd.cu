@@ -39,7 +39,7 @@ static int fail(const char* fmt, ...) {
     if (e_ != cudaSuccess) return fail("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 
 extern "C" const char* b200fdtd_last_error(void) { return g_err; }
-extern "C" int b200fdtd_version(void) { return 1; }
+extern "C" int b200fdtd_version(void) { return 2; }
 extern "C" int64_t b200fdtd_launch_count(void) { return g_launches.load(); }
 
 // ------------------------------------------------------------------------------------
@@ -50,12 +50,15 @@ struct PmlBoxDev {
     long long start;               // first flat element of this box in the concatenated space
     float *flux_v, *flux_i;
     const float *vv, *vvfo, *vvfn, *ii, *iifo, *iifn;
+    const float *xv_v, *xv_i;                  // row compression of the slab coefficients (optional)
+    const unsigned char *meta_v, *meta_i;
 };
 #define MAX_PML_BOXES 8
 struct PmlTable { int n; long long total; PmlBoxDev b[MAX_PML_BOXES]; };
 
 // launch plan of the volume kernels: PML boxes spanning whole x-rows are fused into the volume launches
-struct FusedBox { int y0, by, z0, bz; float *flux_v, *flux_i; const float *vv, *vvfo, *vvfn, *ii, *iifo, *iifn; };
+struct FusedBox { int y0, by, z0, bz; float *flux_v, *flux_i; const float *vv, *vvfo, *vvfn, *ii, *iifo, *iifn;
+                  const float *xv_v, *xv_i; const unsigned char *meta_v, *meta_i; };
 struct VolumePlan {
     bool valid = false;
     int nseg = 0; int seg0[3], seg1[3];          // plane ranges of the plain launches (complement of fused z-slabs)
@@ -94,6 +97,7 @@ struct b200fdtd_ctx {
     // mur
     int64_t n_mur = 0; int64_t *mur_dst = nullptr, *mur_src = nullptr; float *mur_coeff = nullptr, *mur_tmp = nullptr;
     // pml: all boxes as given, the boxes left to the separate pre/post passes, and the fused launch plan
+    int64_t pml_rows_compressed = 0, pml_rows_demoted = 0;
     PmlTable pml_all{};
     PmlTable pml{};
     VolumePlan plan{};
@@ -196,12 +200,14 @@ struct RowParams {
     int sj0a, sj1a, sj0b, sj1b;     // rows that belong to fused y-slabs (skipped by the plain launch; empty ranges if none)
     float* flux;                    // fused slab arrays [3][bz][by][px] (PML launches only)
     const float* a; const float* fo; const float* fn;
+    const float* pxv; const unsigned char* pmeta;   // row compression of a/fo/fn (48-byte records per slab row) or NULL
     int y0, z0, by, bz;
     // narrow x-slabs (columns [0,xw0) and [xx1,xx1+xw1), multiples of 4): the plain launch (MODE 0) does not store
     // these columns; a narrow launch (MODE 2, blockIdx.x = slab) owns them: a warp covers xs float4 columns of 32/xs
     // rows and does the PML pre/update/post like the fused row launch
     float* xflux0; const float* xa0; const float* xfo0; const float* xfn0; int xw0, xs0;
     float* xflux1; const float* xa1; const float* xfo1; const float* xfn1; int xx1, xw1, xs1;
+    const float* pxv0; const unsigned char* pmeta0; const float* pxv1; const unsigned char* pmeta1;
 };
 
 __device__ __forceinline__ float4 pml_pre4(float4 a, float4 fo, float4 fl, float4 e) {
@@ -217,29 +223,67 @@ __device__ __forceinline__ float4 pml_post4(float4 fn, float4 F, float4 h) {
     return make_float4(__fmaf_rn(fn.x, F.x, h.x), __fmaf_rn(fn.y, F.y, h.y), __fmaf_rn(fn.z, F.z, h.z), __fmaf_rn(fn.w, F.w, h.w));
 }
 
+// Slab coefficient rows are compressible exactly like the operator rows (a, fo, fn are products of 1-D PML profiles):
+// 48-byte record per slab row = 9 scales (a_xyz, fo_xyz, fn_xyz) + 9 vector ids; the x-vectors have the slab's row width.
+struct PmlRowMeta { float sc[9]; unsigned char id[9]; unsigned char pad[3]; };
+
+__device__ __forceinline__ float4 pcoef4(unsigned id, float sc, const float* full, const float* __restrict__ xv, int col, int w)
+{
+    if (id != ROW_FULL) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(xv + (size_t)id * w + col));
+        return make_float4(__fmul_rn(sc, v.x), __fmul_rn(sc, v.y), __fmul_rn(sc, v.z), __fmul_rn(sc, v.w));
+    }
+    return __ldcs(reinterpret_cast<const float4*>(full));
+}
+
+// the three PML coefficients of component c4 (0..2) of the current slab row; PM_ = row record or NULL
+#define PML_COEFFS(c4, PA, PFO, PFN, PXV, COL, W, lofs)                                                         \
+    float4 a_, fo_, fn_;                                                                                        \
+    if (pm_ != nullptr) {                                                                                       \
+        a_ = pcoef4(pid_[c4], psc_[c4], (PA) + (lofs), PXV, COL, W);                                            \
+        fo_ = pcoef4(pid_[3 + c4], psc_[3 + c4], (PFO) + (lofs), PXV, COL, W);                                  \
+        fn_ = pcoef4(pid_[6 + c4], psc_[6 + c4], (PFN) + (lofs), PXV, COL, W);                                  \
+    } else { a_ = ld4_ro((PA) + (lofs)); fo_ = ld4_ro((PFO) + (lofs)); fn_ = ld4_ro((PFN) + (lofs)); }
+
+// load the row record into registers (row-uniform in MODE 1, per lane in MODE 2)
+#define PML_ROW_META(PMETA, ROW)                                                                                \
+    const unsigned char* pm_ = (PMETA) ? (PMETA) + (long long)(ROW) * 48 : nullptr;                             \
+    float psc_[9]; unsigned pid_[9];                                                                            \
+    if (pm_ != nullptr) {                                                                                       \
+        const float4 q0_ = __ldg(reinterpret_cast<const float4*>(pm_)), q1_ = __ldg(reinterpret_cast<const float4*>(pm_) + 1), \
+                     q2_ = __ldg(reinterpret_cast<const float4*>(pm_) + 2);                                     \
+        psc_[0] = q0_.x; psc_[1] = q0_.y; psc_[2] = q0_.z; psc_[3] = q0_.w;                                     \
+        psc_[4] = q1_.x; psc_[5] = q1_.y; psc_[6] = q1_.z; psc_[7] = q1_.w; psc_[8] = q2_.x;                    \
+        const unsigned w0_ = __float_as_uint(q2_.y), w1_ = __float_as_uint(q2_.z), w2_ = __float_as_uint(q2_.w); \
+        pid_[0] = w0_ & 255u; pid_[1] = (w0_ >> 8) & 255u; pid_[2] = (w0_ >> 16) & 255u; pid_[3] = w0_ >> 24;   \
+        pid_[4] = w1_ & 255u; pid_[5] = (w1_ >> 8) & 255u; pid_[6] = (w1_ >> 16) & 255u; pid_[7] = w1_ >> 24;   \
+        pid_[8] = w2_ & 255u;                                                                                   \
+    }
+
 // one component of a fused PML row: pre, update, post.  f4 holds the field on entry and the new field on exit.
-#define PML_COMP(f4, ca4, cb4, A, B, C, D, lofs)                                              \
+#define PML_COMP(c4, f4, ca4, cb4, A, B, C, D, lofs)                                          \
     do {                                                                                      \
-        float4 fl_ = zero4(), a_ = zero4(), fo_ = zero4(), fn_ = zero4();                     \
-        if (act) { fl_ = ld4_stream(r.flux + (lofs)); a_ = ld4_ro(r.a + (lofs));              \
-                   fo_ = ld4_ro(r.fo + (lofs)); fn_ = ld4_ro(r.fn + (lofs)); }                 \
-        const float4 h_ = pml_pre4(a_, fo_, fl_, f4);                                         \
-        const float4 F_ = upd4(ca4, fl_, cb4, A, B, C, D);                                    \
+        float4 fl_ = zero4();                                                                 \
+        float4 h_ = zero4(), F_ = zero4(), fnn_ = zero4();                                    \
+        if (act) {                                                                            \
+            fl_ = ld4_stream(r.flux + (lofs));                                                \
+            PML_COEFFS(c4, r.a, r.fo, r.fn, r.pxv, i0, p.px, lofs)                            \
+            h_ = pml_pre4(a_, fo_, fl_, f4); fnn_ = fn_;                                      \
+        }                                                                                     \
+        F_ = upd4(ca4, fl_, cb4, A, B, C, D);                                                 \
         if (act) st4(r.flux + (lofs), F_);                                                    \
-        f4 = pml_post4(fn_, F_, h_);                                                          \
+        f4 = pml_post4(fnn_, F_, h_);                                                         \
     } while (0)
 
-// the same with explicit slab pointers and a per-lane predicate (x-edge launches)
-#define PML_COMP_X(f4, ca4, cb4, A, B, C, D, lofs)                                            \
+// the same with explicit slab pointers (narrow x-slab launches: every lane is inside its slab)
+#define PML_COMP_X(c4, f4, ca4, cb4, A, B, C, D, lofs)                                        \
     do {                                                                                      \
-        if (inx) {                                                                            \
-            const float4 fl_ = ld4_stream(xflux + (lofs)), a_ = ld4_ro(xa + (lofs));          \
-            const float4 fo_ = ld4_ro(xfo + (lofs)), fn_ = ld4_ro(xfn + (lofs));              \
-            const float4 h_ = pml_pre4(a_, fo_, fl_, f4);                                     \
-            const float4 F_ = upd4(ca4, fl_, cb4, A, B, C, D);                                \
-            st4(xflux + (lofs), F_);                                                          \
-            f4 = pml_post4(fn_, F_, h_);                                                      \
-        } else f4 = upd4(ca4, f4, cb4, A, B, C, D);                                           \
+        const float4 fl_ = ld4_stream(xflux + (lofs));                                        \
+        PML_COEFFS(c4, xa, xfo, xfn, xpxv, i0 - xx0, xw, lofs)                                \
+        const float4 h_ = pml_pre4(a_, fo_, fl_, f4);                                         \
+        const float4 F_ = upd4(ca4, fl_, cb4, A, B, C, D);                                    \
+        st4(xflux + (lofs), F_);                                                              \
+        f4 = pml_post4(fn_, F_, h_);                                                          \
     } while (0)
 
 // E update: volt_n = vv_n volt_n + vi_n curl_n(curr)   (App. A1)
@@ -291,10 +335,11 @@ __global__ void __launch_bounds__(32 * TY, MODE ? 1 : (24 / TY > 0 ? 24 / TY : 1
         lsz = (long long)r.by * p.px; lcs = lsz * r.bz;
         lb = (long long)(kbeg - r.z0) * lsz + (long long)(j - r.y0) * p.px + i0;
     }
-    const bool inx = true;
     float* xflux = nullptr; const float* xa = nullptr; const float* xfo = nullptr; const float* xfn = nullptr;
+    const float* xpxv = nullptr; const unsigned char* xpmeta = nullptr;
     if (MODE == 2) {
         xflux = hi_slab ? r.xflux1 : r.xflux0; xa = hi_slab ? r.xa1 : r.xa0; xfo = hi_slab ? r.xfo1 : r.xfo0; xfn = hi_slab ? r.xfn1 : r.xfn0;
+        xpxv = hi_slab ? r.pxv1 : r.pxv0; xpmeta = hi_slab ? r.pmeta1 : r.pmeta0;
         lsz = (long long)r.by * xw; lcs = lsz * r.bz;
         lb = (long long)(kbeg - r.z0) * lsz + (long long)(j - r.y0) * xw + (i0 - xx0);
     }
@@ -327,13 +372,15 @@ __global__ void __launch_bounds__(32 * TY, MODE ? 1 : (24 / TY > 0 ? 24 / TY : 1
         const float4 hy_im = make_float4(hy_l, hy.x, hy.y, hy.z);
 
         if (PML) {
-            PML_COMP(ex, ax, bx, hz, hz_jm, hy, hy_km, lb);
-            PML_COMP(ey, ay, by, hx, hx_km, hz, hz_im, lcs + lb);
-            PML_COMP(ez, az, bz, hy, hy_im, hx, hx_jm, 2 * lcs + lb);
+            PML_ROW_META(r.pmeta, (long long)(k - r.z0) * r.by + (j - r.y0))
+            PML_COMP(0, ex, ax, bx, hz, hz_jm, hy, hy_km, lb);
+            PML_COMP(1, ey, ay, by, hx, hx_km, hz, hz_im, lcs + lb);
+            PML_COMP(2, ez, az, bz, hy, hy_im, hx, hx_jm, 2 * lcs + lb);
         } else if (MODE == 2) {
-            PML_COMP_X(ex, ax, bx, hz, hz_jm, hy, hy_km, lb);
-            PML_COMP_X(ey, ay, by, hx, hx_km, hz, hz_im, lcs + lb);
-            PML_COMP_X(ez, az, bz, hy, hy_im, hx, hx_jm, 2 * lcs + lb);
+            PML_ROW_META(xpmeta, (long long)(k - r.z0) * r.by + (j - r.y0))
+            PML_COMP_X(0, ex, ax, bx, hz, hz_jm, hy, hy_km, lb);
+            PML_COMP_X(1, ey, ay, by, hx, hx_km, hz, hz_im, lcs + lb);
+            PML_COMP_X(2, ez, az, bz, hy, hy_im, hx, hx_jm, 2 * lcs + lb);
         } else {
             ex = upd4(ax, ex, bx, hz, hz_jm, hy, hy_km);
             ey = upd4(ay, ey, by, hx, hx_km, hz, hz_im);
@@ -396,10 +443,11 @@ __global__ void __launch_bounds__(32 * TY, MODE ? 1 : (24 / TY > 0 ? 24 / TY : 1
         lsz = (long long)r.by * p.px; lcs = lsz * r.bz;
         lb = (long long)(kend - 1 - r.z0) * lsz + (long long)(j - r.y0) * p.px + i0;
     }
-    const bool inx = true;
     float* xflux = nullptr; const float* xa = nullptr; const float* xfo = nullptr; const float* xfn = nullptr;
+    const float* xpxv = nullptr; const unsigned char* xpmeta = nullptr;
     if (MODE == 2) {
         xflux = hi_slab ? r.xflux1 : r.xflux0; xa = hi_slab ? r.xa1 : r.xa0; xfo = hi_slab ? r.xfo1 : r.xfo0; xfn = hi_slab ? r.xfn1 : r.xfn0;
+        xpxv = hi_slab ? r.pxv1 : r.pxv0; xpmeta = hi_slab ? r.pmeta1 : r.pmeta0;
         lsz = (long long)r.by * xw; lcs = lsz * r.bz;
         lb = (long long)(kend - 1 - r.z0) * lsz + (long long)(j - r.y0) * xw + (i0 - xx0);
     }
@@ -432,13 +480,15 @@ __global__ void __launch_bounds__(32 * TY, MODE ? 1 : (24 / TY > 0 ? 24 / TY : 1
         const float4 ey_ip = make_float4(ey.y, ey.z, ey.w, ey_r);
 
         if (PML) {
-            PML_COMP(hx, ax, bx, ez, ez_jp, ey, ey_kp, lb);
-            PML_COMP(hy, ay, by, ex, ex_kp, ez, ez_ip, lcs + lb);
-            PML_COMP(hz, az, bz, ey, ey_ip, ex, ex_jp, 2 * lcs + lb);
+            PML_ROW_META(r.pmeta, (long long)(k - r.z0) * r.by + (j - r.y0))
+            PML_COMP(0, hx, ax, bx, ez, ez_jp, ey, ey_kp, lb);
+            PML_COMP(1, hy, ay, by, ex, ex_kp, ez, ez_ip, lcs + lb);
+            PML_COMP(2, hz, az, bz, ey, ey_ip, ex, ex_jp, 2 * lcs + lb);
         } else if (MODE == 2) {
-            PML_COMP_X(hx, ax, bx, ez, ez_jp, ey, ey_kp, lb);
-            PML_COMP_X(hy, ay, by, ex, ex_kp, ez, ez_ip, lcs + lb);
-            PML_COMP_X(hz, az, bz, ey, ey_ip, ex, ex_jp, 2 * lcs + lb);
+            PML_ROW_META(xpmeta, (long long)(k - r.z0) * r.by + (j - r.y0))
+            PML_COMP_X(0, hx, ax, bx, ez, ez_jp, ey, ey_kp, lb);
+            PML_COMP_X(1, hy, ay, by, ex, ex_kp, ez, ez_ip, lcs + lb);
+            PML_COMP_X(2, hz, az, bz, ey, ey_ip, ex, ex_jp, 2 * lcs + lb);
         } else {
             hx = upd4(ax, hx, bx, ez, ez_jp, ey, ey_kp);
             hy = upd4(ay, hy, by, ex, ex_kp, ez, ez_ip);
@@ -533,6 +583,7 @@ static int build_plan(b200fdtd_ctx* c)
             if (!shape || !aligned) continue;
             FusedBox Fb; Fb.y0 = B.y0; Fb.by = B.by; Fb.z0 = B.z0; Fb.bz = B.bz;
             Fb.flux_v = B.flux_v; Fb.flux_i = B.flux_i; Fb.vv = B.vv; Fb.vvfo = B.vvfo; Fb.vvfn = B.vvfn; Fb.ii = B.ii; Fb.iifo = B.iifo; Fb.iifn = B.iifn;
+            Fb.xv_v = B.xv_v; Fb.xv_i = B.xv_i; Fb.meta_v = B.meta_v; Fb.meta_i = B.meta_i;
             if (B.x0 == 0 && !P.has_lo && (!P.has_hi || B.bx <= P.xx1)) { P.has_lo = 1; P.xlo = Fb; P.xw0 = B.bx; kind[b] = 3; }
             else if (B.x0 > 0 && !P.has_hi && (!P.has_lo || B.x0 >= P.xw0)) { P.has_hi = 1; P.xhi = Fb; P.xx1 = B.x0; P.xw1 = B.bx; kind[b] = 3; }
         }
@@ -548,6 +599,7 @@ static int build_plan(b200fdtd_ctx* c)
             Fb.y0 = B.y0; Fb.by = B.by; Fb.z0 = B.z0; Fb.bz = B.bz;
             Fb.flux_v = B.flux_v; Fb.flux_i = B.flux_i; Fb.vv = B.vv; Fb.vvfo = B.vvfo; Fb.vvfn = B.vvfn;
             Fb.ii = B.ii; Fb.iifo = B.iifo; Fb.iifn = B.iifn;
+            Fb.xv_v = B.xv_v; Fb.xv_i = B.xv_i; Fb.meta_v = B.meta_v; Fb.meta_i = B.meta_i;
         }
     }
     P.nseg = 0;
@@ -589,9 +641,11 @@ static int launch_volume_xslabs(b200fdtd_ctx* c, int which, int k0, int k1, cuda
     e.j0 = any.y0; e.j1 = any.y0 + any.by;
     e.y0 = any.y0; e.z0 = any.z0; e.by = any.by; e.bz = any.bz;
     if (P.has_lo) { e.xflux0 = which == 0 ? L.flux_v : L.flux_i; e.xa0 = which == 0 ? L.vv : L.ii;
-                    e.xfo0 = which == 0 ? L.vvfo : L.iifo; e.xfn0 = which == 0 ? L.vvfn : L.iifn; e.xw0 = P.xw0; e.xs0 = slots_for(P.xw0); }
+                    e.xfo0 = which == 0 ? L.vvfo : L.iifo; e.xfn0 = which == 0 ? L.vvfn : L.iifn; e.xw0 = P.xw0; e.xs0 = slots_for(P.xw0);
+                    if ((c->variant & 16) == 0) { e.pxv0 = which == 0 ? L.xv_v : L.xv_i; e.pmeta0 = which == 0 ? L.meta_v : L.meta_i; if (!e.pxv0) e.pmeta0 = nullptr; } }
     if (P.has_hi) { e.xflux1 = which == 0 ? H.flux_v : H.flux_i; e.xa1 = which == 0 ? H.vv : H.ii;
-                    e.xfo1 = which == 0 ? H.vvfo : H.iifo; e.xfn1 = which == 0 ? H.vvfn : H.iifn; e.xx1 = P.xx1; e.xw1 = P.xw1; e.xs1 = slots_for(P.xw1); }
+                    e.xfo1 = which == 0 ? H.vvfo : H.iifo; e.xfn1 = which == 0 ? H.vvfn : H.iifn; e.xx1 = P.xx1; e.xw1 = P.xw1; e.xs1 = slots_for(P.xw1);
+                    if ((c->variant & 16) == 0) { e.pxv1 = which == 0 ? H.xv_v : H.xv_i; e.pmeta1 = which == 0 ? H.meta_v : H.meta_i; if (!e.pxv1) e.pmeta1 = nullptr; } }
     const int a = k0 > any.z0 ? k0 : any.z0, b = k1 < any.z0 + any.bz ? k1 : any.z0 + any.bz;
     if (b <= a) return 0;
     // rows per CTA = ty * 32/xs: size the row grid for the slab with the fewest rows per warp
@@ -617,6 +671,7 @@ static int launch_volume_fused(b200fdtd_ctx* c, int which, int k0, int k1, cudaS
         f.j0 = B.y0; f.j1 = B.y0 + B.by; f.y0 = B.y0; f.z0 = B.z0; f.by = B.by; f.bz = B.bz;
         f.flux = which == 0 ? B.flux_v : B.flux_i;
         f.a = which == 0 ? B.vv : B.ii; f.fo = which == 0 ? B.vvfo : B.iifo; f.fn = which == 0 ? B.vvfn : B.iifn;
+        if ((c->variant & 16) == 0) { f.pxv = which == 0 ? B.xv_v : B.xv_i; f.pmeta = which == 0 ? B.meta_v : B.meta_i; if (!f.pxv) f.pmeta = nullptr; }
         const int a = k0 > B.z0 ? k0 : B.z0, b = k1 < B.z0 + B.bz ? k1 : B.z0 + B.bz;
         if (b <= a) continue;
         // thin slabs: march fewer planes per CTA so the launch still fills the machine (>= ~8 CTAs per SM)
@@ -1082,6 +1137,56 @@ extern "C" int b200fdtd_set_mur(b200fdtd_ctx* c, int64_t n, const int64_t* dst, 
     return 0;
 }
 
+// one warp per (slab row, slot): compressed slab rows must reproduce the full coefficient arrays bit for bit
+__global__ void __launch_bounds__(256) verify_pml_rows_kernel(unsigned char* __restrict__ meta, const float* __restrict__ xv, int nvec,
+        const float* __restrict__ a, const float* __restrict__ fo, const float* __restrict__ fn, int bx, int by, int bz,
+        unsigned long long* __restrict__ counts)
+{
+    const long long w = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const long long nrows = (long long)bz * by;
+    if (w >= nrows * 9) return;
+    const int slot = (int)(w % 9);
+    const long long row = w / 9;
+    PmlRowMeta* M = reinterpret_cast<PmlRowMeta*>(meta + row * 48);
+    const unsigned id = M->id[slot];
+    if (id == ROW_FULL) return;
+    bool ok = id < (unsigned)nvec;
+    if (ok) {
+        const float sc = M->sc[slot];
+        const float* full = (slot < 3 ? a : (slot < 6 ? fo : fn)) + ((long long)(slot % 3) * nrows + row) * bx;
+        const float* v = xv + (size_t)id * bx;
+        for (int i = lane; i < bx; i += 32)
+            if (__float_as_uint(__fmul_rn(sc, v[i])) != __float_as_uint(full[i])) ok = false;
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    if (lane == 0) {
+        if (!ok) { M->id[slot] = (unsigned char)ROW_FULL; atomicAdd(&counts[0], 1ULL); }
+        else atomicAdd(&counts[1], 1ULL);
+    }
+}
+
+static int verify_pml_rows(b200fdtd_ctx* c, const b200fdtd_pml_box& B, int which)
+{
+    unsigned long long* d_counts = nullptr;
+    CK(cudaMalloc((void**)&d_counts, 2 * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(d_counts, 0, 2 * sizeof(unsigned long long), c->stream));
+    const long long warps = (long long)B.bz * B.by * 9;
+    const long long blocks = (warps * 32 + 255) / 256;
+    verify_pml_rows_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>((unsigned char*)(which == 0 ? B.meta_v : B.meta_i),
+        which == 0 ? B.xvecs_v : B.xvecs_i, which == 0 ? B.nvec_v : B.nvec_i,
+        which == 0 ? B.vv : B.ii, which == 0 ? B.vvfo : B.iifo, which == 0 ? B.vvfn : B.iifn, B.bx, B.by, B.bz, d_counts);
+    g_launches.fetch_add(1);
+    cudaError_t e = cudaGetLastError();
+    unsigned long long h[2] = {0, 0};
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, d_counts, sizeof(h), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_counts);
+    if (e != cudaSuccess) return fail("PML row compression verification failed: %s", cudaGetErrorString(e));
+    c->pml_rows_compressed += (int64_t)h[1]; c->pml_rows_demoted += (int64_t)h[0];
+    return 0;
+}
+
 extern "C" int b200fdtd_set_pml(b200fdtd_ctx* c, int nboxes, const b200fdtd_pml_box* boxes)
 {
     if (!c) return fail("NULL ctx");
@@ -1089,6 +1194,7 @@ extern "C" int b200fdtd_set_pml(b200fdtd_ctx* c, int nboxes, const b200fdtd_pml_
     CK(cudaSetDevice(c->device));
     drop_graph(c);
     PmlTable t; memset(&t, 0, sizeof(t));
+    c->pml_rows_compressed = c->pml_rows_demoted = 0;
     t.n = nboxes; long long start = 0;
     for (int b = 0; b < nboxes; ++b) {
         const b200fdtd_pml_box& B = boxes[b];
@@ -1099,6 +1205,15 @@ extern "C" int b200fdtd_set_pml(b200fdtd_ctx* c, int nboxes, const b200fdtd_pml_
         PmlBoxDev& D = t.b[b];
         D.x0 = B.x0; D.y0 = B.y0; D.z0 = B.z0; D.bx = B.bx; D.by = B.by; D.bz = B.bz; D.start = start;
         D.flux_v = B.flux_v; D.flux_i = B.flux_i; D.vv = B.vv; D.vvfo = B.vvfo; D.vvfn = B.vvfn; D.ii = B.ii; D.iifo = B.iifo; D.iifn = B.iifn;
+        D.xv_v = D.xv_i = nullptr; D.meta_v = D.meta_i = nullptr;
+        if (B.nvec_v > 0 && B.xvecs_v && B.meta_v && B.bx % 4 == 0 && !(((uintptr_t)B.xvecs_v | (uintptr_t)B.meta_v) & 15)) {
+            if (verify_pml_rows(c, B, 0)) return 1;
+            D.xv_v = B.xvecs_v; D.meta_v = (const unsigned char*)B.meta_v;
+        }
+        if (B.nvec_i > 0 && B.xvecs_i && B.meta_i && B.bx % 4 == 0 && !(((uintptr_t)B.xvecs_i | (uintptr_t)B.meta_i) & 15)) {
+            if (verify_pml_rows(c, B, 1)) return 1;
+            D.xv_i = B.xvecs_i; D.meta_i = (const unsigned char*)B.meta_i;
+        }
         start += 3LL * B.bx * B.by * B.bz;
     }
     t.total = start;
@@ -1429,6 +1544,13 @@ extern "C" int b200fdtd_plan_info(b200fdtd_ctx* c, int64_t* plain_cells, int64_t
     for (int b = 0; b < c->pml.n; ++b) sep += (int64_t)c->pml.b[b].bx * c->pml.b[b].by * c->pml.b[b].bz;
     *plain_cells = (int64_t)c->px * (c->ny - skip) * planes;       // cells (incl. pad columns) swept by the plain launch
     *fused_cells = fused; *separate_cells = sep;
+    return 0;
+}
+
+extern "C" int b200fdtd_pml_compression_info(b200fdtd_ctx* c, int64_t* rows_compressed, int64_t* rows_demoted)
+{
+    if (!c || !rows_compressed || !rows_demoted) return fail("NULL argument");
+    *rows_compressed = c->pml_rows_compressed; *rows_demoted = c->pml_rows_demoted;
     return 0;
 }
 

@@ -64,7 +64,7 @@ int b200fdtd_set_row_compression(b200fdtd_ctx* ctx, int which, int nvec, const f
                                  int64_t* n_compressed /*host out, may be NULL*/, int64_t* n_demoted /*host out, may be NULL*/);
 /* tuning knobs of the volume kernels: planes marched per CTA (kz), rows per CTA (ty in {2,4,8}),
  * variant bits: 1 = PML slabs by the separate pre/post kernel instead of fused rows, 2 = no side stream,
- * 4 = ignore the row compression */
+ * 4 = ignore the row compression, 8 = narrow x-slabs by the separate kernel, 16 = ignore the PML slab compression */
 int b200fdtd_set_tuning(b200fdtd_ctx* ctx, int kz, int ty, int variant);
 
 /* ---- excitation (openEMS Engine_Ext_Excitation::Apply2Voltages; AddLumpedPort's
@@ -92,8 +92,17 @@ typedef struct {
     const float* ii;               /* dev same three for the currents                    */
     const float* iifo;
     const float* iifn;
+    /* optional lossless row compression of the slab coefficients (like b200fdtd_set_row_compression): x-vector
+     * tables dev [nvec][bx] and writable records dev [bz*by][48 bytes] = { float scale[9]; uint8 vec_id[9]; pad[3] },
+     * slots a_x,a_y,a_z, fo_xyz, fn_xyz (a = vv|ii ...); vec_id 255 = stream the row from the full array.  Claims are
+     * verified on the device; needs bx % 4 == 0.  Leave NULL / 0 to stream everything. */
+    const float* xvecs_v; void* meta_v; int32_t nvec_v;
+    const float* xvecs_i; void* meta_i; int32_t nvec_i;
 } b200fdtd_pml_box;
 int b200fdtd_set_pml(b200fdtd_ctx* ctx, int nboxes, const b200fdtd_pml_box* boxes /*host*/);
+
+/* slab rows (row x slot) whose compression was accepted / demoted by the device-side check in the last set_pml */
+int b200fdtd_pml_compression_info(b200fdtd_ctx* ctx, int64_t* rows_compressed, int64_t* rows_demoted);
 
 /* ---- probes: voltage line integrals / current loop integrals, their time series
  *      and a running DFT (AddLumpedPort's port_ut/port_it probes; CalcPort,
