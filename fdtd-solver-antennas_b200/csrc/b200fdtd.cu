@@ -82,8 +82,17 @@ struct b200fdtd_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaStream_t side = nullptr;           // runs the fused PML slab launches concurrently with the plain launch
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t side_lo = nullptr, side_hi = nullptr;   // the same at default / highest priority (variant bit 32 picks)
+    cudaStream_t side2 = nullptr;          // whole-row slab launches (z/y) while `side` runs the narrow x-slab launch
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
     float *volt = nullptr, *curr = nullptr;
+    // second copy of the fields for the fused H->E launches (they cannot update in place: a CTA recomputes the halo of its
+    // tile from the old values its neighbours are overwriting).  vcur/ccur say which copy holds the current E / H; both are
+    // 0 whenever control returns to the caller, so the bound arrays always hold the state.
+    float *alt_volt = nullptr, *alt_curr = nullptr;
+    int vcur = 0, ccur = 0;
+    bool flip = false;                     // volume launches write the other copy instead of updating in place
+    int he_ty = 7, he_kz = 32;             // fused launch: rows per CTA (+1 halo row), planes marched per CTA
     const float *vv = nullptr, *vi = nullptr, *ii = nullptr, *iv = nullptr;
     int kz = 16, ty = 4, variant = 0;
     const float* cmp_xv[2] = {nullptr, nullptr};          // row compression tables of the E and H pass (caller-owned)
@@ -117,6 +126,11 @@ struct b200fdtd_ctx {
     PmlTable* d_pml = nullptr; FaceTable* d_faces = nullptr;
 };
 
+static float* cur_volt(const b200fdtd_ctx* c) { return c->vcur ? c->alt_volt : c->volt; }
+static float* oth_volt(const b200fdtd_ctx* c) { return c->vcur ? c->volt : c->alt_volt; }
+static float* cur_curr(const b200fdtd_ctx* c) { return c->ccur ? c->alt_curr : c->curr; }
+static float* oth_curr(const b200fdtd_ctx* c) { return c->ccur ? c->curr : c->alt_curr; }
+
 static int sample_interval(const b200fdtd_ctx* c) {
     if (c->n_probes > 0 && c->interval > 0) return c->interval;
     if (c->faces.n > 0 && c->nf_interval > 0) return c->nf_interval;
@@ -127,7 +141,8 @@ static int sample_interval(const b200fdtd_ctx* c) {
 // volume kernels (K1 E update, K2 H update)
 // ------------------------------------------------------------------------------------
 struct VolParams {
-    float* __restrict__ f;          // field updated in place (volt for E, curr for H)
+    float* __restrict__ f;          // updated field is written here (volt for E, curr for H)
+    const float* fin;               // ... and read from here (== f: in place; the other copy in a ping-pong step)
     const float* __restrict__ g;    // the other field (read only in this pass)
     const float* __restrict__ ca;   // vv / ii
     const float* __restrict__ cb;   // vi / iv
@@ -160,6 +175,7 @@ __device__ __forceinline__ float4 coef4(unsigned id, float sc, const float* full
 #define LOAD_COEFFS_CMP()                                                                                   \
     do {                                                                                                    \
         const float4* m_ = reinterpret_cast<const float4*>(p.meta + ((long long)(k + 1) * p.ny + j) * 32);  \
+        prefetch_l1(p.meta + ((long long)(k + 1 + KSTEP) * p.ny + j) * 32);   /* next plane's record: ghost planes exist */ \
         const float4 m0_ = __ldg(m_), m1_ = __ldg(m_ + 1);                                                  \
         const unsigned w0_ = __float_as_uint(m1_.z), w1_ = __float_as_uint(m1_.w);                          \
         ax = coef4(w0_ & 255u, m0_.x, p.ca + base, p.xv, i0, p.px);                                         \
@@ -171,9 +187,13 @@ __device__ __forceinline__ float4 coef4(unsigned id, float sc, const float* full
     } while (0)
 
 
+// the row records steer dependent loads: pulling the next plane's record into L1 one iteration ahead keeps the march
+// at one DRAM round trip per plane
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ float4 ld4_stream(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float4 ld4_ro(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ld4_nc(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 
@@ -233,7 +253,7 @@ __device__ __forceinline__ float4 pcoef4(unsigned id, float sc, const float* ful
         const float4 v = __ldg(reinterpret_cast<const float4*>(xv + (size_t)id * w + col));
         return make_float4(__fmul_rn(sc, v.x), __fmul_rn(sc, v.y), __fmul_rn(sc, v.z), __fmul_rn(sc, v.w));
     }
-    return __ldcs(reinterpret_cast<const float4*>(full));
+    return __ldg(reinterpret_cast<const float4*>(full));
 }
 
 // the three PML coefficients of component c4 (0..2) of the current slab row; PM_ = row record or NULL
@@ -243,13 +263,14 @@ __device__ __forceinline__ float4 pcoef4(unsigned id, float sc, const float* ful
         a_ = pcoef4(pid_[c4], psc_[c4], (PA) + (lofs), PXV, COL, W);                                            \
         fo_ = pcoef4(pid_[3 + c4], psc_[3 + c4], (PFO) + (lofs), PXV, COL, W);                                  \
         fn_ = pcoef4(pid_[6 + c4], psc_[6 + c4], (PFN) + (lofs), PXV, COL, W);                                  \
-    } else { a_ = ld4_ro((PA) + (lofs)); fo_ = ld4_ro((PFO) + (lofs)); fn_ = ld4_ro((PFN) + (lofs)); }
+    } else { a_ = ld4_nc((PA) + (lofs)); fo_ = ld4_nc((PFO) + (lofs)); fn_ = ld4_nc((PFN) + (lofs)); }
 
 // load the row record into registers (row-uniform in MODE 1, per lane in MODE 2)
 #define PML_ROW_META(PMETA, ROW)                                                                                \
     const unsigned char* pm_ = (PMETA) ? (PMETA) + (long long)(ROW) * 48 : nullptr;                             \
     float psc_[9]; unsigned pid_[9];                                                                            \
     if (pm_ != nullptr) {                                                                                       \
+        if (k + KSTEP >= kbeg && k + KSTEP < kend) prefetch_l1(pm_ + (long long)KSTEP * r.by * 48);             \
         const float4 q0_ = __ldg(reinterpret_cast<const float4*>(pm_)), q1_ = __ldg(reinterpret_cast<const float4*>(pm_) + 1), \
                      q2_ = __ldg(reinterpret_cast<const float4*>(pm_) + 2);                                     \
         psc_[0] = q0_.x; psc_[1] = q0_.y; psc_[2] = q0_.z; psc_[3] = q0_.w;                                     \
@@ -260,30 +281,27 @@ __device__ __forceinline__ float4 pcoef4(unsigned id, float sc, const float* ful
         pid_[8] = w2_ & 255u;                                                                                   \
     }
 
-// one component of a fused PML row: pre, update, post.  f4 holds the field on entry and the new field on exit.
-#define PML_COMP(c4, f4, ca4, cb4, A, B, C, D, lofs)                                          \
+// one component of a fused PML row: pre, update, post.  f4 holds the field on entry and the new field on exit; fl4 holds
+// the old flux on entry (loaded by the caller together with every other load of the plane, so one plane costs one
+// round of DRAM latency, not one per component) and the new flux on exit (stored by the caller after all three).
+#define PML_COMP(c4, f4, fl4, ca4, cb4, A, B, C, D, lofs)                                     \
     do {                                                                                      \
-        float4 fl_ = zero4();                                                                 \
-        float4 h_ = zero4(), F_ = zero4(), fnn_ = zero4();                                    \
+        float4 h_ = zero4(), fnn_ = zero4();                                                  \
         if (act) {                                                                            \
-            fl_ = ld4_stream(r.flux + (lofs));                                                \
             PML_COEFFS(c4, r.a, r.fo, r.fn, r.pxv, i0, p.px, lofs)                            \
-            h_ = pml_pre4(a_, fo_, fl_, f4); fnn_ = fn_;                                      \
+            h_ = pml_pre4(a_, fo_, fl4, f4); fnn_ = fn_;                                      \
         }                                                                                     \
-        F_ = upd4(ca4, fl_, cb4, A, B, C, D);                                                 \
-        if (act) st4(r.flux + (lofs), F_);                                                    \
-        f4 = pml_post4(fnn_, F_, h_);                                                         \
+        fl4 = upd4(ca4, fl4, cb4, A, B, C, D);                                                \
+        f4 = pml_post4(fnn_, fl4, h_);                                                        \
     } while (0)
 
 // the same with explicit slab pointers (narrow x-slab launches: every lane is inside its slab)
-#define PML_COMP_X(c4, f4, ca4, cb4, A, B, C, D, lofs)                                        \
+#define PML_COMP_X(c4, f4, fl4, ca4, cb4, A, B, C, D, lofs)                                   \
     do {                                                                                      \
-        const float4 fl_ = ld4_stream(xflux + (lofs));                                        \
         PML_COEFFS(c4, xa, xfo, xfn, xpxv, i0 - xx0, xw, lofs)                                \
-        const float4 h_ = pml_pre4(a_, fo_, fl_, f4);                                         \
-        const float4 F_ = upd4(ca4, fl_, cb4, A, B, C, D);                                    \
-        st4(xflux + (lofs), F_);                                                              \
-        f4 = pml_post4(fn_, F_, h_);                                                          \
+        const float4 h_ = pml_pre4(a_, fo_, fl4, f4);                                         \
+        fl4 = upd4(ca4, fl4, cb4, A, B, C, D);                                                \
+        f4 = pml_post4(fn_, fl4, h_);                                                         \
     } while (0)
 
 // E update: volt_n = vv_n volt_n + vi_n curl_n(curr)   (App. A1)
@@ -291,9 +309,10 @@ __device__ __forceinline__ float4 pcoef4(unsigned id, float sc, const float* ful
 //   y: ((Hx - Hx[k-1]) - Hz) + Hz[i-1]
 //   z: ((Hy - Hy[i-1]) - Hx) + Hx[j-1]
 template <int TY, int MODE, bool CMP>      // MODE 0 plain rows, 1 fused PML rows, 2 plain rows whose x-edge lanes are PML
-__global__ void __launch_bounds__(32 * TY, MODE ? 1 : (24 / TY > 0 ? 24 / TY : 1)) update_e_kernel(const VolParams p, const RowParams r)
+__global__ void __launch_bounds__(32 * TY, MODE ? (12 / TY > 0 ? 12 / TY : 1) : (24 / TY > 0 ? 24 / TY : 1)) update_e_kernel(const VolParams p, const RowParams r)
 {
     constexpr bool PML = MODE == 1;
+    constexpr int KSTEP = 1;                                // the E march goes up in z
     const int lane = threadIdx.x;
     int i0, j;
     bool act;
@@ -323,6 +342,7 @@ __global__ void __launch_bounds__(32 * TY, MODE ? 1 : (24 / TY > 0 ? 24 / TY : 1
     const long long cs = p.cs, sz = p.sz;
     const float* __restrict__ g = p.g;
     float* __restrict__ f = p.f;
+    const float* fin = p.fin;
 
     long long base = (long long)kbeg * sz + (long long)j * p.px + i0;   // plane kbeg-1 (ghost offset +1 applied below)
     float4 hx_km = zero4(), hy_km = zero4();
@@ -349,10 +369,15 @@ __global__ void __launch_bounds__(32 * TY, MODE ? 1 : (24 / TY > 0 ? 24 / TY : 1
         float4 ex = zero4(), ey = zero4(), ez = zero4();
         float4 ax = zero4(), ay = zero4(), az = zero4(), bx = zero4(), by = zero4(), bz = zero4();
         float hz_e = 0.f, hy_e = 0.f;
+        // every load of the plane is issued up front (slab row record and old flux included): one DRAM round trip per plane
+        PML_ROW_META(MODE == 1 ? r.pmeta : (MODE == 2 ? xpmeta : nullptr), (long long)(k - r.z0) * r.by + (j - r.y0))
+        float4 fl0 = zero4(), fl1 = zero4(), fl2 = zero4();
+        if (MODE == 1 && act) { fl0 = ld4_stream(r.flux + lb); fl1 = ld4_stream(r.flux + lcs + lb); fl2 = ld4_stream(r.flux + 2 * lcs + lb); }
+        if (MODE == 2) { fl0 = ld4_stream(xflux + lb); fl1 = ld4_stream(xflux + lcs + lb); fl2 = ld4_stream(xflux + 2 * lcs + lb); }
         if (act) {
             hx = ld4(g + base); hy = ld4(g + cs + base); hz = ld4(g + 2 * cs + base);
             if (has_jm) { hz_jm = ld4(g + 2 * cs + base - p.px); hx_jm = ld4(g + base - p.px); }
-            ex = ld4_stream(f + base); ey = ld4_stream(f + cs + base); ez = ld4_stream(f + 2 * cs + base);
+            ex = ld4_stream(fin + base); ey = ld4_stream(fin + cs + base); ez = ld4_stream(fin + 2 * cs + base);
             if (CMP) LOAD_COEFFS_CMP();
             else {
                 ax = ld4_ro(p.ca + base); ay = ld4_ro(p.ca + cs + base); az = ld4_ro(p.ca + 2 * cs + base);
@@ -372,15 +397,15 @@ __global__ void __launch_bounds__(32 * TY, MODE ? 1 : (24 / TY > 0 ? 24 / TY : 1
         const float4 hy_im = make_float4(hy_l, hy.x, hy.y, hy.z);
 
         if (PML) {
-            PML_ROW_META(r.pmeta, (long long)(k - r.z0) * r.by + (j - r.y0))
-            PML_COMP(0, ex, ax, bx, hz, hz_jm, hy, hy_km, lb);
-            PML_COMP(1, ey, ay, by, hx, hx_km, hz, hz_im, lcs + lb);
-            PML_COMP(2, ez, az, bz, hy, hy_im, hx, hx_jm, 2 * lcs + lb);
+            PML_COMP(0, ex, fl0, ax, bx, hz, hz_jm, hy, hy_km, lb);
+            PML_COMP(1, ey, fl1, ay, by, hx, hx_km, hz, hz_im, lcs + lb);
+            PML_COMP(2, ez, fl2, az, bz, hy, hy_im, hx, hx_jm, 2 * lcs + lb);
+            if (act) { st4(r.flux + lb, fl0); st4(r.flux + lcs + lb, fl1); st4(r.flux + 2 * lcs + lb, fl2); }
         } else if (MODE == 2) {
-            PML_ROW_META(xpmeta, (long long)(k - r.z0) * r.by + (j - r.y0))
-            PML_COMP_X(0, ex, ax, bx, hz, hz_jm, hy, hy_km, lb);
-            PML_COMP_X(1, ey, ay, by, hx, hx_km, hz, hz_im, lcs + lb);
-            PML_COMP_X(2, ez, az, bz, hy, hy_im, hx, hx_jm, 2 * lcs + lb);
+            PML_COMP_X(0, ex, fl0, ax, bx, hz, hz_jm, hy, hy_km, lb);
+            PML_COMP_X(1, ey, fl1, ay, by, hx, hx_km, hz, hz_im, lcs + lb);
+            PML_COMP_X(2, ez, fl2, az, bz, hy, hy_im, hx, hx_jm, 2 * lcs + lb);
+            st4(xflux + lb, fl0); st4(xflux + lcs + lb, fl1); st4(xflux + 2 * lcs + lb, fl2);
         } else {
             ex = upd4(ax, ex, bx, hz, hz_jm, hy, hy_km);
             ey = upd4(ay, ey, by, hx, hx_km, hz, hz_im);
@@ -398,9 +423,10 @@ __global__ void __launch_bounds__(32 * TY, MODE ? 1 : (24 / TY > 0 ? 24 / TY : 1
 //   y: ((Ex - Ex[k+1]) - Ez) + Ez[i+1]
 //   z: ((Ey - Ey[i+1]) - Ex) + Ex[j+1]
 template <int TY, int MODE, bool CMP>
-__global__ void __launch_bounds__(32 * TY, MODE ? 1 : (24 / TY > 0 ? 24 / TY : 1)) update_h_kernel(const VolParams p, const RowParams r)
+__global__ void __launch_bounds__(32 * TY, MODE ? (12 / TY > 0 ? 12 / TY : 1) : (24 / TY > 0 ? 24 / TY : 1)) update_h_kernel(const VolParams p, const RowParams r)
 {
     constexpr bool PML = MODE == 1;
+    constexpr int KSTEP = -1;                               // the H march goes down in z
     const int lane = threadIdx.x;
     int i0, j;
     bool act;
@@ -430,6 +456,7 @@ __global__ void __launch_bounds__(32 * TY, MODE ? 1 : (24 / TY > 0 ? 24 / TY : 1
     const long long cs = p.cs, sz = p.sz;
     const float* __restrict__ g = p.g;
     float* __restrict__ f = p.f;
+    const float* fin = p.fin;
 
     long long base = (long long)(kend + 1) * sz + (long long)j * p.px + i0;   // plane kend (k+1 of the first plane)
     float4 ex_kp = zero4(), ey_kp = zero4();
@@ -457,10 +484,14 @@ __global__ void __launch_bounds__(32 * TY, MODE ? 1 : (24 / TY > 0 ? 24 / TY : 1
         float4 hx = zero4(), hy = zero4(), hz = zero4();
         float4 ax = zero4(), ay = zero4(), az = zero4(), bx = zero4(), by = zero4(), bz = zero4();
         float ez_e = 0.f, ey_e = 0.f;
+        PML_ROW_META(MODE == 1 ? r.pmeta : (MODE == 2 ? xpmeta : nullptr), (long long)(k - r.z0) * r.by + (j - r.y0))
+        float4 fl0 = zero4(), fl1 = zero4(), fl2 = zero4();
+        if (MODE == 1 && act) { fl0 = ld4_stream(r.flux + lb); fl1 = ld4_stream(r.flux + lcs + lb); fl2 = ld4_stream(r.flux + 2 * lcs + lb); }
+        if (MODE == 2) { fl0 = ld4_stream(xflux + lb); fl1 = ld4_stream(xflux + lcs + lb); fl2 = ld4_stream(xflux + 2 * lcs + lb); }
         if (act) {
             ex = ld4(g + base); ey = ld4(g + cs + base); ez = ld4(g + 2 * cs + base);
             if (has_jp) { ez_jp = ld4(g + 2 * cs + base + p.px); ex_jp = ld4(g + base + p.px); }
-            hx = ld4_stream(f + base); hy = ld4_stream(f + cs + base); hz = ld4_stream(f + 2 * cs + base);
+            hx = ld4_stream(fin + base); hy = ld4_stream(fin + cs + base); hz = ld4_stream(fin + 2 * cs + base);
             if (CMP) LOAD_COEFFS_CMP();
             else {
                 ax = ld4_ro(p.ca + base); ay = ld4_ro(p.ca + cs + base); az = ld4_ro(p.ca + 2 * cs + base);
@@ -480,15 +511,15 @@ __global__ void __launch_bounds__(32 * TY, MODE ? 1 : (24 / TY > 0 ? 24 / TY : 1
         const float4 ey_ip = make_float4(ey.y, ey.z, ey.w, ey_r);
 
         if (PML) {
-            PML_ROW_META(r.pmeta, (long long)(k - r.z0) * r.by + (j - r.y0))
-            PML_COMP(0, hx, ax, bx, ez, ez_jp, ey, ey_kp, lb);
-            PML_COMP(1, hy, ay, by, ex, ex_kp, ez, ez_ip, lcs + lb);
-            PML_COMP(2, hz, az, bz, ey, ey_ip, ex, ex_jp, 2 * lcs + lb);
+            PML_COMP(0, hx, fl0, ax, bx, ez, ez_jp, ey, ey_kp, lb);
+            PML_COMP(1, hy, fl1, ay, by, ex, ex_kp, ez, ez_ip, lcs + lb);
+            PML_COMP(2, hz, fl2, az, bz, ey, ey_ip, ex, ex_jp, 2 * lcs + lb);
+            if (act) { st4(r.flux + lb, fl0); st4(r.flux + lcs + lb, fl1); st4(r.flux + 2 * lcs + lb, fl2); }
         } else if (MODE == 2) {
-            PML_ROW_META(xpmeta, (long long)(k - r.z0) * r.by + (j - r.y0))
-            PML_COMP_X(0, hx, ax, bx, ez, ez_jp, ey, ey_kp, lb);
-            PML_COMP_X(1, hy, ay, by, ex, ex_kp, ez, ez_ip, lcs + lb);
-            PML_COMP_X(2, hz, az, bz, ey, ey_ip, ex, ex_jp, 2 * lcs + lb);
+            PML_COMP_X(0, hx, fl0, ax, bx, ez, ez_jp, ey, ey_kp, lb);
+            PML_COMP_X(1, hy, fl1, ay, by, ex, ex_kp, ez, ez_ip, lcs + lb);
+            PML_COMP_X(2, hz, fl2, az, bz, ey, ey_ip, ex, ex_jp, 2 * lcs + lb);
+            st4(xflux + lb, fl0); st4(xflux + lcs + lb, fl1); st4(xflux + 2 * lcs + lb, fl2);
         } else {
             hx = upd4(ax, hx, bx, ez, ez_jp, ey, ey_kp);
             hy = upd4(ay, hy, by, ex, ex_kp, ez, ez_ip);
@@ -506,13 +537,17 @@ static int launch_volume_one(b200fdtd_ctx* c, int which, int k0, int k1, const R
 {
     if (k1 <= k0 || r.j1 <= r.j0 || nchunks <= 0) return 0;
     VolParams p;
-    p.f = which == 0 ? c->volt : c->curr;
-    p.g = which == 0 ? c->curr : c->volt;
+    p.fin = which == 0 ? cur_volt(c) : cur_curr(c);
+    p.f = c->flip ? (which == 0 ? oth_volt(c) : oth_curr(c)) : const_cast<float*>(p.fin);
+    p.g = which == 0 ? cur_curr(c) : cur_volt(c);
     p.ca = which == 0 ? c->vv : c->ii;
     p.cb = which == 0 ? c->vi : c->iv;
     p.nx = c->nx; p.ny = c->ny; p.nz = c->nz; p.px = c->px; p.sz = c->sz; p.cs = c->cs;
     p.kz = kz; p.k0 = k0; p.k1 = k1;
-    const int ty = c->ty;
+    // slab launches may use their own CTA height (variant bits 8-12): a 2-row slab CTA has the register footprint of one
+    // plain CTA, so it fits the slot a retiring plain CTA frees when both run concurrently
+    const int ty_slab = (c->variant >> 8) & 31;
+    const int ty = (MODE != 0 && ty_slab) ? ty_slab : c->ty;
     dim3 block(32, ty);
     dim3 grid(nchunks, grid_y > 0 ? grid_y : (r.j1 - r.j0 + ty - 1) / ty, (k1 - k0 + kz - 1) / kz);
     if (grid.y > 65535 || grid.z > 65535) return fail("grid too large for launch (ny/ty=%u, nz/kz=%u)", grid.y, grid.z);
@@ -628,7 +663,19 @@ static int launch_volume_plain(b200fdtd_ctx* c, int which, int k0, int k1, cudaS
     return 0;
 }
 
+static int slab_ty(const b200fdtd_ctx* c) { const int t = (c->variant >> 8) & 31; return t ? t : c->ty; }
 static int slots_for(int w) { int s = 1; while (s * 4 < w) s *= 2; return s; }
+
+// planes marched per CTA of a thin slab launch: enough CTAs to fill the machine several times over (the march is a
+// serial chain of DRAM round trips, so small launches need their parallelism from the grid), chunks of equal length
+static int slab_kz(int kz, int planes, long long ctas_per_chunk)
+{
+    auto chunks = [&](int q) { return (planes + q - 1) / q; };
+    while (kz > 2 && ctas_per_chunk * chunks(kz) < 148LL * 16) kz = (kz + 1) / 2;
+    if (kz > planes) kz = planes;
+    const int n = chunks(kz);
+    return (planes + n - 1) / n;
+}
 
 // narrow x-slab launches (MODE 2): PML pre/update/post on the slab columns of the plain rows
 static int launch_volume_xslabs(b200fdtd_ctx* c, int which, int k0, int k1, cudaStream_t stream)
@@ -652,10 +699,9 @@ static int launch_volume_xslabs(b200fdtd_ctx* c, int which, int k0, int k1, cuda
     const int xs = (P.has_lo && P.has_hi) ? (e.xs0 > e.xs1 ? e.xs0 : e.xs1) : (P.has_lo ? e.xs0 : e.xs1);
     RowParams g = e;
     g.j1 = e.j1;                                             // kernel bounds rows by j1; grid.y from the widest slab
-    const int rows_per_cta = c->ty * (32 / xs);
+    const int rows_per_cta = slab_ty(c) * (32 / xs);
     const int gy = (any.by + rows_per_cta - 1) / rows_per_cta;
-    int kz = c->kz;
-    while (kz > 2 && (long long)gy * ((b - a + kz - 1) / kz) * (P.has_lo + P.has_hi) < 148LL * 8) kz = (kz + 1) / 2;
+    const int kz = slab_kz(c->kz, b - a, (long long)gy * (P.has_lo + P.has_hi));
     // launch_volume_one derives grid.y from (j1-j0)/ty: pass an equivalent row count
     g.j0 = e.j0; 
     return launch_volume_one<2>(c, which, a, b, g, stream, kz, P.has_lo + P.has_hi, gy);
@@ -675,9 +721,8 @@ static int launch_volume_fused(b200fdtd_ctx* c, int which, int k0, int k1, cudaS
         const int a = k0 > B.z0 ? k0 : B.z0, b = k1 < B.z0 + B.bz ? k1 : B.z0 + B.bz;
         if (b <= a) continue;
         // thin slabs: march fewer planes per CTA so the launch still fills the machine (>= ~8 CTAs per SM)
-        const long long per_chunk = (long long)((c->px + 127) / 128) * ((B.by + c->ty - 1) / c->ty);
-        int kz = c->kz;
-        while (kz > 2 && per_chunk * ((b - a + kz - 1) / kz) < 148LL * 8) kz = (kz + 1) / 2;
+        const long long per_chunk = (long long)((c->px + 127) / 128) * ((B.by + slab_ty(c) - 1) / slab_ty(c));
+        const int kz = slab_kz(c->kz, b - a, per_chunk);
         if (launch_volume_one<1>(c, which, a, b, f, stream, kz, (c->px + 127) / 128)) return 1;
     }
     return 0;
@@ -698,14 +743,19 @@ static int fork_side(b200fdtd_ctx* c)
 {
     CK(cudaEventRecord(c->ev_fork, c->stream));
     CK(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+    CK(cudaStreamWaitEvent(c->side2, c->ev_fork, 0));
     return 0;
 }
 static int join_side(b200fdtd_ctx* c)
 {
     CK(cudaEventRecord(c->ev_join, c->side));
     CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    CK(cudaEventRecord(c->ev_join2, c->side2));
+    CK(cudaStreamWaitEvent(c->stream, c->ev_join2, 0));
     return 0;
 }
+// the stream of the whole-row slab launches: their own side stream, or the x-slab one (variant bit 64)
+static cudaStream_t slab_stream(b200fdtd_ctx* c) { return (c->variant & 64) ? c->side : c->side2; }
 
 // ------------------------------------------------------------------------------------
 // narrow-band kernels
@@ -981,7 +1031,12 @@ extern "C" int b200fdtd_create(b200fdtd_ctx** out, int device, int nx, int ny, i
     c->sz = (long long)ny * px; c->cs = (long long)(nz + 2) * c->sz;
     c->stream = (cudaStream_t)stream;                       // NULL = the default stream (torch's default stream)
     c->own_stream = false;
-    CK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->side_lo, cudaStreamNonBlocking));
+    { int lo = 0, hi = 0; CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      CK(cudaStreamCreateWithPriority(&c->side_hi, cudaStreamNonBlocking, hi)); }
+    c->side = c->side_lo;
+    CK(cudaStreamCreateWithFlags(&c->side2, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->ev_join2, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     CK(cudaMalloc((void**)&c->d_ts, sizeof(int)));
@@ -1006,7 +1061,10 @@ extern "C" int b200fdtd_destroy(b200fdtd_ctx* c)
     cudaFree(c->nf_freqs);
     for (int a = 0; a < 3; ++a) { cudaFree(c->inv_len[a]); cudaFree(c->inv_dual[a]); }
     cudaFree(c->d_pml); cudaFree(c->d_faces);
-    if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
+    if (c->side_lo) { cudaStreamSynchronize(c->side_lo); cudaStreamDestroy(c->side_lo); }
+    if (c->side_hi) { cudaStreamSynchronize(c->side_hi); cudaStreamDestroy(c->side_hi); }
+    if (c->side2) { cudaStreamSynchronize(c->side2); cudaStreamDestroy(c->side2); }
+    if (c->ev_join2) cudaEventDestroy(c->ev_join2);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -1036,7 +1094,9 @@ extern "C" int b200fdtd_set_tuning(b200fdtd_ctx* c, int kz, int ty, int variant)
     if (!c) return fail("NULL ctx");
     if (kz < 1) return fail("kz must be >= 1");
     if (!(ty == 1 || ty == 2 || ty == 4 || ty == 8 || ty == 16)) return fail("ty must be 1,2,4,8 or 16");
+    { const int t = (variant >> 8) & 31; if (!(t == 0 || t == 1 || t == 2 || t == 4 || t == 8 || t == 16)) return fail("slab ty (variant bits 8-12) must be 0,1,2,4,8 or 16"); }
     c->kz = kz; c->ty = ty; c->variant = variant; drop_graph(c);
+    c->side = (variant & 32) ? c->side_hi : c->side_lo;
     c->plan.valid = false;
     return 0;
 }
@@ -1315,7 +1375,7 @@ static int launch_pml(b200fdtd_ctx* c, int which, int post)
         const int ty = 256 / tx;
         if (B.bz > 65535) return fail("PML box too tall for one launch");
         dim3 block(tx, ty), grid((B.by + ty - 1) / ty, B.bz, 3);
-        pml_kernel<<<grid, block, 0, c->stream>>>(which == 0 ? c->volt : c->curr, B, which, post, c->px, c->sz, c->cs);
+        pml_kernel<<<grid, block, 0, c->stream>>>(which == 0 ? cur_volt(c) : cur_curr(c), B, which, post, c->px, c->sz, c->cs);
         CKL();
     }
     return 0;
@@ -1324,7 +1384,7 @@ static int launch_mur(b200fdtd_ctx* c, int phase)
 {
     if (c->n_mur == 0) return 0;
     const int threads = 256;
-    mur_kernel<<<(unsigned)((c->n_mur + threads - 1) / threads), threads, 0, c->stream>>>(c->volt, c->mur_dst, c->mur_src,
+    mur_kernel<<<(unsigned)((c->n_mur + threads - 1) / threads), threads, 0, c->stream>>>(cur_volt(c), c->mur_dst, c->mur_src,
                                                                                        c->mur_coeff, c->mur_tmp, c->n_mur, phase);
     CKL();
     return 0;
@@ -1333,7 +1393,7 @@ static int launch_excite(b200fdtd_ctx* c, int ts_off)
 {
     if (c->n_exc == 0) return 0;
     const int threads = 128;
-    excite_kernel<<<(unsigned)((c->n_exc + threads - 1) / threads), threads, 0, c->stream>>>(c->volt, c->exc_idx, c->exc_amp,
+    excite_kernel<<<(unsigned)((c->n_exc + threads - 1) / threads), threads, 0, c->stream>>>(cur_volt(c), c->exc_idx, c->exc_amp,
         c->exc_delay, c->exc_sig, c->exc_siglen, c->n_exc, c->d_ts, ts_off);
     CKL();
     return 0;
@@ -1341,13 +1401,13 @@ static int launch_excite(b200fdtd_ctx* c, int ts_off)
 static int launch_sampling(b200fdtd_ctx* c, int ts_off)
 {
     if (c->n_probes > 0) {
-        probe_kernel<<<c->n_probes, 128, 0, c->stream>>>(c->volt, c->curr, c->pr_kind, c->pr_off, c->pr_idx, c->pr_w,
+        probe_kernel<<<c->n_probes, 128, 0, c->stream>>>(cur_volt(c), cur_curr(c), c->pr_kind, c->pr_off, c->pr_idx, c->pr_w,
             c->interval, c->max_samples, c->pr_series, c->pr_nfreq, c->pr_freqs, c->pr_dft, c->dt, c->d_ts, ts_off);
         CKL();
     }
     if (c->faces.n > 0) {
         Nf2ffParams P;
-        P.volt = c->volt; P.curr = c->curr; P.ny = c->ny; P.px = c->px; P.sz = c->sz; P.cs = c->cs;
+        P.volt = cur_volt(c); P.curr = cur_curr(c); P.ny = c->ny; P.px = c->px; P.sz = c->sz; P.cs = c->cs;
         for (int a = 0; a < 3; ++a) { P.il[a] = c->inv_len[a]; P.idl[a] = c->inv_dual[a]; }
         P.nfreq = c->nf_nfreq; P.freqs = c->nf_freqs; P.dt = c->nf_dt; P.d_ts = c->d_ts; P.ts_off = ts_off;
         dim3 grid((c->nf_max_nodes + 127) / 128, c->faces.n);
@@ -1370,7 +1430,7 @@ static int e_half(b200fdtd_ctx* c, int off)
     const bool side = (c->plan.nfused > 0 || c->plan.xedge) && (c->variant & 2) == 0;
     if (launch_mur(c, 0)) return 1;              // Mur sees the true field, before any PML pass swaps in the flux
     if (side) { if (fork_side(c)) return 1; if (launch_volume_xslabs(c, 0, 0, c->nz, c->side)) return 1;
-                if (launch_volume_fused(c, 0, 0, c->nz, c->side)) return 1; }
+                if (launch_volume_fused(c, 0, 0, c->nz, slab_stream(c))) return 1; }
     if (launch_pml(c, 0, 0)) return 1;
     if (launch_volume_plain(c, 0, 0, c->nz, c->stream)) return 1;
     if (!side) { if (launch_volume_xslabs(c, 0, 0, c->nz, c->stream)) return 1; if (launch_volume_fused(c, 0, 0, c->nz, c->stream)) return 1; }
@@ -1386,7 +1446,7 @@ static int h_half(b200fdtd_ctx* c)
     if (!c->plan.valid) if (build_plan(c)) return 1;
     const bool side = (c->plan.nfused > 0 || c->plan.xedge) && (c->variant & 2) == 0;
     if (side) { if (fork_side(c)) return 1; if (launch_volume_xslabs(c, 1, 0, c->nz, c->side)) return 1;
-                if (launch_volume_fused(c, 1, 0, c->nz, c->side)) return 1; }
+                if (launch_volume_fused(c, 1, 0, c->nz, slab_stream(c))) return 1; }
     if (launch_pml(c, 1, 0)) return 1;
     if (launch_volume_plain(c, 1, 0, c->nz, c->stream)) return 1;
     if (!side) { if (launch_volume_xslabs(c, 1, 0, c->nz, c->stream)) return 1; if (launch_volume_fused(c, 1, 0, c->nz, c->stream)) return 1; }
@@ -1560,7 +1620,7 @@ extern "C" int b200fdtd_energy(b200fdtd_ctx* c, double* energy)
     if (!c->volt) return fail("fields not bound");
     CK(cudaSetDevice(c->device));
     const long long n_owned = (long long)c->nz * c->sz;
-    energy_partial_kernel<<<c->n_partials, 256, 0, c->stream>>>(c->volt, c->curr, c->sz, c->cs, n_owned, c->d_partials);
+    energy_partial_kernel<<<c->n_partials, 256, 0, c->stream>>>(cur_volt(c), cur_curr(c), c->sz, c->cs, n_owned, c->d_partials);
     CKL();
     energy_final_kernel<<<1, 32, 0, c->stream>>>(c->d_partials, c->n_partials, c->d_energy);
     CKL();
