@@ -59,6 +59,8 @@ SYMBOLS = {
     "b200fdtd_half_step_part": (C.c_int, [vp, C.c_int, C.c_int]),
     "b200fdtd_update_only": (C.c_int, [vp, C.c_int]),
     "b200fdtd_plan_info": (C.c_int, [vp, c_i64, c_i64, c_i64]),
+    "b200fdtd_set_he_tuning": (C.c_int, [vp, C.c_int, C.c_int]),
+    "b200fdtd_he_info": (C.c_int, [vp, C.POINTER(C.c_int)]),
     "b200fdtd_energy": (C.c_int, [vp, c_d]),
     "b200fdtd_sync": (C.c_int, [vp]),
     "b200fdtd_num_samples": (C.c_int, [vp, C.POINTER(C.c_int)]),

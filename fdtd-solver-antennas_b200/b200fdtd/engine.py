@@ -105,6 +105,17 @@ class Engine:
     def set_tuning(self, kz=16, ty=4, variant=0):
         check(self.L.b200fdtd_set_tuning(self.h, int(kz), int(ty), int(variant)))
 
+    def set_he_tuning(self, rows=0, planes=0):
+        """tile of the fused H->E launch: rows per CTA in {3, 7, 15}, planes marched per CTA (0 = keep)"""
+        check(self.L.b200fdtd_set_he_tuning(self.h, int(rows), int(planes)))
+
+    @property
+    def he_active(self):
+        """True if the last graph run used the fused H->E launches"""
+        v = C.c_int()
+        check(self.L.b200fdtd_he_info(self.h, C.byref(v)))
+        return bool(v.value)
+
     def set_excitation(self, idx, amp, delay, signal):
         idx, amp, delay, signal = _np(idx, np.int64), _np(amp, np.float32), _np(delay, np.int32), _np(signal, np.float32)
         check(self.L.b200fdtd_set_excitation(self.h, len(idx), _ptr(idx, c_i64), _ptr(amp, c_f), _ptr(delay, c_i32),

@@ -18,6 +18,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <vector>
 #include <atomic>
 
@@ -66,6 +67,7 @@ struct VolumePlan {
     int nfused = 0; FusedBox fb[4];
     // narrow x-slabs folded into "x-edge" launches of the plain rows
     bool xedge = false; int has_lo = 0, has_hi = 0; FusedBox xlo{}, xhi{}; int xw0 = 0, xx1 = 0, xw1 = 0;
+    int ym0 = 0, ym1 = 0;                        // rows of the plain launches (complement of the fused y-slabs)
 };
 
 struct FaceDev {
@@ -85,6 +87,8 @@ struct b200fdtd_ctx {
     cudaStream_t side_lo = nullptr, side_hi = nullptr;   // the same at default / highest priority (variant bit 32 picks)
     cudaStream_t side2 = nullptr;          // whole-row slab launches (z/y) while `side` runs the narrow x-slab launch
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
+    cudaStream_t slab_s[3] = {nullptr, nullptr, nullptr};   // one stream per further whole-row slab: the slab launches are short and
+    cudaEvent_t slab_ev[3] = {nullptr, nullptr, nullptr};   // latency-bound, so they run side by side rather than one after the other
     float *volt = nullptr, *curr = nullptr;
     // second copy of the fields for the fused H->E launches (they cannot update in place: a CTA recomputes the halo of its
     // tile from the old values its neighbours are overwriting).  vcur/ccur say which copy holds the current E / H; both are
@@ -97,6 +101,7 @@ struct b200fdtd_ctx {
     int kz = 16, ty = 4, variant = 0;
     const float* cmp_xv[2] = {nullptr, nullptr};          // row compression tables of the E and H pass (caller-owned)
     const unsigned char* cmp_meta[2] = {nullptr, nullptr};
+    int cmp_nvec[2] = {0, 0};
     // step counter
     int64_t ts = 0;
     int* d_ts = nullptr;
@@ -122,6 +127,7 @@ struct b200fdtd_ctx {
     double* d_partials = nullptr; int n_partials = 0; double* d_energy = nullptr;
     // graph
     cudaGraphExec_t graph = nullptr; int graph_steps = 0; int64_t graph_kernels = 0;
+    bool he_fused = false;                 // the captured chunk uses the fused H->E launches
     // device copies of the slab / face tables
     PmlTable* d_pml = nullptr; FaceTable* d_faces = nullptr;
 };
@@ -190,6 +196,7 @@ __device__ __forceinline__ float4 coef4(unsigned id, float sc, const float* full
 // the row records steer dependent loads: pulling the next plane's record into L1 one iteration ahead keeps the march
 // at one DRAM round trip per plane
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ float4 ld4_stream(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float4 ld4_ro(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
@@ -309,7 +316,7 @@ __device__ __forceinline__ float4 pcoef4(unsigned id, float sc, const float* ful
 //   y: ((Hx - Hx[k-1]) - Hz) + Hz[i-1]
 //   z: ((Hy - Hy[i-1]) - Hx) + Hx[j-1]
 template <int TY, int MODE, bool CMP>      // MODE 0 plain rows, 1 fused PML rows, 2 plain rows whose x-edge lanes are PML
-__global__ void __launch_bounds__(32 * TY, MODE ? (12 / TY > 0 ? 12 / TY : 1) : (24 / TY > 0 ? 24 / TY : 1)) update_e_kernel(const VolParams p, const RowParams r)
+__global__ void __launch_bounds__(32 * TY, MODE ? (16 / TY > 0 ? 16 / TY : 1) : (24 / TY > 0 ? 24 / TY : 1)) update_e_kernel(const VolParams p, const RowParams r)
 {
     constexpr bool PML = MODE == 1;
     constexpr int KSTEP = 1;                                // the E march goes up in z
@@ -423,7 +430,7 @@ __global__ void __launch_bounds__(32 * TY, MODE ? (12 / TY > 0 ? 12 / TY : 1) : 
 //   y: ((Ex - Ex[k+1]) - Ez) + Ez[i+1]
 //   z: ((Ey - Ey[i+1]) - Ex) + Ex[j+1]
 template <int TY, int MODE, bool CMP>
-__global__ void __launch_bounds__(32 * TY, MODE ? (12 / TY > 0 ? 12 / TY : 1) : (24 / TY > 0 ? 24 / TY : 1)) update_h_kernel(const VolParams p, const RowParams r)
+__global__ void __launch_bounds__(32 * TY, MODE ? (16 / TY > 0 ? 16 / TY : 1) : (24 / TY > 0 ? 24 / TY : 1)) update_h_kernel(const VolParams p, const RowParams r)
 {
     constexpr bool PML = MODE == 1;
     constexpr int KSTEP = -1;                               // the H march goes down in z
@@ -529,6 +536,434 @@ __global__ void __launch_bounds__(32 * TY, MODE ? (12 / TY > 0 ? 12 / TY : 1) : 
             st4(f + base, hx); st4(f + cs + base, hy); st4(f + 2 * cs + base, hz);
         }
         ex_kp = ex; ey_kp = ey;
+    }
+}
+
+
+// ------------------------------------------------------------------------------------
+// fused H->E launch (temporal blocking over the pair  H update of step n, E update of step n+1)
+// ------------------------------------------------------------------------------------
+// Between the H update of one step and the E update of the next nothing else touches the fields, so both can be done
+// in one sweep: 48 B/cell of field traffic (E, H read + written once) instead of 72 B (each pass re-reads the other
+// field).  A CTA owns TY rows x 124 columns and marches up in z.  E_new(i,j,k) needs H_new at (i-1), (j-1), (k-1): the
+// CTA recomputes H_new on a one-cell halo at its low sides (row 0 of the CTA, lane 0 of every warp, one extra plane below
+// the chunk) from the OLD fields, which is why the launch writes a second copy of the fields instead of updating in place.
+// Halo cells that lie outside the launch region (PML slabs, whose H update ran just before this launch into the same
+// output copy) are read from the output copy instead.  Same arithmetic per cell as update_h_kernel / update_e_kernel.
+struct HeParams {
+    const float* __restrict__ ein; const float* __restrict__ hin;
+    float* __restrict__ eout; float* hout;          // hout is also read (halo cells outside the region)
+    const float* __restrict__ vv; const float* __restrict__ vi; const float* __restrict__ ii; const float* __restrict__ iv;
+    const float* __restrict__ xv_e; const unsigned char* __restrict__ meta_e;
+    const float* __restrict__ xv_h; const unsigned char* __restrict__ meta_h;
+    int ny, px; long long sz, cs;
+    int X0, X1, XT0;                // owned columns [X0,X1) and [XT0,px), multiples of 4 (the gap is a narrow PML x-slab)
+    int Y0, Y1, Z0, Z1;             // owned rows and planes
+    int kz;
+    int pf;                         // planes of L2 prefetch distance (0 = off)
+    // byte offsets as launch constants (update_he2_kernel adds them to per-thread plane pointers: two integer
+    // instructions per address instead of a 64-bit index computation)
+    long long b_sz, b_cs, b_2cs, b_sz_cs, b_sz_2cs, b_row, b_row_2cs, b_pfe[3], b_pfh[3];
+    unsigned xv_pitch; int meta_step;
+    int nv_e, nv_h;                 // x-vectors of the E / H pass (update_he2_kernel keeps its 128-column slice of them in smem)
+};
+
+template <bool CMP>
+__device__ __forceinline__ void load_coefs6(const float* __restrict__ ca, const float* __restrict__ cb, const float* __restrict__ xv,
+        const unsigned char* __restrict__ meta, long long base, long long cs, long long row, int ny, int i0, int px,
+        float4& ax, float4& ay, float4& az, float4& bx, float4& by, float4& bz)
+{
+    if (CMP) {
+        const float4* m_ = reinterpret_cast<const float4*>(meta + row * 32);
+        prefetch_l1(meta + (row + ny) * 32);                 // the march goes up: next plane's record
+        const float4 m0_ = __ldg(m_), m1_ = __ldg(m_ + 1);
+        const unsigned w0_ = __float_as_uint(m1_.z), w1_ = __float_as_uint(m1_.w);
+        ax = coef4(w0_ & 255u, m0_.x, ca + base, xv, i0, px);
+        ay = coef4((w0_ >> 8) & 255u, m0_.y, ca + cs + base, xv, i0, px);
+        az = coef4((w0_ >> 16) & 255u, m0_.z, ca + 2 * cs + base, xv, i0, px);
+        bx = coef4(w0_ >> 24, m0_.w, cb + base, xv, i0, px);
+        by = coef4(w1_ & 255u, m1_.x, cb + cs + base, xv, i0, px);
+        bz = coef4((w1_ >> 8) & 255u, m1_.y, cb + 2 * cs + base, xv, i0, px);
+    } else {
+        ax = ld4_ro(ca + base); ay = ld4_ro(ca + cs + base); az = ld4_ro(ca + 2 * cs + base);
+        bx = ld4_ro(cb + base); by = ld4_ro(cb + cs + base); bz = ld4_ro(cb + 2 * cs + base);
+    }
+}
+
+#define HE_SEG 124          // columns owned by a warp: lanes 1..31; lane 0 is the x-halo
+
+template <int TY, bool CMP>
+__global__ void __launch_bounds__(32 * (TY + 1), 16 / (TY + 1)) update_he_kernel(const HeParams p)
+{
+    __shared__ float4 xb[2][TY + 1][2][32];                  // H_new (hz, hx) of every row, for the row above; double buffered
+    const int lane = threadIdx.x, r = threadIdx.y;
+    const int i0 = p.X0 - 4 + HE_SEG * (int)blockIdx.x + 4 * lane;
+    const int j = p.Y0 - 1 + TY * (int)blockIdx.y + r;
+    const int kbeg = p.Z0 + (int)blockIdx.z * p.kz;
+    const int kend = min(kbeg + p.kz, p.Z1);
+    const bool in_grid = i0 >= 0 && i0 < p.px && j >= 0 && j < p.Y1;        // rows >= Y1 are needed by nobody here
+    const bool reg_x = (i0 >= p.X0 && i0 < p.X1) || i0 >= p.XT0;
+    const bool ext = in_grid && (!reg_x || j < p.Y0);       // H_new was written by a slab launch: read it
+    const bool calc = in_grid && !ext;                       // H_new is computed here (owned cells and halo cells)
+    const bool own = calc && lane >= 1 && r >= 1;            // ... and stored, together with E_new
+    const bool has_jp = j + 1 < p.ny;
+    const bool edge_load = in_grid && lane == 31 && i0 + 4 < p.px;
+    const long long cs = p.cs, sz = p.sz;
+    const float* __restrict__ ein = p.ein; const float* __restrict__ hin = p.hin;
+    float* __restrict__ eout = p.eout; float* hout = p.hout;
+
+    const int kfirst = kbeg > p.Z0 ? kbeg - 1 : kbeg;        // one plane below the chunk: H_new(kbeg-1) is recomputed
+    long long base = (long long)(kfirst + 1) * sz + (long long)j * p.px + i0;   // plane kfirst (ghost offset +1)
+    float4 ex = zero4(), ey = zero4(), ez = zero4();         // E_old(k)
+    float4 hx_km = zero4(), hy_km = zero4();                 // H_new(k-1)
+    if (in_grid) { ex = ld4(ein + base); ey = ld4(ein + cs + base); ez = ld4(ein + 2 * cs + base); }
+    if (kfirst == kbeg && own) { hx_km = ld4(hout + base - sz); hy_km = ld4(hout + cs + base - sz); }
+
+    for (int k = kfirst; k < kend; ++k, base += sz) {
+        const bool pro = k < kbeg;                           // prologue plane: H_new only, nothing stored
+        float4 ex1 = zero4(), ey1 = zero4(), ez1 = zero4(), ez_jp = zero4(), ex_jp = zero4();
+        float4 hx = zero4(), hy = zero4(), hz = zero4();
+        float4 ax = zero4(), ay = zero4(), az = zero4(), bx = zero4(), by = zero4(), bz = zero4();
+        float ez_e = 0.f, ey_e = 0.f;
+        if (p.pf > 0 && in_grid && k + p.pf < kend) {
+            // the march is a chain of DRAM round trips with few warps per SM: pull the planes of a later iteration into L2
+            const long long d = (long long)p.pf * sz;
+            prefetch_l2(ein + base + sz + d); prefetch_l2(ein + cs + base + sz + d); prefetch_l2(ein + 2 * cs + base + sz + d);
+            if (calc) { prefetch_l2(hin + base + d); prefetch_l2(hin + cs + base + d); prefetch_l2(hin + 2 * cs + base + d); }
+        }
+        if (in_grid) {
+            ex1 = ld4(ein + base + sz); ey1 = ld4(ein + cs + base + sz); ez1 = ld4(ein + 2 * cs + base + sz);
+            if (has_jp) { ez_jp = ld4(ein + 2 * cs + base + p.px); ex_jp = ld4(ein + base + p.px); }
+        }
+        if (calc) {
+            hx = ld4_stream(hin + base); hy = ld4_stream(hin + cs + base); hz = ld4_stream(hin + 2 * cs + base);
+            load_coefs6<CMP>(p.ii, p.iv, p.xv_h, p.meta_h, base, cs, (long long)(k + 1) * p.ny + j, p.ny, i0, p.px, ax, ay, az, bx, by, bz);
+        } else if (ext) {
+            hx = ld4(hout + base); hy = ld4(hout + cs + base); hz = ld4(hout + 2 * cs + base);
+        }
+        if (edge_load) { ez_e = ein[2 * cs + base + 4]; ey_e = ein[cs + base + 4]; }
+        float ez_r = __shfl_down_sync(0xffffffffu, ez.x, 1);
+        float ey_r = __shfl_down_sync(0xffffffffu, ey.x, 1);
+        if (lane == 31) { ez_r = ez_e; ey_r = ey_e; }
+        if (calc) {
+            const float4 ez_ip = make_float4(ez.y, ez.z, ez.w, ez_r);
+            const float4 ey_ip = make_float4(ey.y, ey.z, ey.w, ey_r);
+            hx = upd4(ax, hx, bx, ez, ez_jp, ey, ey1);
+            hy = upd4(ay, hy, by, ex, ex1, ez, ez_ip);
+            hz = upd4(az, hz, bz, ey, ey_ip, ex, ex_jp);
+        }
+        // hx, hy, hz now hold H_new(k) (zero outside the grid)
+        if (!pro) {
+            if (own) { st4(hout + base, hx); st4(hout + cs + base, hy); st4(hout + 2 * cs + base, hz); }
+            xb[k & 1][r][0][lane] = hz; xb[k & 1][r][1][lane] = hx;
+            __syncthreads();
+            const float hz_l = __shfl_up_sync(0xffffffffu, hz.w, 1);
+            const float hy_l = __shfl_up_sync(0xffffffffu, hy.w, 1);
+            if (own) {
+                const float4 hz_jm = xb[k & 1][r - 1][0][lane], hx_jm = xb[k & 1][r - 1][1][lane];
+                const float4 hz_im = make_float4(hz_l, hz.x, hz.y, hz.z);
+                const float4 hy_im = make_float4(hy_l, hy.x, hy.y, hy.z);
+                load_coefs6<CMP>(p.vv, p.vi, p.xv_e, p.meta_e, base, cs, (long long)(k + 1) * p.ny + j, p.ny, i0, p.px, ax, ay, az, bx, by, bz);
+                ex = upd4(ax, ex, bx, hz, hz_jm, hy, hy_km);
+                ey = upd4(ay, ey, by, hx, hx_km, hz, hz_im);
+                ez = upd4(az, ez, bz, hy, hy_im, hx, hx_jm);
+                st4(eout + base, ex); st4(eout + cs + base, ey); st4(eout + 2 * cs + base, ez);
+            }
+        }
+        hx_km = hx; hy_km = hy;
+        ex = ex1; ey = ey1; ez = ez1;
+    }
+}
+
+
+// ---- the same sweep with the planes staged through shared memory by cp.async (LDGSTS) ----
+// The register version above is bound by DRAM latency: 16 warps per SM, each waiting on the loads of its own plane.
+// Here every thread copies the float4s it will need one plane ahead straight into shared memory (no registers held while
+// the copy is in flight), so a CTA always has a whole plane of loads outstanding while it computes the previous one, and
+// the y-neighbour rows come from shared memory instead of a second global load.
+//   E ring: HE_DIST+2 planes (k and k+1 in use, the rest landing)   [3 comps][TY+2 rows][33 float4]   (row TY+1 / column 32 = +1 halo)
+//   H ring: HE_DIST+1 planes (k in use, the rest landing)           [3 comps][TY+1 rows][32 float4]
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid)
+{
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem);
+    const int n = valid ? 16 : 0;                            // 0 source bytes: the 16 destination bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(gmem), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+#define HE_DIST 2           // planes in flight ahead of the one being computed
+template <int TY>
+struct HeSmem {
+    float4 e[HE_DIST + 2][3][TY + 2][33];
+    float4 h[HE_DIST + 1][3][TY + 1][32];
+    float4 xb[2][TY + 1][2][32];
+};
+
+template <int TY, bool CMP>
+__global__ void __launch_bounds__(32 * (TY + 1), 16 / (TY + 1)) update_he_staged_kernel(const HeParams p)
+{
+    extern __shared__ __align__(16) unsigned char he_smem_raw[];
+    HeSmem<TY>& S = *reinterpret_cast<HeSmem<TY>*>(he_smem_raw);
+    const int lane = threadIdx.x, r = threadIdx.y;
+    const int i0 = p.X0 - 4 + HE_SEG * (int)blockIdx.x + 4 * lane;
+    const int j = p.Y0 - 1 + TY * (int)blockIdx.y + r;
+    const int kbeg = p.Z0 + (int)blockIdx.z * p.kz;
+    const int kend = min(kbeg + p.kz, p.Z1);
+    const bool col_ok = i0 >= 0 && i0 < p.px;
+    const bool in_grid = col_ok && j >= 0 && j < p.Y1;      // rows >= Y1 are needed only as the +1 neighbour row
+    const bool reg_x = (i0 >= p.X0 && i0 < p.X1) || i0 >= p.XT0;
+    const bool ext = in_grid && (!reg_x || j < p.Y0);       // H_new was written by a slab launch: read it
+    const bool calc = in_grid && !ext;
+    const bool own = calc && lane >= 1 && r >= 1;
+    // what this thread stages: its own float4 of E (any row of the grid up to Y1, which is the +1 row of the last owned
+    // row), the +1 row for the top warp, the +1 column for lane 31, and its own float4 of H_old where H_new is computed
+    const bool e_ok = col_ok && j >= 0 && j < p.ny && j <= p.Y1;
+    const bool top = r == TY;
+    const bool e_top_ok = top && col_ok && j + 1 < p.ny && j + 1 <= p.Y1;
+    const bool e_col_ok = lane == 31 && i0 + 4 < p.px && j >= 0 && j < p.Y1;
+    const long long cs = p.cs, sz = p.sz;
+    const float* __restrict__ ein = p.ein; const float* __restrict__ hin = p.hin;
+    float* __restrict__ eout = p.eout; float* hout = p.hout;
+    const long long rowoff = (long long)j * p.px + i0;       // may be "negative" for halo threads: only used when valid
+
+    auto stage_e = [&](int k) {                              // E_old(k) -> ring slot k % (HE_DIST+2)
+        const int s = k % (HE_DIST + 2);
+        const long long b = (long long)(k + 1) * sz + rowoff;
+        const float* src = e_ok ? ein + b : ein;
+        cp_async16(&S.e[s][0][r][lane], src, e_ok);
+        cp_async16(&S.e[s][1][r][lane], src + (e_ok ? cs : 0), e_ok);
+        cp_async16(&S.e[s][2][r][lane], src + (e_ok ? 2 * cs : 0), e_ok);
+        if (top) {                                           // row TY+1: (ex, ez) of row j+1
+            const float* st = e_top_ok ? ein + b + p.px : ein;
+            cp_async16(&S.e[s][0][TY + 1][lane], st, e_top_ok);
+            cp_async16(&S.e[s][2][TY + 1][lane], st + (e_top_ok ? 2 * cs : 0), e_top_ok);
+        }
+        if (lane == 31) {                                    // column 32: (ey, ez) of the float4 right of the segment
+            const float* sc = e_col_ok ? ein + b + 4 : ein;
+            cp_async16(&S.e[s][1][r][32], sc + (e_col_ok ? cs : 0), e_col_ok);
+            cp_async16(&S.e[s][2][r][32], sc + (e_col_ok ? 2 * cs : 0), e_col_ok);
+        }
+    };
+    auto stage_h = [&](int k) {                              // H_old(k) -> ring slot k % (HE_DIST+1)
+        const int s = k % (HE_DIST + 1);
+        const float* src = calc ? hin + (long long)(k + 1) * sz + rowoff : hin;
+        cp_async16(&S.h[s][0][r][lane], src, calc);
+        cp_async16(&S.h[s][1][r][lane], src + (calc ? cs : 0), calc);
+        cp_async16(&S.h[s][2][r][lane], src + (calc ? 2 * cs : 0), calc);
+    };
+
+    const int kfirst = kbeg > p.Z0 ? kbeg - 1 : kbeg;        // one plane below the chunk: H_new(kbeg-1) is recomputed
+    // one commit group per plane of the march: group d holds what iteration kfirst+d needs on top of the groups before it
+    stage_e(kfirst); stage_e(kfirst + 1); stage_h(kfirst);
+    cp_async_commit();
+#pragma unroll
+    for (int d = 1; d < HE_DIST; ++d) {
+        if (kfirst + d < kend) { stage_e(kfirst + d + 1); stage_h(kfirst + d); }
+        cp_async_commit();
+    }
+    long long base = (long long)(kfirst + 1) * sz + rowoff;  // plane kfirst (ghost offset +1)
+    float4 hx_km = zero4(), hy_km = zero4();                 // H_new(k-1)
+    if (kfirst == kbeg && own) { hx_km = ld4(hout + base - sz); hy_km = ld4(hout + cs + base - sz); }
+    cp_async_wait<HE_DIST - 1>();
+    __syncthreads();
+
+    for (int k = kfirst; k < kend; ++k, base += sz) {
+        const bool pro = k < kbeg;                           // prologue plane: H_new only, nothing stored
+        if (k + HE_DIST < kend) { stage_e(k + HE_DIST + 1); stage_h(k + HE_DIST); }
+        cp_async_commit();
+        const int se = k % (HE_DIST + 2), se1 = (k + 1) % (HE_DIST + 2), sh = k % (HE_DIST + 1);
+        float4 hx = zero4(), hy = zero4(), hz = zero4();
+        float4 ax, ay, az, bx, by, bz;
+        const float4 ex = S.e[se][0][r][lane], ey = S.e[se][1][r][lane], ez = S.e[se][2][r][lane];
+        if (calc) {
+            load_coefs6<CMP>(p.ii, p.iv, p.xv_h, p.meta_h, base, cs, (long long)(k + 1) * p.ny + j, p.ny, i0, p.px, ax, ay, az, bx, by, bz);
+            hx = S.h[sh][0][r][lane]; hy = S.h[sh][1][r][lane]; hz = S.h[sh][2][r][lane];
+        } else if (ext) {
+            hx = ld4(hout + base); hy = ld4(hout + cs + base); hz = ld4(hout + 2 * cs + base);
+        }
+        float ez_r = __shfl_down_sync(0xffffffffu, ez.x, 1);
+        float ey_r = __shfl_down_sync(0xffffffffu, ey.x, 1);
+        if (lane == 31) { ez_r = S.e[se][2][r][32].x; ey_r = S.e[se][1][r][32].x; }
+        if (calc) {
+            const float4 ex1 = S.e[se1][0][r][lane], ey1 = S.e[se1][1][r][lane];
+            const float4 ex_jp = S.e[se][0][r + 1][lane], ez_jp = S.e[se][2][r + 1][lane];
+            const float4 ez_ip = make_float4(ez.y, ez.z, ez.w, ez_r);
+            const float4 ey_ip = make_float4(ey.y, ey.z, ey.w, ey_r);
+            hx = upd4(ax, hx, bx, ez, ez_jp, ey, ey1);
+            hy = upd4(ay, hy, by, ex, ex1, ez, ez_ip);
+            hz = upd4(az, hz, bz, ey, ey_ip, ex, ex_jp);
+        }
+        // hx, hy, hz now hold H_new(k) (zero outside the grid)
+        if (own && !pro) { st4(hout + base, hx); st4(hout + cs + base, hy); st4(hout + 2 * cs + base, hz); }
+        S.xb[k & 1][r][0][lane] = hz; S.xb[k & 1][r][1][lane] = hx;
+        cp_async_wait<HE_DIST - 1>();                        // the next plane has landed (this thread's copies) ...
+        __syncthreads();                                     // ... and everybody's, together with this plane's H_new rows
+        const float hz_l = __shfl_up_sync(0xffffffffu, hz.w, 1);
+        const float hy_l = __shfl_up_sync(0xffffffffu, hy.w, 1);
+        if (own && !pro) {
+            const float4 hz_jm = S.xb[k & 1][r - 1][0][lane], hx_jm = S.xb[k & 1][r - 1][1][lane];
+            const float4 hz_im = make_float4(hz_l, hz.x, hz.y, hz.z);
+            const float4 hy_im = make_float4(hy_l, hy.x, hy.y, hy.z);
+            load_coefs6<CMP>(p.vv, p.vi, p.xv_e, p.meta_e, base, cs, (long long)(k + 1) * p.ny + j, p.ny, i0, p.px, ax, ay, az, bx, by, bz);
+            const float4 exn = upd4(ax, ex, bx, hz, hz_jm, hy, hy_km);
+            const float4 eyn = upd4(ay, ey, by, hx, hx_km, hz, hz_im);
+            const float4 ezn = upd4(az, ez, bz, hy, hy_im, hx, hx_jm);
+            st4(eout + base, exn); st4(eout + cs + base, eyn); st4(eout + 2 * cs + base, ezn);
+        }
+        hx_km = hx; hy_km = hy;
+    }
+}
+
+
+// ---- the register version again, with the address arithmetic written out ----
+// update_he_kernel spends ~60 % of its instructions on 64-bit index arithmetic and on the "row streamed in full"
+// alternative of every coefficient; with 16 warps per SM that, not DRAM, bounds it.  Here every array has one per-thread
+// byte pointer that advances by a plane per iteration, all other offsets are launch constants, the x-vector of a
+// compressed row is one mad.wide away, and rows with a slot streamed in full take a (warp-uniform) side path.
+__device__ __forceinline__ float4 ldb4(const char* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ldb4_cs(const char* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ldb4_nc(const char* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void stb4(char* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 xv4(const float4* xs, unsigned id, float sc)      // xs = this lane's column of the smem copy
+{
+    const float4 v = xs[id * 32];
+    return make_float4(__fmul_rn(sc, v.x), __fmul_rn(sc, v.y), __fmul_rn(sc, v.z), __fmul_rn(sc, v.w));
+}
+#define ROW_ANY_FULL(w1) (((w1) >> 16) & 255u)       // pad[0] of the record: set on the device when a slot is streamed in full
+
+// coefficients of one row from its record (m0, m1 = the two float4 halves of the 32-byte record, already in registers)
+__device__ __forceinline__ void row_coefs(const float4 m0, const float4 m1, const float4* xs,
+        const float* __restrict__ ca, const float* __restrict__ cb, const float* __restrict__ xv, long long base, long long cs, int i0, int px,
+        float4& ax, float4& ay, float4& az, float4& bx, float4& by, float4& bz)
+{
+    const unsigned w0 = __float_as_uint(m1.z), w1 = __float_as_uint(m1.w);
+    if (ROW_ANY_FULL(w1) == 0) {
+        ax = xv4(xs, w0 & 255u, m0.x);
+        ay = xv4(xs, (w0 >> 8) & 255u, m0.y);
+        az = xv4(xs, (w0 >> 16) & 255u, m0.z);
+        bx = xv4(xs, w0 >> 24, m0.w);
+        by = xv4(xs, w1 & 255u, m1.x);
+        bz = xv4(xs, (w1 >> 8) & 255u, m1.y);
+    } else {
+        ax = coef4(w0 & 255u, m0.x, ca + base, xv, i0, px);
+        ay = coef4((w0 >> 8) & 255u, m0.y, ca + cs + base, xv, i0, px);
+        az = coef4((w0 >> 16) & 255u, m0.z, ca + 2 * cs + base, xv, i0, px);
+        bx = coef4(w0 >> 24, m0.w, cb + base, xv, i0, px);
+        by = coef4(w1 & 255u, m1.x, cb + cs + base, xv, i0, px);
+        bz = coef4((w1 >> 8) & 255u, m1.y, cb + 2 * cs + base, xv, i0, px);
+    }
+}
+
+template <int TY>
+__global__ void __launch_bounds__(32 * (TY + 1), 16 / (TY + 1)) update_he2_kernel(const HeParams p)
+{
+    __shared__ float4 xb[2][TY + 1][2][32];
+    // row records of the H and E pass, staged one plane ahead by the warp that uses them (lanes 0-3, cp.async): the
+    // records steer dependent loads, so they must not cost a cache miss on the critical path of the march
+    __shared__ float4 ms[2][TY + 1][4];
+    // the CTA's 128-column slice of every x-vector ([nv_h + nv_e][32] float4, loaded once): a coefficient of a compressed
+    // row is one LDS and one multiply
+    extern __shared__ float4 xs_all[];
+    const int lane = threadIdx.x, r = threadIdx.y;
+    const int i0 = p.X0 - 4 + HE_SEG * (int)blockIdx.x + 4 * lane;
+    {
+        const bool col_ok = i0 >= 0 && i0 < p.px;
+        for (int v = r; v < p.nv_h + p.nv_e; v += TY + 1) {
+            const float* src = v < p.nv_h ? p.xv_h + (size_t)v * p.px : p.xv_e + (size_t)(v - p.nv_h) * p.px;
+            xs_all[v * 32 + lane] = col_ok ? __ldg(reinterpret_cast<const float4*>(src + i0)) : zero4();
+        }
+    }
+    const float4* xsh = xs_all + lane;
+    const float4* xse = xs_all + p.nv_h * 32 + lane;
+    const int j = p.Y0 - 1 + TY * (int)blockIdx.y + r;
+    const int kbeg = p.Z0 + (int)blockIdx.z * p.kz;
+    const int kend = min(kbeg + p.kz, p.Z1);
+    const bool in_grid = i0 >= 0 && i0 < p.px && j >= 0 && j < p.Y1;
+    const bool reg_x = (i0 >= p.X0 && i0 < p.X1) || i0 >= p.XT0;
+    const bool ext = in_grid && (!reg_x || j < p.Y0);
+    const bool calc = in_grid && !ext;
+    const bool own = calc && lane >= 1 && r >= 1;
+    const bool has_jp = in_grid && j + 1 < p.ny;
+    const bool edge_load = in_grid && lane == 31 && i0 + 4 < p.px;
+    const bool row_ok = j >= 0 && j < p.Y1;                  // the row has records (warp-uniform)
+    const int kfirst = kbeg > p.Z0 ? kbeg - 1 : kbeg;
+    const long long base0 = (long long)(kfirst + 1) * p.sz + (long long)j * p.px + i0;
+    const long long mrow0 = ((long long)(kfirst + 1) * p.ny + j) * 32;
+    // per-thread plane pointers (never dereferenced where the thread is outside the grid)
+    const char* pe = reinterpret_cast<const char*>(p.ein + base0);
+    const char* ph = reinterpret_cast<const char*>(p.hin + base0);
+    char* qe = reinterpret_cast<char*>(p.eout + base0);
+    char* qh = reinterpret_cast<char*>(p.hout + base0);
+    // lanes 0,1 stage the H record, lanes 2,3 the E record of this warp's row
+    const char* mrec = (lane < 2 ? reinterpret_cast<const char*>(p.meta_h) : reinterpret_cast<const char*>(p.meta_e)) + mrow0 + (lane & 1) * 16;
+
+    float4 ex = zero4(), ey = zero4(), ez = zero4();         // E_old(k)
+    float4 hx_km = zero4(), hy_km = zero4();                 // H_new(k-1)
+    if (lane < 4) cp_async16(&ms[kfirst & 1][r][lane], row_ok ? mrec : reinterpret_cast<const char*>(p.meta_h), row_ok);
+    cp_async_commit();
+    if (in_grid) { ex = ldb4(pe); ey = ldb4(pe + p.b_cs); ez = ldb4(pe + p.b_2cs); }
+    if (kfirst == kbeg && own) { hx_km = ldb4(qh - p.b_sz); hy_km = ldb4(qh - p.b_sz + p.b_cs); }
+    cp_async_wait<0>();
+    __syncthreads();                                         // x-vector slices and the first records are in place
+
+    for (int k = kfirst; k < kend; ++k, pe += p.b_sz, ph += p.b_sz, qe += p.b_sz, qh += p.b_sz, mrec += p.meta_step) {
+        const bool pro = k < kbeg;
+        float4 ex1 = zero4(), ey1 = zero4(), ez1 = zero4(), ez_jp = zero4(), ex_jp = zero4();
+        float4 hx = zero4(), hy = zero4(), hz = zero4();
+        float4 ax = zero4(), ay = zero4(), az = zero4(), bx = zero4(), by = zero4(), bz = zero4();
+        float ez_e = 0.f, ey_e = 0.f;
+        // next plane's records (ghost planes have records too)
+        if (lane < 4) cp_async16(&ms[(k + 1) & 1][r][lane], row_ok ? mrec + p.meta_step : reinterpret_cast<const char*>(p.meta_h), row_ok);
+        cp_async_commit();
+        if (in_grid) {
+            if (p.pf > 0 && k + p.pf < kend) {
+                prefetch_l2(pe + p.b_pfe[0]); prefetch_l2(pe + p.b_pfe[1]); prefetch_l2(pe + p.b_pfe[2]);
+                if (calc) { prefetch_l2(ph + p.b_pfh[0]); prefetch_l2(ph + p.b_pfh[1]); prefetch_l2(ph + p.b_pfh[2]); }
+            }
+            ex1 = ldb4(pe + p.b_sz); ey1 = ldb4(pe + p.b_sz_cs); ez1 = ldb4(pe + p.b_sz_2cs);
+            if (has_jp) { ex_jp = ldb4(pe + p.b_row); ez_jp = ldb4(pe + p.b_row_2cs); }
+        }
+        if (calc) {
+            hx = ldb4_cs(ph); hy = ldb4_cs(ph + p.b_cs); hz = ldb4_cs(ph + p.b_2cs);
+            row_coefs(ms[k & 1][r][0], ms[k & 1][r][1], xsh, p.ii, p.iv, p.xv_h,
+                      (long long)((ph - reinterpret_cast<const char*>(p.hin)) >> 2), p.cs, i0, p.px, ax, ay, az, bx, by, bz);
+        } else if (ext) {
+            hx = ldb4(qh); hy = ldb4(qh + p.b_cs); hz = ldb4(qh + p.b_2cs);
+        }
+        if (edge_load) { ey_e = *reinterpret_cast<const float*>(pe + p.b_cs + 16); ez_e = *reinterpret_cast<const float*>(pe + p.b_2cs + 16); }
+        float ez_r = __shfl_down_sync(0xffffffffu, ez.x, 1);
+        float ey_r = __shfl_down_sync(0xffffffffu, ey.x, 1);
+        if (lane == 31) { ez_r = ez_e; ey_r = ey_e; }
+        if (calc) {
+            const float4 ez_ip = make_float4(ez.y, ez.z, ez.w, ez_r);
+            const float4 ey_ip = make_float4(ey.y, ey.z, ey.w, ey_r);
+            hx = upd4(ax, hx, bx, ez, ez_jp, ey, ey1);
+            hy = upd4(ay, hy, by, ex, ex1, ez, ez_ip);
+            hz = upd4(az, hz, bz, ey, ey_ip, ex, ex_jp);
+        }
+        if (own && !pro) {
+            stb4(qh, hx); stb4(qh + p.b_cs, hy); stb4(qh + p.b_2cs, hz);
+            // the E coefficients do not depend on H_new: fetch them before the barrier, into the registers the H pass freed
+            row_coefs(ms[k & 1][r][2], ms[k & 1][r][3], xse, p.vv, p.vi, p.xv_e,
+                      (long long)((pe - reinterpret_cast<const char*>(p.ein)) >> 2), p.cs, i0, p.px, ax, ay, az, bx, by, bz);
+        }
+        xb[k & 1][r][0][lane] = hz; xb[k & 1][r][1][lane] = hx;
+        cp_async_wait<0>();                                  // next plane's records (this warp's own copies)
+        __syncthreads();
+        const float hz_l = __shfl_up_sync(0xffffffffu, hz.w, 1);
+        const float hy_l = __shfl_up_sync(0xffffffffu, hy.w, 1);
+        if (own && !pro) {
+            const float4 hz_jm = xb[k & 1][r - 1][0][lane], hx_jm = xb[k & 1][r - 1][1][lane];
+            const float4 hz_im = make_float4(hz_l, hz.x, hz.y, hz.z);
+            const float4 hy_im = make_float4(hy_l, hy.x, hy.y, hy.z);
+            ex = upd4(ax, ex, bx, hz, hz_jm, hy, hy_km);
+            ey = upd4(ay, ey, by, hx, hx_km, hz, hz_im);
+            ez = upd4(az, ez, bz, hy, hy_im, hx, hx_jm);
+            stb4(qe, ex); stb4(qe + p.b_cs, ey); stb4(qe + p.b_2cs, ez);
+        }
+        hx_km = hx; hy_km = hy;
+        ex = ex1; ey = ey1; ez = ez1;
     }
 }
 
@@ -639,6 +1074,8 @@ static int build_plan(b200fdtd_ctx* c)
     }
     P.nseg = 0;
     if (zhi > zlo) { P.seg0[0] = zlo; P.seg1[0] = zhi; P.nseg = 1; }
+    P.ym0 = 0; P.ym1 = c->ny;
+    for (int q = 0; q < P.nskip; ++q) { if (P.sj0[q] == 0) P.ym0 = P.sj1[q]; else P.ym1 = P.sj0[q]; }
     P.valid = true;
     c->plan = P;
     c->pml = rest;
@@ -723,7 +1160,9 @@ static int launch_volume_fused(b200fdtd_ctx* c, int which, int k0, int k1, cudaS
         // thin slabs: march fewer planes per CTA so the launch still fills the machine (>= ~8 CTAs per SM)
         const long long per_chunk = (long long)((c->px + 127) / 128) * ((B.by + slab_ty(c) - 1) / slab_ty(c));
         const int kz = slab_kz(c->kz, b - a, per_chunk);
-        if (launch_volume_one<1>(c, which, a, b, f, stream, kz, (c->px + 127) / 128)) return 1;
+        cudaStream_t st = stream;
+        if (stream == c->side2 && q > 0 && q <= 3 && (c->variant & 1024) == 0) st = c->slab_s[q - 1];
+        if (launch_volume_one<1>(c, which, a, b, f, st, kz, (c->px + 127) / 128)) return 1;
     }
     return 0;
 }
@@ -738,12 +1177,97 @@ static int launch_volume(b200fdtd_ctx* c, int which, int k0, int k1)
     return launch_volume_fused(c, which, k0, k1, c->stream);
 }
 
+
+// fused H->E launch over the plain region: reads the current copies, writes the other copies (the caller flips)
+static int launch_he(b200fdtd_ctx* c, cudaStream_t stream)
+{
+    const VolumePlan& P = c->plan;
+    if (P.nseg != 1) return fail("fused H->E launch without a plain region");
+    HeParams p;
+    p.ein = cur_volt(c); p.hin = cur_curr(c); p.eout = oth_volt(c); p.hout = oth_curr(c);
+    p.vv = c->vv; p.vi = c->vi; p.ii = c->ii; p.iv = c->iv;
+    const bool cmp = c->cmp_meta[0] != nullptr && c->cmp_meta[1] != nullptr && (c->variant & 4) == 0;
+    p.xv_e = c->cmp_xv[0]; p.meta_e = c->cmp_meta[0]; p.xv_h = c->cmp_xv[1]; p.meta_h = c->cmp_meta[1];
+    p.ny = c->ny; p.px = c->px; p.sz = c->sz; p.cs = c->cs;
+    p.X0 = P.has_lo ? P.xw0 : 0; p.X1 = P.has_hi ? P.xx1 : c->px; p.XT0 = P.has_hi ? P.xx1 + P.xw1 : c->px;
+    p.Y0 = P.ym0; p.Y1 = P.ym1; p.Z0 = P.seg0[0]; p.Z1 = P.seg1[0];
+    if (p.Y1 <= p.Y0 || p.Z1 <= p.Z0 || p.X1 <= p.X0) return fail("fused H->E launch over an empty region");
+    const int ty = c->he_ty;
+    int kz = c->he_kz; if (kz > p.Z1 - p.Z0) kz = p.Z1 - p.Z0;
+    { const int n = (p.Z1 - p.Z0 + kz - 1) / kz; kz = (p.Z1 - p.Z0 + n - 1) / n; }      // chunks of equal length
+    p.kz = kz;
+    p.pf = (c->variant >> 16) & 3;                   // L2 prefetch distance in planes: 0 = default (1), 3 = off
+    p.pf = p.pf == 0 ? 1 : (p.pf == 3 ? 0 : p.pf);
+    dim3 block(32, ty + 1);
+    dim3 grid((c->px - p.X0 + HE_SEG - 1) / HE_SEG, (p.Y1 - p.Y0 + ty - 1) / ty, (p.Z1 - p.Z0 + kz - 1) / kz);
+    if (grid.y > 65535 || grid.z > 65535) return fail("grid too large for the fused launch");
+    p.b_sz = 4 * p.sz; p.b_cs = 4 * p.cs; p.b_2cs = 8 * p.cs; p.b_sz_cs = 4 * (p.sz + p.cs); p.b_sz_2cs = 4 * (p.sz + 2 * p.cs);
+    p.b_row = 4LL * p.px; p.b_row_2cs = 4 * (p.px + 2 * p.cs);
+    for (int q = 0; q < 3; ++q) { p.b_pfe[q] = 4 * ((1 + p.pf) * p.sz + q * p.cs); p.b_pfh[q] = 4 * (p.pf * p.sz + q * p.cs); }
+    p.xv_pitch = 4u * (unsigned)p.px; p.meta_step = 32 * p.ny;
+    const bool staged = (c->variant & 256) != 0;
+    p.nv_e = c->cmp_nvec[0]; p.nv_h = c->cmp_nvec[1];
+    const size_t xs_bytes = (size_t)(p.nv_e + p.nv_h) * 32 * sizeof(float4);
+    const bool v2 = cmp && (c->variant & 512) == 0 && xs_bytes <= 96 * 1024;
+#define LAUNCH_HE(TYV) do { \
+        if (v2) { if (xs_bytes > 8 * 1024) CK(cudaFuncSetAttribute(update_he2_kernel<TYV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xs_bytes)); \
+                  update_he2_kernel<TYV><<<grid, block, xs_bytes, stream>>>(p); } \
+        else if (staged) { \
+            const size_t sm = sizeof(HeSmem<TYV>); \
+            if (cmp) { CK(cudaFuncSetAttribute(update_he_staged_kernel<TYV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+                       update_he_staged_kernel<TYV, true><<<grid, block, sm, stream>>>(p); } \
+            else { CK(cudaFuncSetAttribute(update_he_staged_kernel<TYV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+                   update_he_staged_kernel<TYV, false><<<grid, block, sm, stream>>>(p); } \
+        } else if (cmp) update_he_kernel<TYV, true><<<grid, block, 0, stream>>>(p); \
+        else update_he_kernel<TYV, false><<<grid, block, 0, stream>>>(p); } while (0)
+    switch (ty) {
+        case 3: LAUNCH_HE(3); break;
+        case 7: LAUNCH_HE(7); break;
+        case 15: LAUNCH_HE(15); break;
+        default: return fail("unsupported fused-launch tile height %d", ty);
+    }
+#undef LAUNCH_HE
+    CKL();
+    return 0;
+}
+
+// can one graph chunk of `steps` steps use the fused H->E launches?  (single slab, every PML box fused into the volume
+// launches, a plain region, memory for the second copy of the fields)
+static bool he_ready(b200fdtd_ctx* c, int steps)
+{
+    if ((c->variant & 128) || steps < 2 || !c->plan.valid || c->pml.n > 0 || c->plan.nseg != 1) return false;
+    const VolumePlan& P = c->plan;
+    if (P.ym1 <= P.ym0 || (P.has_hi ? P.xx1 : c->px) <= (P.has_lo ? P.xw0 : 0)) return false;
+    if (!c->alt_volt) {
+        const size_t bytes = sizeof(float) * 3 * (size_t)c->cs;
+        if (cudaMalloc((void**)&c->alt_volt, bytes) != cudaSuccess) { cudaGetLastError(); c->alt_volt = nullptr; return false; }
+        if (cudaMalloc((void**)&c->alt_curr, bytes) != cudaSuccess) { cudaGetLastError(); cudaFree(c->alt_volt); c->alt_volt = c->alt_curr = nullptr; return false; }
+        cudaMemsetAsync(c->alt_volt, 0, bytes, c->stream);
+        cudaMemsetAsync(c->alt_curr, 0, bytes, c->stream);
+    }
+    return true;
+}
+
+// ghost planes of the second copy follow the bound arrays (the caller may rewrite its ghost planes between runs)
+static int sync_alt_ghosts(b200fdtd_ctx* c)
+{
+    if (!c->alt_volt) return 0;
+    const size_t pitch = sizeof(float) * (size_t)c->cs, w = sizeof(float) * (size_t)c->sz;
+    const long long top = (long long)(c->nz + 1) * c->sz;
+    CK(cudaMemcpy2DAsync(c->alt_volt, pitch, c->volt, pitch, w, 3, cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaMemcpy2DAsync(c->alt_volt + top, pitch, c->volt + top, pitch, w, 3, cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaMemcpy2DAsync(c->alt_curr, pitch, c->curr, pitch, w, 3, cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaMemcpy2DAsync(c->alt_curr + top, pitch, c->curr + top, pitch, w, 3, cudaMemcpyDeviceToDevice, c->stream));
+    return 0;
+}
+
 // fork/join of the side stream that runs the fused PML slab launches next to the plain launch
 static int fork_side(b200fdtd_ctx* c)
 {
     CK(cudaEventRecord(c->ev_fork, c->stream));
     CK(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
     CK(cudaStreamWaitEvent(c->side2, c->ev_fork, 0));
+    for (int q = 0; q < 3; ++q) CK(cudaStreamWaitEvent(c->slab_s[q], c->ev_fork, 0));
     return 0;
 }
 static int join_side(b200fdtd_ctx* c)
@@ -752,6 +1276,7 @@ static int join_side(b200fdtd_ctx* c)
     CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
     CK(cudaEventRecord(c->ev_join2, c->side2));
     CK(cudaStreamWaitEvent(c->stream, c->ev_join2, 0));
+    for (int q = 0; q < 3; ++q) { CK(cudaEventRecord(c->slab_ev[q], c->slab_s[q])); CK(cudaStreamWaitEvent(c->stream, c->slab_ev[q], 0)); }
     return 0;
 }
 // the stream of the whole-row slab launches: their own side stream, or the x-slab one (variant bit 64)
@@ -1037,10 +1562,14 @@ extern "C" int b200fdtd_create(b200fdtd_ctx** out, int device, int nx, int ny, i
     c->side = c->side_lo;
     CK(cudaStreamCreateWithFlags(&c->side2, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&c->ev_join2, cudaEventDisableTiming));
+    for (int q = 0; q < 3; ++q) { CK(cudaStreamCreateWithFlags(&c->slab_s[q], cudaStreamNonBlocking));
+                                  CK(cudaEventCreateWithFlags(&c->slab_ev[q], cudaEventDisableTiming)); }
     CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     CK(cudaMalloc((void**)&c->d_ts, sizeof(int)));
     CK(cudaMemsetAsync(c->d_ts, 0, sizeof(int), c->stream));
+    if (const char* e = getenv("B200FDTD_HE_TY")) { const int t = atoi(e); if (t == 3 || t == 7 || t == 15) c->he_ty = t; }
+    if (const char* e = getenv("B200FDTD_HE_KZ")) { const int t = atoi(e); if (t >= 1) c->he_kz = t; }
     c->n_partials = 148 * 8;
     CK(cudaMalloc((void**)&c->d_partials, sizeof(double) * 2 * c->n_partials));
     CK(cudaMalloc((void**)&c->d_energy, sizeof(double) * 2));
@@ -1055,6 +1584,7 @@ extern "C" int b200fdtd_destroy(b200fdtd_ctx* c)
     cudaStreamSynchronize(c->stream);
     drop_graph(c);
     cudaFree(c->d_ts); cudaFree(c->d_partials); cudaFree(c->d_energy);
+    cudaFree(c->alt_volt); cudaFree(c->alt_curr);
     cudaFree(c->exc_idx); cudaFree(c->exc_amp); cudaFree(c->exc_delay); cudaFree(c->exc_sig);
     cudaFree(c->mur_dst); cudaFree(c->mur_src); cudaFree(c->mur_coeff); cudaFree(c->mur_tmp);
     cudaFree(c->pr_kind); cudaFree(c->pr_off); cudaFree(c->pr_idx); cudaFree(c->pr_w); cudaFree(c->pr_freqs);
@@ -1065,6 +1595,8 @@ extern "C" int b200fdtd_destroy(b200fdtd_ctx* c)
     if (c->side_hi) { cudaStreamSynchronize(c->side_hi); cudaStreamDestroy(c->side_hi); }
     if (c->side2) { cudaStreamSynchronize(c->side2); cudaStreamDestroy(c->side2); }
     if (c->ev_join2) cudaEventDestroy(c->ev_join2);
+    for (int q = 0; q < 3; ++q) { if (c->slab_s[q]) { cudaStreamSynchronize(c->slab_s[q]); cudaStreamDestroy(c->slab_s[q]); }
+                                  if (c->slab_ev[q]) cudaEventDestroy(c->slab_ev[q]); }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -1131,6 +1663,17 @@ __global__ void __launch_bounds__(256) verify_rows_kernel(unsigned char* __restr
     }
 }
 
+// pad[0] of a row record = 1 if any of its six slots is streamed in full (the volume kernels branch on it once per row)
+__global__ void __launch_bounds__(256) flag_rows_kernel(unsigned char* __restrict__ meta, long long nrows)
+{
+    const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (q >= nrows) return;
+    RowMeta* M = reinterpret_cast<RowMeta*>(meta + q * 32);
+    bool any = false;
+    for (int sl = 0; sl < 6; ++sl) any |= M->id[sl] == ROW_FULL;
+    M->pad[0] = any ? 1 : 0;
+}
+
 extern "C" int b200fdtd_set_row_compression(b200fdtd_ctx* c, int which, int nvec, const float* xvecs, void* meta,
                                              int64_t* n_compressed, int64_t* n_demoted)
 {
@@ -1150,6 +1693,9 @@ extern "C" int b200fdtd_set_row_compression(b200fdtd_ctx* c, int which, int nvec
     verify_rows_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>((unsigned char*)meta, xvecs, nvec,
         which == 0 ? c->vv : c->ii, which == 0 ? c->vi : c->iv, c->ny, c->nz, c->px, c->sz, c->cs, d_counts);
     g_launches.fetch_add(1);
+    { const long long nrows = (long long)(c->nz + 2) * c->ny;
+      flag_rows_kernel<<<(unsigned)((nrows + 255) / 256), 256, 0, c->stream>>>((unsigned char*)meta, nrows);
+      g_launches.fetch_add(1); }
     cudaError_t e = cudaGetLastError();
     unsigned long long h[2] = {0, 0};
     if (e == cudaSuccess) e = cudaMemcpyAsync(h, d_counts, sizeof(h), cudaMemcpyDeviceToHost, c->stream);
@@ -1158,7 +1704,7 @@ extern "C" int b200fdtd_set_row_compression(b200fdtd_ctx* c, int which, int nvec
     if (e != cudaSuccess) return fail("row compression verification failed: %s", cudaGetErrorString(e));
     if (n_demoted) *n_demoted = (int64_t)h[0];
     if (n_compressed) *n_compressed = (int64_t)h[1];
-    c->cmp_xv[which] = xvecs; c->cmp_meta[which] = (const unsigned char*)meta;
+    c->cmp_xv[which] = xvecs; c->cmp_meta[which] = (const unsigned char*)meta; c->cmp_nvec[which] = nvec;
     return 0;
 }
 
@@ -1436,6 +1982,7 @@ static int e_half(b200fdtd_ctx* c, int off)
     if (!side) { if (launch_volume_xslabs(c, 0, 0, c->nz, c->stream)) return 1; if (launch_volume_fused(c, 0, 0, c->nz, c->stream)) return 1; }
     if (launch_pml(c, 0, 1)) return 1;
     if (side) if (join_side(c)) return 1;
+    if (c->flip) c->vcur ^= 1;                    // the new E lives in the other copy
     if (launch_mur(c, 1)) return 1;
     if (launch_excite(c, off)) return 1;
     if (launch_mur(c, 2)) return 1;
@@ -1452,7 +1999,37 @@ static int h_half(b200fdtd_ctx* c)
     if (!side) { if (launch_volume_xslabs(c, 1, 0, c->nz, c->stream)) return 1; if (launch_volume_fused(c, 1, 0, c->nz, c->stream)) return 1; }
     if (launch_pml(c, 1, 1)) return 1;
     if (side) if (join_side(c)) return 1;
+    if (c->flip) c->ccur ^= 1;
     return 0;
+}
+
+// H update of step n and E update of step n+1 in one sweep (graph chunks only; see update_he_kernel):
+//   PML slabs: H update into the other copy  ->  fused H->E launch over the plain region  ->  PML slabs: E update
+static int he_step(b200fdtd_ctx* c, int off)
+{
+    const bool slabs = c->plan.nfused > 0 || c->plan.xedge;
+    const bool side = slabs && (c->variant & 2) == 0;
+    if (launch_mur(c, 0)) return 1;              // Mur reads the old E
+    c->flip = true;
+    int rc = 0;
+    do {
+        if (side) { if ((rc = fork_side(c))) break; }
+        if ((rc = launch_volume_xslabs(c, 1, 0, c->nz, side ? c->side : c->stream))) break;
+        if ((rc = launch_volume_fused(c, 1, 0, c->nz, side ? slab_stream(c) : c->stream))) break;
+        if (side) { if ((rc = join_side(c))) break; }
+        if ((rc = launch_he(c, c->stream))) break;
+        c->ccur ^= 1;                            // H is new from here on
+        if (side) { if ((rc = fork_side(c))) break; }
+        if ((rc = launch_volume_xslabs(c, 0, 0, c->nz, side ? c->side : c->stream))) break;
+        if ((rc = launch_volume_fused(c, 0, 0, c->nz, side ? slab_stream(c) : c->stream))) break;
+        if (side) { if ((rc = join_side(c))) break; }
+        c->vcur ^= 1;
+    } while (0);
+    c->flip = false;
+    if (rc) return 1;
+    if (launch_mur(c, 1)) return 1;
+    if (launch_excite(c, off)) return 1;
+    return launch_mur(c, 2);
 }
 
 static int run_eager(b200fdtd_ctx* c, int64_t n)
@@ -1474,11 +2051,25 @@ static int build_graph(b200fdtd_ctx* c, int steps)
     const int iv = sample_interval(c);
     cudaGraph_t g = nullptr;
     const int64_t before = g_launches.load();
+    const bool fuse = he_ready(c, steps);           // allocates the second field copy: before the capture starts
+    c->he_fused = fuse;
     CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
     int rc = 0;
-    for (int s = 0; s < steps && !rc; ++s) {
-        rc = e_half(c, s);
-        if (!rc) rc = h_half(c);
+    if (!fuse) {
+        for (int s = 0; s < steps && !rc; ++s) {
+            rc = e_half(c, s);
+            if (!rc) rc = h_half(c);
+        }
+    } else {
+        // E(0) | H(0)+E(1) | ... | H(steps-2)+E(steps-1) | H(steps-1): each fused launch flips both copies; the two
+        // unfused half steps at the ends flip too when the number of fused launches is odd, so the chunk ends where it began
+        const bool odd = ((steps - 1) & 1) != 0;
+        c->vcur = c->ccur = 0;
+        c->flip = odd; rc = e_half(c, 0); c->flip = false;
+        for (int s = 1; s < steps && !rc; ++s) rc = he_step(c, s);
+        if (!rc) { c->flip = odd; rc = h_half(c); c->flip = false; }
+        if (!rc && (c->vcur || c->ccur)) rc = fail("fused chunk did not return to the bound field arrays");
+        c->vcur = c->ccur = 0;
     }
     if (!rc && iv > 0) rc = launch_sampling(c, steps);      // graph starts at ts % iv == 0 and spans iv steps
     if (!rc) rc = launch_ts_add(c, steps);
@@ -1514,6 +2105,7 @@ extern "C" int b200fdtd_run(b200fdtd_ctx* c, int64_t nsteps, int use_graph)
     }
     if (left >= chunk) {
         if (!c->graph || c->graph_steps != chunk) if (build_graph(c, chunk)) return 1;
+        if (c->he_fused) if (sync_alt_ghosts(c)) return 1;
         while (left >= chunk) {
             CK(cudaGraphLaunch(c->graph, c->stream));
             g_launches.fetch_add(c->graph_kernels, std::memory_order_relaxed);
@@ -1604,6 +2196,24 @@ extern "C" int b200fdtd_plan_info(b200fdtd_ctx* c, int64_t* plain_cells, int64_t
     for (int b = 0; b < c->pml.n; ++b) sep += (int64_t)c->pml.b[b].bx * c->pml.b[b].by * c->pml.b[b].bz;
     *plain_cells = (int64_t)c->px * (c->ny - skip) * planes;       // cells (incl. pad columns) swept by the plain launch
     *fused_cells = fused; *separate_cells = sep;
+    return 0;
+}
+
+extern "C" int b200fdtd_set_he_tuning(b200fdtd_ctx* c, int rows, int planes)
+{
+    if (!c) return fail("NULL ctx");
+    if (!(rows == 0 || rows == 3 || rows == 7 || rows == 15)) return fail("rows must be 0, 3, 7 or 15");
+    if (planes < 0) return fail("planes must be >= 0");
+    if (rows) c->he_ty = rows;
+    if (planes) c->he_kz = planes;
+    drop_graph(c);
+    return 0;
+}
+
+extern "C" int b200fdtd_he_info(b200fdtd_ctx* c, int* active)
+{
+    if (!c || !active) return fail("NULL argument");
+    *active = (c->graph && c->he_fused) ? 1 : 0;
     return 0;
 }
 

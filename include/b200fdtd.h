@@ -64,7 +64,9 @@ int b200fdtd_set_row_compression(b200fdtd_ctx* ctx, int which, int nvec, const f
                                  int64_t* n_compressed /*host out, may be NULL*/, int64_t* n_demoted /*host out, may be NULL*/);
 /* tuning knobs of the volume kernels: planes marched per CTA (kz), rows per CTA (ty in {2,4,8}),
  * variant bits: 1 = PML slabs by the separate pre/post kernel instead of fused rows, 2 = no side stream,
- * 4 = ignore the row compression, 8 = narrow x-slabs by the separate kernel, 16 = ignore the PML slab compression */
+ * 4 = ignore the row compression, 8 = narrow x-slabs by the separate kernel, 16 = ignore the PML slab compression,
+ * 32 = slab side stream at highest priority, 64 = one side stream for all slab launches, 128 = no fused H->E launches,
+ * bits 8-12 = rows per CTA of the slab launches (0 = ty) */
 int b200fdtd_set_tuning(b200fdtd_ctx* ctx, int kz, int ty, int variant);
 
 /* ---- excitation (openEMS Engine_Ext_Excitation::Apply2Voltages; AddLumpedPort's
@@ -156,6 +158,14 @@ int b200fdtd_update_only(b200fdtd_ctx* ctx, int which);
 /* how the volume is split: cells (incl. pad columns) swept by the plain launch, by the fused PML slab launches, and
  * by the separate PML pre/post kernel */
 int b200fdtd_plan_info(b200fdtd_ctx* ctx, int64_t* plain_cells, int64_t* fused_cells, int64_t* separate_cells);
+/* Fused H->E launches (graph runs on one slab): the H update of step n and the E update of step n+1 of the plain region
+ * are done in one sweep that writes a second copy of the fields (allocated by the library, 24 B/cell; the run falls
+ * back to the separate E and H launches if that allocation fails, if a PML box is not slab-shaped, or with
+ * variant bit 128).  Results are identical either way.  rows in {3,7,15} = rows per CTA, planes >= 1 = planes marched
+ * per CTA; 0 keeps the current value. */
+int b200fdtd_set_he_tuning(b200fdtd_ctx* ctx, int rows, int planes);
+/* *active = 1 if the chunk graph built by the last b200fdtd_run uses the fused H->E launches */
+int b200fdtd_he_info(b200fdtd_ctx* ctx, int* active);
 /* openEMS CalcFastEnergy: 0.5*eps0*sum(volt^2) + 0.5*mu0*sum(curr^2) over owned planes
  * (synchronises the stream) */
 int b200fdtd_energy(b200fdtd_ctx* ctx, double* energy);

@@ -161,3 +161,35 @@ def test_degenerate_inputs():
     G.set_excitation([], [], [], [0.0])
     G.set_mur([], [], [])
     G.set_pml([])
+
+
+@pytest.mark.parametrize("shape", [(37, 29, 23, 40), (261, 21, 14, 288), (130, 12, 9, 160)])
+@pytest.mark.parametrize("layout", ["slabs", "mur", "bare"])
+@pytest.mark.parametrize("interval,tile", [(2, (7, 32)), (3, (3, 2)), (4, (15, 5)), (7, (7, 1))])
+def test_fused_h_to_e_launches_bit_exact(shape, layout, interval, tile):
+    """graph chunks run H(n)+E(n+1) in one sweep over the plain region (update_he_kernel, second field copy): fields must
+    equal the oracle's separate passes bit for bit for even and odd numbers of fused launches per chunk, several
+    x-segments (nx > 124), PML slabs on every side (halo cells read from the slab launches' output), Mur and excitation
+    between the steps, and every tile shape"""
+    nx, ny, nz, px = shape
+    kw = dict(with_pml=layout == "slabs", fused_pml=layout == "slabs", with_mur=layout != "bare", with_exc=layout != "bare",
+              with_probes=True, with_nf2ff=False, interval=interval)
+    P = synth.make_problem(nx, ny, nz, px, seed=nx + interval, **kw)
+    R, G = _engines(P)
+    G.set_he_tuning(*tile)
+    n = 2 * interval + 1                   # two graph chunks and one eager step
+    R.run(n); G.run(n, use_graph=True)
+    assert G.he_active
+    _assert_fields_equal(R, G, f"{layout} interval {interval} tile {tile}")
+    G.set_tuning(variant=128)              # same again without the fused launches
+    R.run(2 * interval - 1); G.run(2 * interval - 1, use_graph=True)     # eager up to the chunk boundary, then one graph chunk
+    assert not G.he_active
+    _assert_fields_equal(R, G, "unfused chunk after fused chunks")
+
+
+def test_fused_h_to_e_with_row_compression():
+    P = synth.make_problem(37, 29, 23, 40, seed=9, fused_pml=True, compress=True, interval=4)
+    R, G = _engines(P)
+    R.run(13); G.run(13, use_graph=True)
+    assert G.he_active
+    _assert_fields_equal(R, G, "fused H->E with row compression")

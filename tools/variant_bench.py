@@ -23,6 +23,7 @@ ap.add_argument("--workload", default="patch100m")
 ap.add_argument("--cube-n", type=int, default=768)
 ap.add_argument("--out", default="variants.json")
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--he", default="0:0", help="fused H->E tiles rows:planes[,rows:planes...] (0 = keep)")
 args = ap.parse_args()
 
 if args.workload == "cube":
@@ -35,7 +36,9 @@ sim = Simulation(S, device=0, nf2ff_freqs=F.nf2ff_freqs, probe_freqs=S.probe_fre
 sim.prepare()
 E = sim.engine
 res = []
-for variant in [int(v) for v in args.variants.split(",")]:
+for he in args.he.split(","):
+  E.set_he_tuning(*[int(v) for v in he.split(":")])
+  for variant in [int(v) for v in args.variants.split(",")]:
     for ty in [int(v) for v in args.ty.split(",")]:
         for kz in [int(v) for v in args.kz.split(",")]:
             E.set_tuning(kz=kz, ty=ty, variant=variant)
@@ -51,7 +54,7 @@ for variant in [int(v) for v in args.variants.split(",")]:
                 torch.cuda.synchronize()
                 best = min(best, a.elapsed_time(b) / args.steps)
             ms = best
-            r = dict(variant=variant, ty=ty, kz=kz, ms_per_step=round(ms, 5), mcells=round(sim.cells / ms / 1e3, 1))
+            r = dict(he=he, fused=E.he_active, variant=variant, ty=ty, kz=kz, ms_per_step=round(ms, 5), mcells=round(sim.cells / ms / 1e3, 1))
             res.append(r)
             print(r, flush=True)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
