@@ -228,11 +228,14 @@ def run_b200(args):
     barrier()
     ms = ev0.elapsed_time(ev1)
     launches = eng_mod.launch_count() - l0
-    # ---- dominant kernel: the E/H volume update, timed alone on the same data, same stream ----
+    # ---- dominant kernel, timed alone on the same data, same stream ----
+    # single GPU: the fused H->E launch (H update of step n + E update of step n+1 of the plain region in one sweep,
+    # 120 B/cell algorithmic); z-slab ranks: the separate plain E and H launches (60 B/cell each)
     reps = 10
     kms = []
     plain_cells, fused_cells, sep_cells = E.plan_info()
-    for which in (2, 3):                       # plain launch only (the rows outside the fused PML slabs)
+    fused_he = world == 1 and E.he_active
+    for which in ((4,) if fused_he else (2, 3)):
         E.update_only(which, join=False)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
@@ -287,14 +290,21 @@ def run_b200(args):
             dist.destroy_process_group()
         return
     peak, peak_src = measured_peak()
-    k_ms = 0.5 * (kms[0] + kms[1])
-    achieved = BYTES_PER_CELL_PASS * plain_cells / (k_ms / 1e3) / 1e9
+    if fused_he:
+        k_ms, bytes_per_cell_launch = kms[0], BYTES_PER_CELL_STEP
+        kname = "update_he2_kernel<7> fused H->E launch over the plain region (one launch = both passes)"
+        kernel_ms = {"HE": round(kms[0], 4)}
+    else:
+        k_ms, bytes_per_cell_launch = 0.5 * (kms[0] + kms[1]), BYTES_PER_CELL_PASS
+        kname = "update_e_kernel<4,0,1>/update_h_kernel<4,0,1> plain launch (mean of both passes)"
+        kernel_ms = {"E": round(kms[0], 4), "H": round(kms[1], 4)}
+    achieved = bytes_per_cell_launch * plain_cells / (k_ms / 1e3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
             tj = json.load(open(tp))
-            per_cell = tj.get("dram_bytes_per_cell_pass")
+            per_cell = tj.get("dram_bytes_per_cell_fused_launch" if fused_he else "dram_bytes_per_cell_pass")
             traffic = None if per_cell is None else per_cell * plain_cells
         except Exception:
             traffic = None
@@ -311,10 +321,10 @@ def run_b200(args):
                    "operator_build_s": round(build_s, 2),
                    "row_compression": {("E" if w == 0 else "H"): {"row_slots_compressed": v[0], "row_slots_demoted": v[1], "x_vectors": v[2]}
                                        for w, v in sim.compression.items()}},
-        "roofline": {"bound": "hbm", "kernel": "update_e_kernel<4,false>/update_h_kernel<4,false> plain launch (mean of both passes)",
+        "roofline": {"bound": "hbm", "kernel": kname,
                      "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                     "traffic": traffic, "peak_source": peak_src, "kernel_ms": {"E": round(kms[0], 4), "H": round(kms[1], 4)},
-                     "bytes_per_cell_pass": BYTES_PER_CELL_PASS, "cells_per_launch": plain_cells,
+                     "traffic": traffic, "peak_source": peak_src, "kernel_ms": kernel_ms,
+                     "bytes_per_cell_launch": bytes_per_cell_launch, "cells_per_launch": plain_cells,
                      "fused_pml_cells": fused_cells, "separate_pml_cells": sep_cells,
                      "whole_step_frac": round(BYTES_PER_CELL_STEP * local_cells / (ms / K / 1e3) / 1e9 / peak, 4),
                      "frac_of_nominal_8TBs": round(achieved / 8000.0, 4)},

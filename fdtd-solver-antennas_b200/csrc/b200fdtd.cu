@@ -127,7 +127,8 @@ struct b200fdtd_ctx {
     double* d_partials = nullptr; int n_partials = 0; double* d_energy = nullptr;
     // graph
     cudaGraphExec_t graph = nullptr; int graph_steps = 0; int64_t graph_kernels = 0;
-    bool he_fused = false;                 // the captured chunk uses the fused H->E launches
+    bool he_fused = false;                 // the last b200fdtd_run used fused H->E launches
+    bool graph_fused = false;              // ... and so does the captured chunk
     // device copies of the slab / face tables
     PmlTable* d_pml = nullptr; FaceTable* d_faces = nullptr;
 };
@@ -856,7 +857,7 @@ __device__ __forceinline__ void row_coefs(const float4 m0, const float4 m1, cons
 }
 
 template <int TY>
-__global__ void __launch_bounds__(32 * (TY + 1), 16 / (TY + 1)) update_he2_kernel(const HeParams p)
+__global__ void __launch_bounds__(32 * (TY + 1)) __maxnreg__(TY == 5 ? 112 : (TY == 9 ? 96 : 128)) update_he2_kernel(const HeParams p)
 {
     __shared__ float4 xb[2][TY + 1][2][32];
     // row records of the H and E pass, staged one plane ahead by the warp that uses them (lanes 0-3, cp.async): the
@@ -917,9 +918,14 @@ __global__ void __launch_bounds__(32 * (TY + 1), 16 / (TY + 1)) update_he2_kerne
         if (lane < 4) cp_async16(&ms[(k + 1) & 1][r][lane], row_ok ? mrec + p.meta_step : reinterpret_cast<const char*>(p.meta_h), row_ok);
         cp_async_commit();
         if (in_grid) {
-            if (p.pf > 0 && k + p.pf < kend) {
-                prefetch_l2(pe + p.b_pfe[0]); prefetch_l2(pe + p.b_pfe[1]); prefetch_l2(pe + p.b_pfe[2]);
-                if (calc) { prefetch_l2(ph + p.b_pfh[0]); prefetch_l2(ph + p.b_pfh[1]); prefetch_l2(ph + p.b_pfh[2]); }
+            if (p.pf > 0 && k + 1 < kend) {
+                if (p.pf == 2) {
+                    prefetch_l1(pe + p.b_pfe[0]); prefetch_l1(pe + p.b_pfe[1]); prefetch_l1(pe + p.b_pfe[2]);
+                    if (calc) { prefetch_l1(ph + p.b_pfh[0]); prefetch_l1(ph + p.b_pfh[1]); prefetch_l1(ph + p.b_pfh[2]); }
+                } else {
+                    prefetch_l2(pe + p.b_pfe[0]); prefetch_l2(pe + p.b_pfe[1]); prefetch_l2(pe + p.b_pfe[2]);
+                    if (calc) { prefetch_l2(ph + p.b_pfh[0]); prefetch_l2(ph + p.b_pfh[1]); prefetch_l2(ph + p.b_pfh[2]); }
+                }
             }
             ex1 = ldb4(pe + p.b_sz); ey1 = ldb4(pe + p.b_sz_cs); ez1 = ldb4(pe + p.b_sz_2cs);
             if (has_jp) { ex_jp = ldb4(pe + p.b_row); ez_jp = ldb4(pe + p.b_row_2cs); }
@@ -1203,7 +1209,7 @@ static int launch_he(b200fdtd_ctx* c, cudaStream_t stream)
     if (grid.y > 65535 || grid.z > 65535) return fail("grid too large for the fused launch");
     p.b_sz = 4 * p.sz; p.b_cs = 4 * p.cs; p.b_2cs = 8 * p.cs; p.b_sz_cs = 4 * (p.sz + p.cs); p.b_sz_2cs = 4 * (p.sz + 2 * p.cs);
     p.b_row = 4LL * p.px; p.b_row_2cs = 4 * (p.px + 2 * p.cs);
-    for (int q = 0; q < 3; ++q) { p.b_pfe[q] = 4 * ((1 + p.pf) * p.sz + q * p.cs); p.b_pfh[q] = 4 * (p.pf * p.sz + q * p.cs); }
+    for (int q = 0; q < 3; ++q) { p.b_pfe[q] = 4 * (2 * p.sz + q * p.cs); p.b_pfh[q] = 4 * (p.sz + q * p.cs); }   // one plane ahead
     p.xv_pitch = 4u * (unsigned)p.px; p.meta_step = 32 * p.ny;
     const bool staged = (c->variant & 256) != 0;
     p.nv_e = c->cmp_nvec[0]; p.nv_h = c->cmp_nvec[1];
@@ -1222,7 +1228,9 @@ static int launch_he(b200fdtd_ctx* c, cudaStream_t stream)
         else update_he_kernel<TYV, false><<<grid, block, 0, stream>>>(p); } while (0)
     switch (ty) {
         case 3: LAUNCH_HE(3); break;
+        case 5: LAUNCH_HE(5); break;
         case 7: LAUNCH_HE(7); break;
+        case 9: LAUNCH_HE(9); break;
         case 15: LAUNCH_HE(15); break;
         default: return fail("unsupported fused-launch tile height %d", ty);
     }
@@ -2032,14 +2040,42 @@ static int he_step(b200fdtd_ctx* c, int off)
     return launch_mur(c, 2);
 }
 
+// n consecutive steps with no sampling point inside (device step counter untouched: launches use offsets 0..n-1).
+//   unfused: E(0) H(0) E(1) H(1) ...
+//   fused  : E(0) | H(0)+E(1) | ... | H(n-2)+E(n-1) | H(n-1): each fused launch flips both field copies; the two unfused
+//            half steps at the ends flip too when the number of fused launches is odd, so the span ends where it began
+static int run_span(b200fdtd_ctx* c, int n, bool fuse)
+{
+    int rc = 0;
+    if (!fuse || n < 2) {
+        for (int s = 0; s < n && !rc; ++s) {
+            rc = e_half(c, s);
+            if (!rc) rc = h_half(c);
+        }
+        return rc;
+    }
+    const bool odd = ((n - 1) & 1) != 0;
+    c->vcur = c->ccur = 0;
+    c->flip = odd; rc = e_half(c, 0); c->flip = false;
+    for (int s = 1; s < n && !rc; ++s) rc = he_step(c, s);
+    if (!rc) { c->flip = odd; rc = h_half(c); c->flip = false; }
+    if (!rc && (c->vcur || c->ccur)) rc = fail("fused span did not return to the bound field arrays");
+    c->vcur = c->ccur = 0; c->flip = false;
+    return rc;
+}
+
 static int run_eager(b200fdtd_ctx* c, int64_t n)
 {
     const int iv = sample_interval(c);
-    for (int64_t s = 0; s < n; ++s) {
-        if (e_half(c, 0)) return 1;
-        if (h_half(c)) return 1;
-        if (launch_ts_add(c, 1)) return 1;
-        c->ts += 1;
+    bool ghosts = false;
+    while (n > 0) {
+        int64_t span = n < 64 ? n : 64;
+        if (iv > 0) { const int64_t to_sample = iv - (c->ts % iv); if (span > to_sample) span = to_sample; }
+        const bool fuse = he_ready(c, (int)span);
+        if (fuse) { c->he_fused = true; if (!ghosts) { if (sync_alt_ghosts(c)) return 1; ghosts = true; } }
+        if (run_span(c, (int)span, fuse)) return 1;
+        if (launch_ts_add(c, (int)span)) return 1;
+        c->ts += span; n -= span;
         if (iv > 0 && (c->ts % iv) == 0) if (launch_sampling(c, 0)) return 1;
     }
     return 0;
@@ -2052,25 +2088,10 @@ static int build_graph(b200fdtd_ctx* c, int steps)
     cudaGraph_t g = nullptr;
     const int64_t before = g_launches.load();
     const bool fuse = he_ready(c, steps);           // allocates the second field copy: before the capture starts
-    c->he_fused = fuse;
+    if (fuse) c->he_fused = true;
+    c->graph_fused = fuse;
     CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-    int rc = 0;
-    if (!fuse) {
-        for (int s = 0; s < steps && !rc; ++s) {
-            rc = e_half(c, s);
-            if (!rc) rc = h_half(c);
-        }
-    } else {
-        // E(0) | H(0)+E(1) | ... | H(steps-2)+E(steps-1) | H(steps-1): each fused launch flips both copies; the two
-        // unfused half steps at the ends flip too when the number of fused launches is odd, so the chunk ends where it began
-        const bool odd = ((steps - 1) & 1) != 0;
-        c->vcur = c->ccur = 0;
-        c->flip = odd; rc = e_half(c, 0); c->flip = false;
-        for (int s = 1; s < steps && !rc; ++s) rc = he_step(c, s);
-        if (!rc) { c->flip = odd; rc = h_half(c); c->flip = false; }
-        if (!rc && (c->vcur || c->ccur)) rc = fail("fused chunk did not return to the bound field arrays");
-        c->vcur = c->ccur = 0;
-    }
+    int rc = run_span(c, steps, fuse);
     if (!rc && iv > 0) rc = launch_sampling(c, steps);      // graph starts at ts % iv == 0 and spans iv steps
     if (!rc) rc = launch_ts_add(c, steps);
     cudaError_t e = cudaStreamEndCapture(c->stream, &g);
@@ -2092,6 +2113,7 @@ extern "C" int b200fdtd_run(b200fdtd_ctx* c, int64_t nsteps, int use_graph)
     if (!c->volt || !c->vv) return fail("fields/coefficients not bound");
     CK(cudaSetDevice(c->device));
     if (!c->plan.valid) if (build_plan(c)) return 1;        // never inside a stream capture
+    c->he_fused = false;
     if (!use_graph || c->stream == nullptr) return run_eager(c, nsteps);   // the NULL stream cannot be captured
     const int iv = sample_interval(c);
     const int chunk = iv > 0 ? iv : 16;
@@ -2105,7 +2127,7 @@ extern "C" int b200fdtd_run(b200fdtd_ctx* c, int64_t nsteps, int use_graph)
     }
     if (left >= chunk) {
         if (!c->graph || c->graph_steps != chunk) if (build_graph(c, chunk)) return 1;
-        if (c->he_fused) if (sync_alt_ghosts(c)) return 1;
+        if (c->graph_fused) { c->he_fused = true; if (sync_alt_ghosts(c)) return 1; }
         while (left >= chunk) {
             CK(cudaGraphLaunch(c->graph, c->stream));
             g_launches.fetch_add(c->graph_kernels, std::memory_order_relaxed);
@@ -2173,8 +2195,16 @@ extern "C" int b200fdtd_half_step_part(b200fdtd_ctx* c, int phase, int part)
 extern "C" int b200fdtd_update_only(b200fdtd_ctx* c, int which)
 {
     if (!c) return fail("NULL ctx");
-    if (which < 0 || which > 3) return fail("which must be 0..3");
+    if (which < 0 || which > 4) return fail("which must be 0..4");
     CK(cudaSetDevice(c->device));
+    if (which == 4) {
+        // only the fused H->E launch over the plain region, for timing: it reads the bound arrays and writes the second
+        // copy, so the state of the run is untouched
+        if (!c->volt || !c->vv) return fail("fields/coefficients not bound");
+        if (!c->plan.valid) if (build_plan(c)) return 1;
+        if (!he_ready(c, 2)) return fail("fused H->E launch not available for this set-up");
+        return launch_he(c, c->stream);
+    }
     if (which < 2) return launch_volume(c, which, 0, c->nz);
     // 2/3: only the plain (non-PML) launch of the E/H update — the kernel the roofline is quoted on
     if (!c->volt || !c->vv) return fail("fields/coefficients not bound");
@@ -2202,7 +2232,7 @@ extern "C" int b200fdtd_plan_info(b200fdtd_ctx* c, int64_t* plain_cells, int64_t
 extern "C" int b200fdtd_set_he_tuning(b200fdtd_ctx* c, int rows, int planes)
 {
     if (!c) return fail("NULL ctx");
-    if (!(rows == 0 || rows == 3 || rows == 7 || rows == 15)) return fail("rows must be 0, 3, 7 or 15");
+    if (!(rows == 0 || rows == 3 || rows == 5 || rows == 7 || rows == 9 || rows == 15)) return fail("rows must be 0, 3, 5, 7, 9 or 15");
     if (planes < 0) return fail("planes must be >= 0");
     if (rows) c->he_ty = rows;
     if (planes) c->he_kz = planes;
@@ -2213,7 +2243,7 @@ extern "C" int b200fdtd_set_he_tuning(b200fdtd_ctx* c, int rows, int planes)
 extern "C" int b200fdtd_he_info(b200fdtd_ctx* c, int* active)
 {
     if (!c || !active) return fail("NULL argument");
-    *active = (c->graph && c->he_fused) ? 1 : 0;
+    *active = c->he_fused ? 1 : 0;
     return 0;
 }
 

@@ -153,18 +153,19 @@ int b200fdtd_half_step(b200fdtd_ctx* ctx, int phase);
  *   phase 1: part 0 = pre passes + planes [0,nz-1), part 1 = plane nz-1 (reads the upper ghost E) + post, ++ts */
 int b200fdtd_half_step_part(b200fdtd_ctx* ctx, int phase, int part);
 /* only the volume kernels (bench / roofline): which = 0 E update, 1 H update (plain + fused PML slab launches);
- * 2 / 3 = only the plain launch of the E / H update (rows outside the fused PML slabs) */
+ * 2 / 3 = only the plain launch of the E / H update (rows outside the fused PML slabs);
+ * 4 = only the fused H->E launch over the plain region (writes the second field copy: the state is untouched) */
 int b200fdtd_update_only(b200fdtd_ctx* ctx, int which);
 /* how the volume is split: cells (incl. pad columns) swept by the plain launch, by the fused PML slab launches, and
  * by the separate PML pre/post kernel */
 int b200fdtd_plan_info(b200fdtd_ctx* ctx, int64_t* plain_cells, int64_t* fused_cells, int64_t* separate_cells);
-/* Fused H->E launches (graph runs on one slab): the H update of step n and the E update of step n+1 of the plain region
+/* Fused H->E launches (b200fdtd_run on one slab, graph or eager): the H update of step n and the E update of step n+1 of the plain region
  * are done in one sweep that writes a second copy of the fields (allocated by the library, 24 B/cell; the run falls
  * back to the separate E and H launches if that allocation fails, if a PML box is not slab-shaped, or with
  * variant bit 128).  Results are identical either way.  rows in {3,7,15} = rows per CTA, planes >= 1 = planes marched
  * per CTA; 0 keeps the current value. */
 int b200fdtd_set_he_tuning(b200fdtd_ctx* ctx, int rows, int planes);
-/* *active = 1 if the chunk graph built by the last b200fdtd_run uses the fused H->E launches */
+/* *active = 1 if the last b200fdtd_run used fused H->E launches */
 int b200fdtd_he_info(b200fdtd_ctx* ctx, int* active);
 /* openEMS CalcFastEnergy: 0.5*eps0*sum(volt^2) + 0.5*mu0*sum(curr^2) over owned planes
  * (synchronises the stream) */
