@@ -382,6 +382,12 @@ __global__ void __launch_bounds__(32 * TY, MODE ? (16 / TY > 0 ? 16 / TY : 1) : 
         float4 fl0 = zero4(), fl1 = zero4(), fl2 = zero4();
         if (MODE == 1 && act) { fl0 = ld4_stream(r.flux + lb); fl1 = ld4_stream(r.flux + lcs + lb); fl2 = ld4_stream(r.flux + 2 * lcs + lb); }
         if (MODE == 2) { fl0 = ld4_stream(xflux + lb); fl1 = ld4_stream(xflux + lcs + lb); fl2 = ld4_stream(xflux + 2 * lcs + lb); }
+        if (MODE != 0 && act && k + 1 < kend) {             // slab launches are latency-bound: pull the next plane into L2
+            prefetch_l2(g + base + sz); prefetch_l2(g + cs + base + sz); prefetch_l2(g + 2 * cs + base + sz);
+            prefetch_l2(fin + base + sz); prefetch_l2(fin + cs + base + sz); prefetch_l2(fin + 2 * cs + base + sz);
+            const float* fx = MODE == 1 ? r.flux : xflux;
+            prefetch_l2(fx + lb + lsz); prefetch_l2(fx + lcs + lb + lsz); prefetch_l2(fx + 2 * lcs + lb + lsz);
+        }
         if (act) {
             hx = ld4(g + base); hy = ld4(g + cs + base); hz = ld4(g + 2 * cs + base);
             if (has_jm) { hz_jm = ld4(g + 2 * cs + base - p.px); hx_jm = ld4(g + base - p.px); }
@@ -496,6 +502,12 @@ __global__ void __launch_bounds__(32 * TY, MODE ? (16 / TY > 0 ? 16 / TY : 1) : 
         float4 fl0 = zero4(), fl1 = zero4(), fl2 = zero4();
         if (MODE == 1 && act) { fl0 = ld4_stream(r.flux + lb); fl1 = ld4_stream(r.flux + lcs + lb); fl2 = ld4_stream(r.flux + 2 * lcs + lb); }
         if (MODE == 2) { fl0 = ld4_stream(xflux + lb); fl1 = ld4_stream(xflux + lcs + lb); fl2 = ld4_stream(xflux + 2 * lcs + lb); }
+        if (MODE != 0 && act && k - 1 >= kbeg) {
+            prefetch_l2(g + base - sz); prefetch_l2(g + cs + base - sz); prefetch_l2(g + 2 * cs + base - sz);
+            prefetch_l2(fin + base - sz); prefetch_l2(fin + cs + base - sz); prefetch_l2(fin + 2 * cs + base - sz);
+            const float* fx = MODE == 1 ? r.flux : xflux;
+            prefetch_l2(fx + lb - lsz); prefetch_l2(fx + lcs + lb - lsz); prefetch_l2(fx + 2 * lcs + lb - lsz);
+        }
         if (act) {
             ex = ld4(g + base); ey = ld4(g + cs + base); ez = ld4(g + 2 * cs + base);
             if (has_jp) { ez_jp = ld4(g + 2 * cs + base + p.px); ex_jp = ld4(g + base + p.px); }
@@ -1114,7 +1126,8 @@ static int slots_for(int w) { int s = 1; while (s * 4 < w) s *= 2; return s; }
 static int slab_kz(int kz, int planes, long long ctas_per_chunk)
 {
     auto chunks = [&](int q) { return (planes + q - 1) / q; };
-    while (kz > 2 && ctas_per_chunk * chunks(kz) < 148LL * 16) kz = (kz + 1) / 2;
+    static const long long target = [] { const char* e = getenv("B200FDTD_SLAB_CTAS"); return e ? atoll(e) : 148LL * 4; }();
+    while (kz > 2 && ctas_per_chunk * chunks(kz) < target) kz = (kz + 1) / 2;
     if (kz > planes) kz = planes;
     const int n = chunks(kz);
     return (planes + n - 1) / n;

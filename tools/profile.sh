@@ -1,13 +1,17 @@
 #!/bin/bash
 # ncu recipe of /opt/skills/guides/B200_PROFILING.md: plain run first, then the launch list, then full captures.
+#   tools/profile.sh [tag]     (outputs under gpurun_out/, copy the summaries you want judged into profiles/)
 set -u
-CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
-FILT='regex:update_|pml_|mur_|excite|probe|nf2ff|ts_add|energy'
+TAG=${1:-r01b}
+CMD="python bench.py --steps 4 --warmup 3 --no-cpu-baseline"
+FILT='regex:update_|pml_k|mur_|excite|probe|nf2ff|ts_add|energy'
 mkdir -p gpurun_out
-$CMD > gpurun_out/plain.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/plain.log; exit 1; }
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k "$FILT" -c 300 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
-python tools/summarize_launches.py gpurun_out/launches.csv
-# plain E/H launches are the ones with the big grid: skip the warm-up step launches, take 2
-ncu --set full --clock-control none --import-source on -k regex:"update_e_kernel.*false, true|update_e_kernel<4, 0, 1>" -s 4 -c 2 -f -o gpurun_out/prof_update_e $CMD > gpurun_out/ncu_e.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"update_h_kernel<4, 0, 1>" -s 4 -c 2 -f -o gpurun_out/prof_update_h $CMD > gpurun_out/ncu_h.log 2>&1
+timeout 600 $CMD > gpurun_out/plain_$TAG.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/plain_$TAG.log; exit 1; }
+timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k "$FILT" -c 400 --csv \
+    --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_launches_$TAG.log 2>&1
+python tools/summarize_launches.py gpurun_out/launches_$TAG.csv
+# the dominant kernel (fused H->E launch over the plain region) and one launch of each slab kind
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:update_he2_kernel -s 2 -c 1 -f -o gpurun_out/prof_he2_$TAG $CMD > gpurun_out/ncu_he2_$TAG.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"update_[eh]_kernel<\(int\)4, \(int\)[12]" -s 10 -c 5 -f \
+    -o gpurun_out/prof_slabs_$TAG $CMD > gpurun_out/ncu_slabs_$TAG.log 2>&1
 ls -la gpurun_out | grep -E "ncu-rep|csv"
