@@ -45,6 +45,7 @@ SYMBOLS = {
     "b200fdtd_bind_coeffs": (C.c_int, [vp, vp, vp, vp, vp]),
     "b200fdtd_set_tuning": (C.c_int, [vp, C.c_int, C.c_int, C.c_int]),
     "b200fdtd_set_row_compression": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, c_i64, c_i64]),
+    "b200fdtd_expand_rows": (C.c_int, [vp, C.c_int, C.c_int, vp, vp]),
     "b200fdtd_set_excitation": (C.c_int, [vp, C.c_int64, c_i64, c_f, c_i32, c_f, C.c_int32]),
     "b200fdtd_set_mur": (C.c_int, [vp, C.c_int64, c_i64, c_i64, c_f]),
     "b200fdtd_set_pml": (C.c_int, [vp, C.c_int, C.POINTER(PmlBox)]),

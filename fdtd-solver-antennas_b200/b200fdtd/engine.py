@@ -102,6 +102,12 @@ class Engine:
                                                   C.byref(nc), C.byref(nd)))
         return nc.value, nd.value
 
+    def expand_rows(self, which, xvecs, meta):
+        """fill the bound full arrays of one pass from compression tables on the device (rows streamed in full become 0)"""
+        self._pre()
+        check(self.L.b200fdtd_expand_rows(self.h, int(which), int(xvecs.shape[0]), xvecs.data_ptr(), meta.data_ptr()))
+        self._post()
+
     def set_tuning(self, kz=16, ty=4, variant=0):
         check(self.L.b200fdtd_set_tuning(self.h, int(kz), int(ty), int(variant)))
 

@@ -242,15 +242,10 @@ class Simulation:
             H = op[which]
             xv = H["xvecs"].to(dev, non_blocking=True)
             meta = H["meta"].to(dev, non_blocking=True)
-            m = meta.view(self.nz + 2, self.ny, 32)
-            scales = m[..., :24].contiguous().view(torch.float32)       # [nzp, ny, 6]
-            ids = m[..., 24:30]
+            xv = xv.contiguous(); meta = meta.contiguous()
+            E.expand_rows(which, xv, meta)                     # C-ABI b200fdtd_expand_rows: one kernel, HBM write speed
             for slot in range(6):
                 arr = (ca, cb)[slot // 3][slot % 3]
-                idl = ids[..., slot].long()
-                comp = idl != 255
-                arr.copy_(torch.where(comp.unsqueeze(-1), scales[..., slot].unsqueeze(-1) * xv[idl.clamp(max=xv.shape[0] - 1)],
-                                      torch.zeros((), dtype=torch.float32, device=dev)))
                 idx = H["full_idx"][slot].to(dev, non_blocking=True)
                 if idx.numel():
                     arr[idx[:, 0], idx[:, 1]] = H["full_rows"][slot].to(dev, non_blocking=True)

@@ -1157,7 +1157,8 @@ static int launch_volume_xslabs(b200fdtd_ctx* c, int which, int k0, int k1, cuda
     g.j1 = e.j1;                                             // kernel bounds rows by j1; grid.y from the widest slab
     const int rows_per_cta = slab_ty(c) * (32 / xs);
     const int gy = (any.by + rows_per_cta - 1) / rows_per_cta;
-    const int kz = slab_kz(c->kz, b - a, (long long)gy * (P.has_lo + P.has_hi));
+    // the narrow-slab launch is latency-bound (one row per lane): it wants four times the CTAs of the whole-row slabs
+    const int kz = slab_kz(c->kz, b - a, ((long long)gy * (P.has_lo + P.has_hi) + 3) / 4);
     // launch_volume_one derives grid.y from (j1-j0)/ty: pass an equivalent row count
     g.j0 = e.j0; 
     return launch_volume_one<2>(c, which, a, b, g, stream, kz, P.has_lo + P.has_hi, gy);
@@ -1682,6 +1683,46 @@ __global__ void __launch_bounds__(256) verify_rows_kernel(unsigned char* __restr
         if (!ok) { M->id[slot] = (unsigned char)ROW_FULL; atomicAdd(&counts[0], 1ULL); }
         else atomicAdd(&counts[1], 1ULL);
     }
+}
+
+// expansion of a compressed operator into the bound full arrays: one warp per (row, slot), full[i] = fl32(scale*xvec[i])
+// for a compressed slot, 0 for a slot that is streamed in full (the caller patches those rows afterwards)
+__global__ void __launch_bounds__(256) expand_rows_kernel(const unsigned char* __restrict__ meta, const float* __restrict__ xv, int nvec,
+        float* __restrict__ ca, float* __restrict__ cb, long long nrows, int px, long long cs)
+{
+    const long long w = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= nrows * 6) return;
+    const int slot = (int)(w % 6);
+    const long long row = w / 6;
+    const RowMeta* M = reinterpret_cast<const RowMeta*>(meta + row * 32);
+    const unsigned id = M->id[slot];
+    const float sc = M->sc[slot];
+    float4* dst = reinterpret_cast<float4*>((slot < 3 ? ca : cb) + (long long)(slot % 3) * cs + row * px);
+    const float4* v = reinterpret_cast<const float4*>(xv + (size_t)(id < (unsigned)nvec ? id : 0) * px);
+    const bool cmp = id < (unsigned)nvec;
+    for (int i = lane; i < px / 4; i += 32) {
+        float4 o = zero4();
+        if (cmp) { const float4 x = __ldg(v + i); o = make_float4(__fmul_rn(sc, x.x), __fmul_rn(sc, x.y), __fmul_rn(sc, x.z), __fmul_rn(sc, x.w)); }
+        __stcs(dst + i, o);
+    }
+}
+
+extern "C" int b200fdtd_expand_rows(b200fdtd_ctx* c, int which, int nvec, const float* xvecs, const void* meta)
+{
+    if (!c) return fail("NULL ctx");
+    if (which != 0 && which != 1) return fail("which must be 0 (E pass) or 1 (H pass)");
+    if (!c->vv) return fail("bind the coefficient arrays before expanding into them");
+    if (nvec < 1 || nvec > 255 || !xvecs || !meta) return fail("bad compression tables");
+    if (((uintptr_t)xvecs | (uintptr_t)meta) & 15) return fail("compression tables must be 16-byte aligned");
+    CK(cudaSetDevice(c->device));
+    drop_graph(c);
+    const long long nrows = (long long)(c->nz + 2) * c->ny;
+    const long long blocks = (nrows * 6 * 32 + 255) / 256;
+    expand_rows_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>((const unsigned char*)meta, xvecs, nvec,
+        const_cast<float*>(which == 0 ? c->vv : c->ii), const_cast<float*>(which == 0 ? c->vi : c->iv), nrows, c->px, c->cs);
+    CKL();
+    return 0;
 }
 
 // pad[0] of a row record = 1 if any of its six slots is streamed in full (the volume kernels branch on it once per row)

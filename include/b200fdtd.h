@@ -62,6 +62,11 @@ int b200fdtd_bind_coeffs(b200fdtd_ctx* ctx, const float* vv, const float* vi,
  * depend on the compression.  The full arrays must stay bound.  nvec = 0 switches compression off. */
 int b200fdtd_set_row_compression(b200fdtd_ctx* ctx, int which, int nvec, const float* xvecs, void* meta,
                                  int64_t* n_compressed /*host out, may be NULL*/, int64_t* n_demoted /*host out, may be NULL*/);
+/* Expansion of a compressed operator into the bound (writable) full arrays of one pass: full[i] = fl32(scale*xvec[i]) for
+ * every compressed row slot, 0 for slots with vec_id 255 (the caller writes those rows itself afterwards, then calls
+ * b200fdtd_set_row_compression, which verifies the result).  Lets a host ship the operator in its compressed form
+ * (~0.1 % of the bytes) and build the full arrays at HBM speed. */
+int b200fdtd_expand_rows(b200fdtd_ctx* ctx, int which, int nvec, const float* xvecs /*dev*/, const void* meta /*dev*/);
 /* tuning knobs of the volume kernels: planes marched per CTA (kz), rows per CTA (ty in {2,4,8}),
  * variant bits: 1 = PML slabs by the separate pre/post kernel instead of fused rows, 2 = no side stream,
  * 4 = ignore the row compression, 8 = narrow x-slabs by the separate kernel, 16 = ignore the PML slab compression,
