@@ -179,18 +179,33 @@ __device__ __forceinline__ float4 coef4(unsigned id, float sc, const float* full
     return __ldcs(reinterpret_cast<const float4*>(full));
 }
 
+// xv_lane_ = this lane's column of the x-vector table (hoisted out of the march), xv_pitch_ = bytes per x-vector
+__device__ __forceinline__ float4 xvg4(const char* xv_lane, unsigned id, unsigned pitch, float sc)
+{
+    const float4 v = __ldg(reinterpret_cast<const float4*>(xv_lane + (unsigned long long)id * pitch));
+    return make_float4(__fmul_rn(sc, v.x), __fmul_rn(sc, v.y), __fmul_rn(sc, v.z), __fmul_rn(sc, v.w));
+}
 #define LOAD_COEFFS_CMP()                                                                                   \
     do {                                                                                                    \
         const float4* m_ = reinterpret_cast<const float4*>(p.meta + ((long long)(k + 1) * p.ny + j) * 32);  \
         prefetch_l1(p.meta + ((long long)(k + 1 + KSTEP) * p.ny + j) * 32);   /* next plane's record: ghost planes exist */ \
         const float4 m0_ = __ldg(m_), m1_ = __ldg(m_ + 1);                                                  \
         const unsigned w0_ = __float_as_uint(m1_.z), w1_ = __float_as_uint(m1_.w);                          \
-        ax = coef4(w0_ & 255u, m0_.x, p.ca + base, p.xv, i0, p.px);                                         \
-        ay = coef4((w0_ >> 8) & 255u, m0_.y, p.ca + cs + base, p.xv, i0, p.px);                             \
-        az = coef4((w0_ >> 16) & 255u, m0_.z, p.ca + 2 * cs + base, p.xv, i0, p.px);                        \
-        bx = coef4(w0_ >> 24, m0_.w, p.cb + base, p.xv, i0, p.px);                                          \
-        by = coef4(w1_ & 255u, m1_.x, p.cb + cs + base, p.xv, i0, p.px);                                    \
-        bz = coef4((w1_ >> 8) & 255u, m1_.y, p.cb + 2 * cs + base, p.xv, i0, p.px);                         \
+        if (((w1_ >> 16) & 255u) == 0) {          /* pad[0]: no slot of this row is streamed in full (row-uniform) */ \
+            ax = xvg4(xv_lane_, w0_ & 255u, xv_pitch_, m0_.x);                                              \
+            ay = xvg4(xv_lane_, (w0_ >> 8) & 255u, xv_pitch_, m0_.y);                                       \
+            az = xvg4(xv_lane_, (w0_ >> 16) & 255u, xv_pitch_, m0_.z);                                      \
+            bx = xvg4(xv_lane_, w0_ >> 24, xv_pitch_, m0_.w);                                               \
+            by = xvg4(xv_lane_, w1_ & 255u, xv_pitch_, m1_.x);                                              \
+            bz = xvg4(xv_lane_, (w1_ >> 8) & 255u, xv_pitch_, m1_.y);                                       \
+        } else {                                                                                            \
+            ax = coef4(w0_ & 255u, m0_.x, p.ca + base, p.xv, i0, p.px);                                     \
+            ay = coef4((w0_ >> 8) & 255u, m0_.y, p.ca + cs + base, p.xv, i0, p.px);                         \
+            az = coef4((w0_ >> 16) & 255u, m0_.z, p.ca + 2 * cs + base, p.xv, i0, p.px);                    \
+            bx = coef4(w0_ >> 24, m0_.w, p.cb + base, p.xv, i0, p.px);                                      \
+            by = coef4(w1_ & 255u, m1_.x, p.cb + cs + base, p.xv, i0, p.px);                                \
+            bz = coef4((w1_ >> 8) & 255u, m1_.y, p.cb + 2 * cs + base, p.xv, i0, p.px);                     \
+        }                                                                                                   \
     } while (0)
 
 
@@ -267,7 +282,12 @@ __device__ __forceinline__ float4 pcoef4(unsigned id, float sc, const float* ful
 // the three PML coefficients of component c4 (0..2) of the current slab row; PM_ = row record or NULL
 #define PML_COEFFS(c4, PA, PFO, PFN, PXV, COL, W, lofs)                                                         \
     float4 a_, fo_, fn_;                                                                                        \
-    if (pm_ != nullptr) {                                                                                       \
+    if (pm_ != nullptr && pfull_ == 0) {          /* every slot of the slab row is compressed */                 \
+        const char* pl_ = reinterpret_cast<const char*>((PXV) + (COL)); const unsigned pp_ = 4u * (unsigned)(W); \
+        a_ = xvg4(pl_, pid_[c4], pp_, psc_[c4]);                                                                \
+        fo_ = xvg4(pl_, pid_[3 + c4], pp_, psc_[3 + c4]);                                                       \
+        fn_ = xvg4(pl_, pid_[6 + c4], pp_, psc_[6 + c4]);                                                       \
+    } else if (pm_ != nullptr) {                                                                                \
         a_ = pcoef4(pid_[c4], psc_[c4], (PA) + (lofs), PXV, COL, W);                                            \
         fo_ = pcoef4(pid_[3 + c4], psc_[3 + c4], (PFO) + (lofs), PXV, COL, W);                                  \
         fn_ = pcoef4(pid_[6 + c4], psc_[6 + c4], (PFN) + (lofs), PXV, COL, W);                                  \
@@ -276,7 +296,7 @@ __device__ __forceinline__ float4 pcoef4(unsigned id, float sc, const float* ful
 // load the row record into registers (row-uniform in MODE 1, per lane in MODE 2)
 #define PML_ROW_META(PMETA, ROW)                                                                                \
     const unsigned char* pm_ = (PMETA) ? (PMETA) + (long long)(ROW) * 48 : nullptr;                             \
-    float psc_[9]; unsigned pid_[9];                                                                            \
+    float psc_[9]; unsigned pid_[9]; unsigned pfull_ = 1;                                                       \
     if (pm_ != nullptr) {                                                                                       \
         if (k + KSTEP >= kbeg && k + KSTEP < kend) prefetch_l1(pm_ + (long long)KSTEP * r.by * 48);             \
         const float4 q0_ = __ldg(reinterpret_cast<const float4*>(pm_)), q1_ = __ldg(reinterpret_cast<const float4*>(pm_) + 1), \
@@ -286,7 +306,7 @@ __device__ __forceinline__ float4 pcoef4(unsigned id, float sc, const float* ful
         const unsigned w0_ = __float_as_uint(q2_.y), w1_ = __float_as_uint(q2_.z), w2_ = __float_as_uint(q2_.w); \
         pid_[0] = w0_ & 255u; pid_[1] = (w0_ >> 8) & 255u; pid_[2] = (w0_ >> 16) & 255u; pid_[3] = w0_ >> 24;   \
         pid_[4] = w1_ & 255u; pid_[5] = (w1_ >> 8) & 255u; pid_[6] = (w1_ >> 16) & 255u; pid_[7] = w1_ >> 24;   \
-        pid_[8] = w2_ & 255u;                                                                                   \
+        pid_[8] = w2_ & 255u; pfull_ = (w2_ >> 8) & 255u;      /* pad[0]: a slot of this slab row is streamed in full */ \
     }
 
 // one component of a fused PML row: pre, update, post.  f4 holds the field on entry and the new field on exit; fl4 holds
@@ -351,6 +371,8 @@ __global__ void __launch_bounds__(32 * TY, MODE ? (16 / TY > 0 ? 16 / TY : 1) : 
     const float* __restrict__ g = p.g;
     float* __restrict__ f = p.f;
     const float* fin = p.fin;
+    const char* xv_lane_ = reinterpret_cast<const char*>(p.xv + i0); const unsigned xv_pitch_ = 4u * (unsigned)p.px;
+    (void)xv_lane_; (void)xv_pitch_;
 
     long long base = (long long)kbeg * sz + (long long)j * p.px + i0;   // plane kbeg-1 (ghost offset +1 applied below)
     float4 hx_km = zero4(), hy_km = zero4();
@@ -471,6 +493,8 @@ __global__ void __launch_bounds__(32 * TY, MODE ? (16 / TY > 0 ? 16 / TY : 1) : 
     const float* __restrict__ g = p.g;
     float* __restrict__ f = p.f;
     const float* fin = p.fin;
+    const char* xv_lane_ = reinterpret_cast<const char*>(p.xv + i0); const unsigned xv_pitch_ = 4u * (unsigned)p.px;
+    (void)xv_lane_; (void)xv_pitch_;
 
     long long base = (long long)(kend + 1) * sz + (long long)j * p.px + i0;   // plane kend (k+1 of the first plane)
     float4 ex_kp = zero4(), ey_kp = zero4();
@@ -1834,6 +1858,17 @@ __global__ void __launch_bounds__(256) verify_pml_rows_kernel(unsigned char* __r
     }
 }
 
+// pad[0] of a slab row record = 1 if any of its nine slots is streamed in full
+__global__ void __launch_bounds__(256) flag_pml_rows_kernel(unsigned char* __restrict__ meta, long long nrows)
+{
+    const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (q >= nrows) return;
+    PmlRowMeta* M = reinterpret_cast<PmlRowMeta*>(meta + q * 48);
+    bool any = false;
+    for (int sl = 0; sl < 9; ++sl) any |= M->id[sl] == ROW_FULL;
+    M->pad[0] = any ? 1 : 0;
+}
+
 static int verify_pml_rows(b200fdtd_ctx* c, const b200fdtd_pml_box& B, int which)
 {
     unsigned long long* d_counts = nullptr;
@@ -1845,6 +1880,9 @@ static int verify_pml_rows(b200fdtd_ctx* c, const b200fdtd_pml_box& B, int which
         which == 0 ? B.xvecs_v : B.xvecs_i, which == 0 ? B.nvec_v : B.nvec_i,
         which == 0 ? B.vv : B.ii, which == 0 ? B.vvfo : B.iifo, which == 0 ? B.vvfn : B.iifn, B.bx, B.by, B.bz, d_counts);
     g_launches.fetch_add(1);
+    { const long long nrows = (long long)B.bz * B.by;
+      flag_pml_rows_kernel<<<(unsigned)((nrows + 255) / 256), 256, 0, c->stream>>>((unsigned char*)(which == 0 ? B.meta_v : B.meta_i), nrows);
+      g_launches.fetch_add(1); }
     cudaError_t e = cudaGetLastError();
     unsigned long long h[2] = {0, 0};
     if (e == cudaSuccess) e = cudaMemcpyAsync(h, d_counts, sizeof(h), cudaMemcpyDeviceToHost, c->stream);
