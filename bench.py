@@ -260,7 +260,11 @@ def run_b200(args):
     # few non-separable rows, pinned); the timed region uploads it, expands it into the bound arrays on the device,
     # re-verifies the compression (C-ABI b200fdtd_set_row_compression), steps K times and reads every result back.
     host_op = sim.export_operator(pin=True)
-    before = [t.clone() for t in (E.vv, E.vi, E.ii, E.iv)]
+    big = local_cells > 300e6              # no room for a second copy of the operator: compare fp64 checksums + sample planes
+    if big:
+        before = [(float(torch.sum(t, dtype=torch.float64)), t[:, 1::max(1, sim.nz // 7)].clone()) for t in (E.vv, E.vi, E.ii, E.iv)]
+    else:
+        before = [t.clone() for t in (E.vv, E.vi, E.ii, E.iv)]
     for t in (E.vv, E.vi, E.ii, E.iv):
         t.zero_()
     torch.cuda.synchronize()
@@ -275,7 +279,11 @@ def run_b200(args):
             res_host.append(o.to("cpu", non_blocking=False))
     barrier()
     e2e_s = time.perf_counter() - t_e0
-    e2e_ok = [int((a != b).sum()) for a, b in zip(before, (E.vv, E.vi, E.ii, E.iv))]
+    if big:
+        e2e_ok = [int(float(torch.sum(t, dtype=torch.float64)) != cs) + int((t[:, 1::max(1, sim.nz // 7)] != smp).count_nonzero())
+                  for (cs, smp), t in zip(before, (E.vv, E.vi, E.ii, E.iv))]
+    else:
+        e2e_ok = [sum(int((a[c] != b[c]).count_nonzero()) for c in range(3)) for a, b in zip(before, (E.vv, E.vi, E.ii, E.iv))]
     del before
     if world > 1:
         t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
