@@ -1154,6 +1154,181 @@ __global__ void __launch_bounds__(32 * (TY + 1), 16 / (TY + 1)) update_he3_kerne
     }
 }
 
+
+// ---- update_he3_kernel without the CTA barrier ----
+// ncu on update_he3_kernel: 30 % of the stall samples sit on the per-plane __syncthreads (8 warps in lock step, the
+// slowest warp's memory latency is everybody's).  A warp only needs its two neighbours: the H_new row of the warp below,
+// the staged +1 row of the warp above.  Three monotonic per-warp counters in shared memory replace the barrier:
+//   prod[w] = planes whose H_new row warp w has published (xb is 2 deep: w waits for rd[w+1] >= t-1 before reuse)
+//   stg[w]  = planes whose staged copies of warp w have landed (+1: plane t+1 is in place when stg[w] >= t+2)
+//   rd[w]   = planes for which warp w is done reading other warps' data (w+1 may then reuse the E ring slot)
+// Every wait is for a warp at an earlier or equal plane, so the slowest warp can always proceed (no cycle).
+__device__ __forceinline__ void spin_ge(const volatile int* f, int v)
+{
+    while (*f < v) { }
+    __threadfence_block();
+}
+__device__ __forceinline__ void publish1(volatile int* f, int v)
+{
+    __syncwarp();
+    __threadfence_block();
+    if (threadIdx.x == 0) *f = v;
+}
+__device__ __forceinline__ void publish2(volatile int* f, int v, volatile int* g, int w)
+{
+    __syncwarp();
+    __threadfence_block();
+    if (threadIdx.x == 0) { *f = v; *g = w; }
+}
+template <int TY>
+struct He4Smem {
+    float4 es[3][3][TY + 2][33];
+    float4 hs[2][3][TY + 1][32];
+    float4 xb[2][TY + 1][2][32];
+    float4 ms[2][TY + 1][4];
+    int prod[TY + 2], rd[TY + 2], stg[TY + 2];               // per-warp progress counters (see update_he4_kernel)
+    int pad_[(4 - (3 * (TY + 2)) % 4) % 4];
+    float4 xs[1];                                            // [nv_h + nv_e][32], sized at launch
+};
+
+template <int TY>
+__global__ void __launch_bounds__(32 * (TY + 1), 16 / (TY + 1)) update_he4_kernel(const HeParams p)
+{
+    extern __shared__ __align__(16) unsigned char he4_raw[];
+    He4Smem<TY>& S = *reinterpret_cast<He4Smem<TY>*>(he4_raw);
+    const int lane = threadIdx.x, r = threadIdx.y;
+    const int i0 = p.X0 - 4 + HE_SEG * (int)blockIdx.x + 4 * lane;
+    const int j = p.Y0 - 1 + TY * (int)blockIdx.y + r;
+    const int kbeg = p.Z0 + (int)blockIdx.z * p.kz;
+    const int kend = min(kbeg + p.kz, p.Z1);
+    const bool col_ok = i0 >= 0 && i0 < p.px;
+    {
+        for (int v = r; v < p.nv_h + p.nv_e; v += TY + 1) {
+            const float* src = v < p.nv_h ? p.xv_h + (size_t)v * p.px : p.xv_e + (size_t)(v - p.nv_h) * p.px;
+            S.xs[v * 32 + lane] = col_ok ? __ldg(reinterpret_cast<const float4*>(src + i0)) : zero4();
+        }
+    }
+    const float4* xsh = S.xs + lane;
+    const float4* xse = S.xs + p.nv_h * 32 + lane;
+    const bool in_grid = col_ok && j >= 0 && j < p.Y1;
+    const bool reg_x = (i0 >= p.X0 && i0 < p.X1) || i0 >= p.XT0;
+    const bool ext = in_grid && (!reg_x || j < p.Y0);
+    const bool calc = in_grid && !ext;
+    const bool own = calc && lane >= 1 && r >= 1;
+    const bool row_ok = j >= 0 && j < p.Y1;
+    // what this thread stages per plane: its own float4 of E (rows up to Y1, the +1 row of the last owned row), the +1 row
+    // for the top warp, the +1 column for lane 31, its own float4 of H_old where H_new is computed, 16 bytes of a record
+    const bool e_ok = col_ok && j >= 0 && j < p.ny && j <= p.Y1;
+    const bool top = r == TY;
+    const bool e_top_ok = top && col_ok && j + 1 >= 0 && j + 1 < p.ny && j + 1 <= p.Y1;
+    const bool e_col_ok = lane == 31 && i0 + 4 < p.px && j >= 0 && j < p.Y1;
+    const int kfirst = kbeg > p.Z0 ? kbeg - 1 : kbeg;
+    const long long base0 = (long long)(kfirst + 1) * p.sz + (long long)j * p.px + i0;
+    const long long mrow0 = ((long long)(kfirst + 1) * p.ny + j) * 32;
+    const char* pe = reinterpret_cast<const char*>(p.ein + base0);          // plane k of E_old / H_old / outputs
+    const char* ph = reinterpret_cast<const char*>(p.hin + base0);
+    char* qe = reinterpret_cast<char*>(p.eout + base0);
+    char* qh = reinterpret_cast<char*>(p.hout + base0);
+    const char* mrec = (lane < 2 ? reinterpret_cast<const char*>(p.meta_h) : reinterpret_cast<const char*>(p.meta_e)) + mrow0 + (lane & 1) * 16;
+    const char* safe = reinterpret_cast<const char*>(p.ein);               // any valid address for the zero-fill copies
+
+    // stage E_old of the plane d planes above the current one into ring slot se
+    auto stage_e = [&](int se, long long d) {
+        const char* b = pe + d;
+        cp_async16(&S.es[se][0][r][lane], e_ok ? b : safe, e_ok);
+        cp_async16(&S.es[se][1][r][lane], e_ok ? b + p.b_cs : safe, e_ok);
+        cp_async16(&S.es[se][2][r][lane], e_ok ? b + p.b_2cs : safe, e_ok);
+        if (top) {
+            cp_async16(&S.es[se][0][TY + 1][lane], e_top_ok ? b + p.b_row : safe, e_top_ok);
+            cp_async16(&S.es[se][2][TY + 1][lane], e_top_ok ? b + p.b_row_2cs : safe, e_top_ok);
+        }
+        if (lane == 31) {
+            cp_async16(&S.es[se][1][r][32], e_col_ok ? b + p.b_cs + 16 : safe, e_col_ok);
+            cp_async16(&S.es[se][2][r][32], e_col_ok ? b + p.b_2cs + 16 : safe, e_col_ok);
+        }
+    };
+    auto stage_h = [&](int sh, long long d) {
+        const char* b = ph + d;
+        cp_async16(&S.hs[sh][0][r][lane], calc ? b : safe, calc);
+        cp_async16(&S.hs[sh][1][r][lane], calc ? b + p.b_cs : safe, calc);
+        cp_async16(&S.hs[sh][2][r][lane], calc ? b + p.b_2cs : safe, calc);
+    };
+
+    int se = 0, sh = 0;                                      // ring slots of plane k
+    stage_e(0, 0); stage_e(1, p.b_sz); stage_h(0, 0);
+    if (lane < 4) cp_async16(&S.ms[0][r][lane], row_ok ? mrec : safe, row_ok);
+    cp_async_commit();
+    float4 hx_km = zero4(), hy_km = zero4();                 // H_new(k-1)
+    if (kfirst == kbeg && own) { hx_km = ldb4(qh - p.b_sz); hy_km = ldb4(qh - p.b_sz + p.b_cs); }
+    if (lane == 0) { S.prod[r] = 0; S.rd[r] = 0; S.stg[r] = 1; }
+    cp_async_wait<0>();
+    __syncthreads();
+    volatile int* const prod = S.prod; volatile int* const rd = S.rd; volatile int* const stg = S.stg;
+
+    for (int k = kfirst; k < kend; ++k, pe += p.b_sz, ph += p.b_sz, qe += p.b_sz, qh += p.b_sz, mrec += p.meta_step) {
+        const bool pro = k < kbeg;
+        const int t = k - kfirst;
+        const int se1 = se == 2 ? 0 : se + 1, se2 = se1 == 2 ? 0 : se1 + 1, mb = t & 1;
+        // ring slot se2 held plane k-1, whose row r the warp below read during its iteration t-1
+        if (r >= 1 && t >= 1) spin_ge(&rd[r - 1], t);
+        if (k + 1 < kend) {                                  // next iteration's new data: E(k+2), H_old(k+1), records of k+1
+            stage_e(se2, 2 * p.b_sz); stage_h(sh ^ 1, p.b_sz);
+            if (lane < 4) cp_async16(&S.ms[mb ^ 1][r][lane], row_ok ? mrec + p.meta_step : safe, row_ok);
+        }
+        cp_async_commit();
+        float4 hx = zero4(), hy = zero4(), hz = zero4();
+        float4 ax = zero4(), ay = zero4(), az = zero4(), bx = zero4(), by = zero4(), bz = zero4();
+        if (r < TY) spin_ge(&stg[r + 1], t + 1);             // row r+1 of plane k is staged by the warp above
+        const float4 ex = S.es[se][0][r][lane], ey = S.es[se][1][r][lane], ez = S.es[se][2][r][lane];
+        if (calc) {
+            hx = S.hs[sh][0][r][lane]; hy = S.hs[sh][1][r][lane]; hz = S.hs[sh][2][r][lane];
+            row_coefs(S.ms[mb][r][0], S.ms[mb][r][1], xsh, p.ii, p.iv, p.xv_h,
+                      (long long)((ph - reinterpret_cast<const char*>(p.hin)) >> 2), p.cs, i0, p.px, ax, ay, az, bx, by, bz);
+        } else if (ext) {
+            hx = ldb4(qh); hy = ldb4(qh + p.b_cs); hz = ldb4(qh + p.b_2cs);
+        }
+        float ez_r = __shfl_down_sync(0xffffffffu, ez.x, 1);
+        float ey_r = __shfl_down_sync(0xffffffffu, ey.x, 1);
+        if (lane == 31) { ez_r = S.es[se][2][r][32].x; ey_r = S.es[se][1][r][32].x; }
+        if (calc) {
+            const float4 ex1 = S.es[se1][0][r][lane], ey1 = S.es[se1][1][r][lane];
+            const float4 ex_jp = S.es[se][0][r + 1][lane], ez_jp = S.es[se][2][r + 1][lane];
+            const float4 ez_ip = make_float4(ez.y, ez.z, ez.w, ez_r);
+            const float4 ey_ip = make_float4(ey.y, ey.z, ey.w, ey_r);
+            hx = upd4(ax, hx, bx, ez, ez_jp, ey, ey1);
+            hy = upd4(ay, hy, by, ex, ex1, ez, ez_ip);
+            hz = upd4(az, hz, bz, ey, ey_ip, ex, ex_jp);
+        }
+        if (own && !pro) {
+            stb4(qh, hx); stb4(qh + p.b_cs, hy); stb4(qh + p.b_2cs, hz);
+            row_coefs(S.ms[mb][r][2], S.ms[mb][r][3], xse, p.vv, p.vi, p.xv_e,
+                      (long long)((pe - reinterpret_cast<const char*>(p.ein)) >> 2), p.cs, i0, p.px, ax, ay, az, bx, by, bz);
+        }
+        // publish this plane's H_new row for the warp above (it must have consumed the row of two planes ago) ...
+        if (r < TY && t >= 2) spin_ge(&rd[r + 1], t - 1);
+        S.xb[mb][r][0][lane] = hz; S.xb[mb][r][1][lane] = hx;
+        cp_async_wait<0>();                                  // ... and the staged data of the next plane (this warp's copies)
+        publish2(&prod[r], t + 1, &stg[r], t + 2);
+        if (r >= 1) spin_ge(&prod[r - 1], t + 1);            // the row below has published H_new(k)
+        const float hz_l = __shfl_up_sync(0xffffffffu, hz.w, 1);
+        const float hy_l = __shfl_up_sync(0xffffffffu, hy.w, 1);
+        float4 hz_jm = zero4(), hx_jm = zero4();
+        if (r >= 1) { hz_jm = S.xb[mb][r - 1][0][lane]; hx_jm = S.xb[mb][r - 1][1][lane]; }
+        publish1(&rd[r], t + 1);                             // done with every other warp's data of this plane
+        if (own && !pro) {
+            const float4 hz_im = make_float4(hz_l, hz.x, hz.y, hz.z);
+            const float4 hy_im = make_float4(hy_l, hy.x, hy.y, hy.z);
+            const float4 exn = upd4(ax, ex, bx, hz, hz_jm, hy, hy_km);
+            const float4 eyn = upd4(ay, ey, by, hx, hx_km, hz, hz_im);
+            const float4 ezn = upd4(az, ez, bz, hy, hy_im, hx, hx_jm);
+            stb4(qe, exn); stb4(qe + p.b_cs, eyn); stb4(qe + p.b_2cs, ezn);
+        }
+        hx_km = hx; hy_km = hy;
+        se = se1; sh ^= 1;
+    }
+}
+
+
 template <int MODE>
 static int launch_volume_one(b200fdtd_ctx* c, int which, int k0, int k1, const RowParams& r, cudaStream_t stream, int kz, int nchunks, int grid_y = 0)
 {
@@ -1398,9 +1573,12 @@ static int launch_he(b200fdtd_ctx* c, cudaStream_t stream)
     p.nv_e = c->cmp_nvec[0]; p.nv_h = c->cmp_nvec[1];
     const size_t xs_bytes = (size_t)(p.nv_e + p.nv_h) * 32 * sizeof(float4);
     const bool v2 = cmp && (c->variant & 512) == 0 && xs_bytes <= 96 * 1024;
-    const bool v3 = v2 && (c->variant & 2048) == 0;
+    const bool v3 = v2 && (c->variant & (1 << 18)) == 0;
 #define LAUNCH_HE(TYV) do { \
-        if (v3) { const size_t sm3 = sizeof(He3Smem<TYV>) + xs_bytes; \
+        if (v3 && (c->variant & (1 << 19)) != 0) { const size_t sm4 = sizeof(He4Smem<TYV>) + xs_bytes; \
+                  CK(cudaFuncSetAttribute(update_he4_kernel<TYV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4)); \
+                  update_he4_kernel<TYV><<<grid, block, sm4, stream>>>(p); } \
+        else if (v3) { const size_t sm3 = sizeof(He3Smem<TYV>) + xs_bytes; \
                   CK(cudaFuncSetAttribute(update_he3_kernel<TYV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3)); \
                   update_he3_kernel<TYV><<<grid, block, sm3, stream>>>(p); } \
         else if (v2) { if (xs_bytes > 8 * 1024) CK(cudaFuncSetAttribute(update_he2_kernel<TYV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xs_bytes)); \
