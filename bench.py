@@ -28,6 +28,10 @@ for _p in (ROOT, PKG):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
+# stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION in some images) out of it
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 import numpy as np  # noqa: E402
 
 BYTES_PER_CELL_PASS = 60          # 15 fp32 streams per E (or H) pass

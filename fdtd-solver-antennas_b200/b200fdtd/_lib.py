@@ -59,6 +59,10 @@ SYMBOLS = {
     "b200fdtd_half_step": (C.c_int, [vp, C.c_int]),
     "b200fdtd_half_step_part": (C.c_int, [vp, C.c_int, C.c_int]),
     "b200fdtd_update_only": (C.c_int, [vp, C.c_int]),
+    "b200fdtd_bind_alt_fields": (C.c_int, [vp, vp, vp]),
+    "b200fdtd_fused_step_part": (C.c_int, [vp, C.c_int]),
+    "b200fdtd_current_copy": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "b200fdtd_reset_current_copy": (C.c_int, [vp]),
     "b200fdtd_plan_info": (C.c_int, [vp, c_i64, c_i64, c_i64]),
     "b200fdtd_set_he_tuning": (C.c_int, [vp, C.c_int, C.c_int]),
     "b200fdtd_he_info": (C.c_int, [vp, C.POINTER(C.c_int)]),

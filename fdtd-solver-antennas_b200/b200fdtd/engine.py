@@ -216,6 +216,24 @@ class Engine:
         """no stream joins: the caller orders work on self.stream itself (z-slab overlap, simulation._step_multi)"""
         check(self.L.b200fdtd_half_step_part(self.h, int(phase), int(part)))
 
+    # ---- fused H->E steps on a z-slab rank (b200fdtd_fused_step_part) ----
+    def bind_alt_fields(self):
+        """allocate and bind the second copy of the fields (caller-owned variant: the halo exchange needs the tensors)"""
+        self.volt2 = torch.zeros(self.shape, dtype=torch.float32, device=self.device)
+        self.curr2 = torch.zeros(self.shape, dtype=torch.float32, device=self.device)
+        check(self.L.b200fdtd_bind_alt_fields(self.h, self.volt2.data_ptr(), self.curr2.data_ptr()))
+
+    def fused_step_part(self, part):
+        check(self.L.b200fdtd_fused_step_part(self.h, int(part)))
+
+    def current_copy(self):
+        a, b = C.c_int(), C.c_int()
+        check(self.L.b200fdtd_current_copy(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def reset_current_copy(self):
+        check(self.L.b200fdtd_reset_current_copy(self.h))
+
     def half_step_raw(self, phase):
         check(self.L.b200fdtd_half_step(self.h, int(phase)))
 

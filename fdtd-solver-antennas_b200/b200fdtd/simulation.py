@@ -45,7 +45,8 @@ def _default_engine_factory(nx, ny, nz, px, device):
 
 class Simulation:
     def __init__(self, setup: Setup, device=0, rank=0, world=1, group=None, engine_factory=None,
-                 build_device=None, px_align=32, log=None, nf2ff_freqs=None, probe_freqs=None, align_x_slabs=True, compress_pml=True):
+                 build_device=None, px_align=32, log=None, nf2ff_freqs=None, probe_freqs=None, align_x_slabs=True, compress_pml=True,
+                 fused_multi=True):
         self.setup = setup
         self.rank, self.world, self.group = int(rank), int(world), group
         self.device = device
@@ -55,6 +56,7 @@ class Simulation:
         self.px_align = px_align
         self.align_x_slabs = bool(align_x_slabs)
         self.compress_pml = bool(compress_pml)
+        self.fused_multi = bool(fused_multi)
         self.nf2ff_freqs = None if nf2ff_freqs is None else np.atleast_1d(np.asarray(nf2ff_freqs, np.float64))
         self.probe_freqs = None if probe_freqs is None else np.atleast_1d(np.asarray(probe_freqs, np.float64))
         self.engine = None
@@ -265,7 +267,21 @@ class Simulation:
             self._tc = torch.from_numpy(E.curr) if isinstance(E.curr, np.ndarray) else E.curr
             self._gpu = self._tv.is_cuda
             self._pend_e, self._pend_h = [], []
+            # fused H->E steps (second field copy, C-ABI b200fdtd_fused_step_part): CUDA engine with >= 3 planes per slab
+            self._fused = bool(self._gpu and self.fused_multi and hasattr(E, "fused_step_part") and self.nz >= 3)
+            self._copies_v, self._copies_c = [self._tv], [self._tc]
+            if self._fused:
+                try:
+                    E.bind_alt_fields()
+                    self._copies_v.append(E.volt2); self._copies_c.append(E.curr2)
+                except Exception:            # e.g. out of memory: keep the separate half steps
+                    self._fused = False
+            self._vcur = self._ccur = 0
         return self._tv, self._tc
+
+    def _cur(self):
+        """the copies that hold E and H right now (the fused steps ping-pong between two copies)"""
+        return self._copies_v[self._vcur], self._copies_c[self._ccur]
 
     def _exchange_async(self, f, direction, ncomp):
         """direction +1: my top owned plane -> upper neighbour's lower ghost; -1: my plane 0 -> lower neighbour's upper ghost"""
@@ -289,28 +305,72 @@ class Simulation:
         for w in works:
             w.wait()            # NCCL: the current (engine) stream waits on the device; gloo: host wait
 
+    def _e_half(self):
+        """E half step in two parts around the wait for the lower ghost H; then my plane 0 goes down"""
+        E = self.engine
+        E.half_step_part(0, 0)                       # E: pre passes + planes [1,nz)      (overlaps the H halo)
+        self._wait(self._pend_h); self._pend_h = []
+        E.half_step_part(0, 1)                       # E: plane 0 + post passes
+        self._pend_e = self._exchange_async(self._cur()[0], -1, 2)
+
+    def _h_half(self):
+        E = self.engine
+        E.half_step_part(1, 0)                       # H: pre passes + planes [0,nz-1)    (overlaps the E halo)
+        self._wait(self._pend_e); self._pend_e = []
+        E.half_step_part(1, 1)                       # H: top plane + post passes, ++ts
+        self._pend_h = self._exchange_async(self._cur()[1], +1, 2)
+
+    def _fused_step(self):
+        """H(n) + E(n+1): boundary planes by separate launches, interior planes by the fused launch (csrc, part 0..3)"""
+        E = self.engine
+        E.fused_step_part(0)                         # H: plane 0 + interior PML slabs
+        self._wait(self._pend_e); self._pend_e = []
+        E.fused_step_part(1)                         # H: top plane (needed the upper ghost E)
+        h_new = self._copies_c[self._ccur ^ 1]       # the H launches wrote the other copy; it becomes current in part 2
+        self._pend_h = self._exchange_async(h_new, +1, 2)
+        E.fused_step_part(2)                         # fused launch over the interior planes (overlaps the H halo), ++ts
+        self._ccur ^= 1
+        self._wait(self._pend_h); self._pend_h = []
+        E.fused_step_part(3)                         # E: interior PML slabs, plane 0 (lower ghost H_new), top plane; excitation
+        self._vcur ^= 1
+        self._pend_e = self._exchange_async(self._cur()[0], -1, 2)
+
     def _step_multi(self, n):
         import contextlib
         E = self.engine
-        volt, curr = self._views()
+        self._views()
         ctx = torch.cuda.stream(E.stream) if self._gpu else contextlib.nullcontext()
         sampling = bool(self.faces) or bool(self.probe_names)
         with ctx:
-            for _ in range(n):
-                E.half_step_part(0, 0)                       # E: pre passes + planes [1,nz)      (overlaps the H halo)
-                self._wait(self._pend_h)
-                E.half_step_part(0, 1)                       # E: plane 0 + post passes
-                self._pend_e = self._exchange_async(volt, -1, 2)
-                E.half_step_part(1, 0)                       # H: pre passes + planes [0,nz-1)    (overlaps the E halo)
-                self._wait(self._pend_e)
-                E.half_step_part(1, 1)                       # H: top plane + post passes, ++ts
-                self._pend_h = self._exchange_async(curr, +1, 2)
+            left = n
+            while left > 0:
+                span = left
+                if sampling:
+                    span = min(span, self.interval - (E.ts % self.interval))
+                # E(0) | H(0)+E(1) | ... | H(span-2)+E(span-1) | H(span-1)
+                self._e_half()
+                for _ in range(span - 1):
+                    if self._fused:
+                        self._fused_step()
+                    else:
+                        self._h_half(); self._e_half()
+                self._h_half()
+                left -= span
                 if sampling and (E.ts % self.interval) == 0:
                     self._wait(self._pend_h); self._pend_h = []
                     if self.faces:                           # NF2FF node interpolation reads E of plane K0-1 too
-                        self._wait(self._exchange_async(volt, +1, 3))
+                        self._wait(self._exchange_async(self._cur()[0], +1, 3))
                     E.half_step_raw(2)
             self._wait(self._pend_h); self._pend_h = []
+            self._wait(self._pend_e); self._pend_e = []
+            if self._fused and (self._vcur or self._ccur):
+                # hand the state back in the bound arrays (the caller, tests and collect() look at those)
+                if self._vcur:
+                    self._copies_v[0].copy_(self._copies_v[1])
+                if self._ccur:
+                    self._copies_c[0].copy_(self._copies_c[1])
+                self._vcur = self._ccur = 0
+                E.reset_current_copy()
         if self._gpu:
             torch.cuda.current_stream(E.device).wait_stream(E.stream)
 

@@ -94,6 +94,7 @@ struct b200fdtd_ctx {
     // tile from the old values its neighbours are overwriting).  vcur/ccur say which copy holds the current E / H; both are
     // 0 whenever control returns to the caller, so the bound arrays always hold the state.
     float *alt_volt = nullptr, *alt_curr = nullptr;
+    bool alt_owned = false;                // allocated by the library (else bound by the caller, b200fdtd_bind_alt_fields)
     int vcur = 0, ccur = 0;
     bool flip = false;                     // volume launches write the other copy instead of updating in place
     int he_ty = 7, he_kz = 32;             // fused launch: rows per CTA (+1 halo row), planes marched per CTA
@@ -1543,10 +1544,11 @@ static int launch_volume(b200fdtd_ctx* c, int which, int k0, int k1)
 
 
 // fused H->E launch over the plain region: reads the current copies, writes the other copies (the caller flips)
-static int launch_he(b200fdtd_ctx* c, cudaStream_t stream)
+static int launch_he(b200fdtd_ctx* c, cudaStream_t stream, int zc0 = -1, int zc1 = -1)
 {
     const VolumePlan& P = c->plan;
-    if (P.nseg != 1) return fail("fused H->E launch without a plain region");
+    const bool clipped = zc0 >= 0;                           // z-slab ranks: interior planes [zc0, zc1) only
+    if (P.nseg != 1) return clipped ? 0 : fail("fused H->E launch without a plain region");
     HeParams p;
     p.ein = cur_volt(c); p.hin = cur_curr(c); p.eout = oth_volt(c); p.hout = oth_curr(c);
     p.vv = c->vv; p.vi = c->vi; p.ii = c->ii; p.iv = c->iv;
@@ -1555,6 +1557,7 @@ static int launch_he(b200fdtd_ctx* c, cudaStream_t stream)
     p.ny = c->ny; p.px = c->px; p.sz = c->sz; p.cs = c->cs;
     p.X0 = P.has_lo ? P.xw0 : 0; p.X1 = P.has_hi ? P.xx1 : c->px; p.XT0 = P.has_hi ? P.xx1 + P.xw1 : c->px;
     p.Y0 = P.ym0; p.Y1 = P.ym1; p.Z0 = P.seg0[0]; p.Z1 = P.seg1[0];
+    if (clipped) { if (p.Z0 < zc0) p.Z0 = zc0; if (p.Z1 > zc1) p.Z1 = zc1; if (p.Z1 <= p.Z0) return 0; }
     if (p.Y1 <= p.Y0 || p.Z1 <= p.Z0 || p.X1 <= p.X0) return fail("fused H->E launch over an empty region");
     const int ty = c->he_ty;
     int kz = c->he_kz; if (kz > p.Z1 - p.Z0) kz = p.Z1 - p.Z0;
@@ -1617,6 +1620,7 @@ static bool he_ready(b200fdtd_ctx* c, int steps)
         if (cudaMalloc((void**)&c->alt_curr, bytes) != cudaSuccess) { cudaGetLastError(); cudaFree(c->alt_volt); c->alt_volt = c->alt_curr = nullptr; return false; }
         cudaMemsetAsync(c->alt_volt, 0, bytes, c->stream);
         cudaMemsetAsync(c->alt_curr, 0, bytes, c->stream);
+        c->alt_owned = true;
     }
     return true;
 }
@@ -1957,7 +1961,7 @@ extern "C" int b200fdtd_destroy(b200fdtd_ctx* c)
     cudaStreamSynchronize(c->stream);
     drop_graph(c);
     cudaFree(c->d_ts); cudaFree(c->d_partials); cudaFree(c->d_energy);
-    cudaFree(c->alt_volt); cudaFree(c->alt_curr);
+    if (c->alt_owned) { cudaFree(c->alt_volt); cudaFree(c->alt_curr); }
     cudaFree(c->exc_idx); cudaFree(c->exc_amp); cudaFree(c->exc_delay); cudaFree(c->exc_sig);
     cudaFree(c->mur_dst); cudaFree(c->mur_src); cudaFree(c->mur_coeff); cudaFree(c->mur_tmp);
     cudaFree(c->pr_kind); cudaFree(c->pr_off); cudaFree(c->pr_idx); cudaFree(c->pr_w); cudaFree(c->pr_freqs);
@@ -2608,6 +2612,96 @@ extern "C" int b200fdtd_half_step_part(b200fdtd_ctx* c, int phase, int part)
     if (launch_pml(c, 1, 1)) return 1;
     if (launch_ts_add(c, 1)) return 1;
     c->ts += 1;
+    return 0;
+}
+
+// ---- fused H->E step on a z-slab rank -------------------------------------------------------------------------------
+// The fused launch cannot cover a rank's boundary planes: E_new of plane 0 needs the lower neighbour's H_new (computed in
+// the same sweep over there), H_new of the top plane needs the upper neighbour's E.  So the two boundary planes keep the
+// separate H and E launches (they write the other field copy like the fused launch does) and the fused launch covers the
+// interior planes [1, nz-1); it reads H_new of plane 0 from the output copy like any other halo cell outside its region.
+//   part 0: Mur pre; H of plane 0 and of the PML slabs of the interior planes            (needs no ghost plane)
+//   part 1: H of the top plane                          (needs the upper ghost E; caller then sends H_new(top) up)
+//   part 2: fused H->E launch over the interior planes; H is new from here on; ++ts      (overlaps that exchange)
+//   part 3: E of the PML slabs of the interior planes, of plane 0 (needs the lower ghost H_new) and of the top plane; E is
+//           new from here on; Mur post, excitation, Mur apply                            (caller then sends E_new(0) down)
+// b200fdtd_current_copy tells which copy (0 = bound arrays, 1 = second copy) holds E and H afterwards.
+extern "C" int b200fdtd_fused_step_part(b200fdtd_ctx* c, int part)
+{
+    if (!c) return fail("NULL ctx");
+    if (!c->volt || !c->vv) return fail("fields/coefficients not bound");
+    if (!c->alt_volt || !c->alt_curr) return fail("bind the second field copy first (b200fdtd_bind_alt_fields)");
+    if (part < 0 || part > 3) return fail("part must be 0..3");
+    CK(cudaSetDevice(c->device));
+    if (!c->plan.valid) if (build_plan(c)) return 1;
+    if (c->pml.n > 0) return fail("fused steps need every PML box fused into the volume launches");
+    const int nz = c->nz;
+    if (nz < 3) return fail("fused steps need at least 3 planes per slab");
+    int rc = 0;
+    const bool side = (c->plan.nfused > 0 || c->plan.xedge) && (c->variant & 2) == 0;    // interior slab launches side by side
+    if (part == 0) {
+        if (launch_mur(c, 0)) return 1;
+        c->flip = true;
+        if (side) rc = fork_side(c);
+        if (!rc) rc = launch_volume_xslabs(c, 1, 1, nz - 1, side ? c->side : c->stream);
+        if (!rc) rc = launch_volume_fused(c, 1, 1, nz - 1, side ? slab_stream(c) : c->stream);
+        if (!rc) rc = launch_volume(c, 1, 0, 1);
+        if (!rc && side) rc = join_side(c);
+        c->flip = false;
+        return rc;
+    }
+    if (part == 1) {
+        c->flip = true;
+        rc = launch_volume(c, 1, nz - 1, nz);
+        c->flip = false;
+        return rc;
+    }
+    if (part == 2) {
+        if (launch_he(c, c->stream, 1, nz - 1)) return 1;
+        c->ccur ^= 1;
+        if (launch_ts_add(c, 1)) return 1;
+        c->ts += 1;
+        return 0;
+    }
+    c->flip = true;
+    if (side) rc = fork_side(c);
+    if (!rc) rc = launch_volume_xslabs(c, 0, 1, nz - 1, side ? c->side : c->stream);
+    if (!rc) rc = launch_volume_fused(c, 0, 1, nz - 1, side ? slab_stream(c) : c->stream);
+    if (!rc) rc = launch_volume(c, 0, 0, 1);
+    if (!rc) rc = launch_volume(c, 0, nz - 1, nz);
+    if (!rc && side) rc = join_side(c);
+    c->flip = false;
+    if (rc) return 1;
+    c->vcur ^= 1;
+    if (launch_mur(c, 1)) return 1;
+    if (launch_excite(c, 0)) return 1;
+    return launch_mur(c, 2);
+}
+
+extern "C" int b200fdtd_bind_alt_fields(b200fdtd_ctx* c, float* volt2, float* curr2)
+{
+    if (!c) return fail("NULL ctx");
+    if ((volt2 == nullptr) != (curr2 == nullptr)) return fail("bind both copies or none");
+    if (((uintptr_t)volt2 | (uintptr_t)curr2) & 15) return fail("field pointers must be 16-byte aligned");
+    if (c->vcur || c->ccur) return fail("the state lives in the second copy: normalise first (b200fdtd_reset_current_copy)");
+    CK(cudaSetDevice(c->device));
+    drop_graph(c);
+    if (c->alt_owned) { cudaFree(c->alt_volt); cudaFree(c->alt_curr); c->alt_owned = false; }
+    c->alt_volt = volt2; c->alt_curr = curr2;
+    return 0;
+}
+
+extern "C" int b200fdtd_current_copy(b200fdtd_ctx* c, int* vcur, int* ccur)
+{
+    if (!c || !vcur || !ccur) return fail("NULL argument");
+    *vcur = c->vcur; *ccur = c->ccur;
+    return 0;
+}
+
+extern "C" int b200fdtd_reset_current_copy(b200fdtd_ctx* c)
+{
+    if (!c) return fail("NULL ctx");
+    c->vcur = c->ccur = 0;                       // the caller has copied the state back into the bound arrays
     return 0;
 }
 

@@ -159,6 +159,21 @@ int b200fdtd_half_step(b200fdtd_ctx* ctx, int phase);
  *   phase 0: part 0 = pre passes + planes [1,nz),   part 1 = plane 0 (reads the lower ghost H) + post passes
  *   phase 1: part 0 = pre passes + planes [0,nz-1), part 1 = plane nz-1 (reads the upper ghost E) + post, ++ts */
 int b200fdtd_half_step_part(b200fdtd_ctx* ctx, int phase, int part);
+/* Fused H->E steps on a z-slab rank (see b200fdtd_run for the single-slab case).  The caller owns the second copy of the
+ * fields ([3][nz+2][ny][px] each, zero-initialised, ghost planes included) and does the halo exchange on whichever copy is
+ * current.  One step = parts 0..3 in order:
+ *   0: Mur pre, H of plane 0 and of the interior PML slabs   1: H of the top plane (after the upper ghost E has arrived;
+ *   then send H_new(top) up from the NOT yet current H copy)   2: fused launch over planes [1,nz-1), H copy flips, ++ts
+ *   3: E of the interior PML slabs, plane 0 (after the lower ghost H_new has arrived in the current H copy) and top
+ *      plane, E copy flips, Mur post / excitation / Mur apply (then send E_new(0) down from the current E copy).
+ * The step starts from (E(n), H(n-1)) and ends at (E(n+1), H(n)): bracket a span of steps with half steps
+ * b200fdtd_half_step_part(0, .) and (1, .), which work on the current copies. */
+int b200fdtd_bind_alt_fields(b200fdtd_ctx* ctx, float* volt2, float* curr2);
+int b200fdtd_fused_step_part(b200fdtd_ctx* ctx, int part);
+/* which copy holds E / H now: 0 = the arrays of b200fdtd_bind_fields, 1 = the second copy */
+int b200fdtd_current_copy(b200fdtd_ctx* ctx, int* vcur, int* ccur);
+/* the caller has copied the state back into the bound arrays: copy 0 is current again */
+int b200fdtd_reset_current_copy(b200fdtd_ctx* ctx);
 /* only the volume kernels (bench / roofline): which = 0 E update, 1 H update (plain + fused PML slab launches);
  * 2 / 3 = only the plain launch of the E / H update (rows outside the fused PML slabs);
  * 4 = only the fused H->E launch over the plain region (writes the second field copy: the state is untouched) */
