@@ -193,3 +193,38 @@ def test_fused_h_to_e_with_row_compression():
     R.run(13); G.run(13, use_graph=True)
     assert G.he_active
     _assert_fields_equal(R, G, "fused H->E with row compression")
+
+
+@pytest.mark.parametrize("layout", ["slabs", "mur"])
+@pytest.mark.parametrize("shape", [(37, 29, 23, 40), (261, 21, 14, 288)])
+def test_fused_step_parts_of_a_z_slab_rank(layout, shape):
+    """the z-slab form of the fused step (b200fdtd_fused_step_part: boundary planes by separate launches, interior planes by
+    the fused launch, caller-owned second copy) on a single slab with zero ghost planes must equal the oracle's steps"""
+    nx, ny, nz, px = shape
+    P = synth.make_problem(nx, ny, nz, px, seed=5, with_pml=layout == "slabs", fused_pml=layout == "slabs",
+                           with_probes=False, with_nf2ff=False)
+    R, G = _engines(P)
+    G.bind_alt_fields()
+    # the synthetic problem has (static, non-zero) ghost planes: a real z-slab run receives them into whichever copy is
+    # current, here they are simply mirrored into the second copy
+    G.volt2[:, [0, nz + 1]] = G.volt[:, [0, nz + 1]]
+    G.curr2[:, [0, nz + 1]] = G.curr[:, [0, nz + 1]]
+    import torch
+    torch.cuda.synchronize()
+    n = 6
+    G.half_step_part(0, 0); G.half_step_part(0, 1)            # E(0)
+    for _ in range(n - 1):                                     # H(s-1) + E(s)
+        for part in range(4):
+            G.fused_step_part(part)
+    G.half_step_part(1, 0); G.half_step_part(1, 1)            # H(n-1)
+    G.sync()                                                   # the part calls do not join the engine stream with torch's
+    vcur, ccur = G.current_copy()
+    assert (vcur, ccur) == ((n - 1) % 2, (n - 1) % 2)
+    if vcur:
+        G.volt.copy_(G.volt2)
+    if ccur:
+        G.curr.copy_(G.curr2)
+    G.reset_current_copy()
+    R.run(n)
+    assert G.ts == n
+    _assert_fields_equal(R, G, f"{n} steps through the fused step parts")
