@@ -324,11 +324,12 @@ class Simulation:
         """H(n) + E(n+1): boundary planes by separate launches, interior planes by the fused launch (csrc, part 0..3)"""
         E = self.engine
         E.fused_step_part(0)                         # H: plane 0 + interior PML slabs
+        E.fused_step_part(4)                         # fused launch, lower half of the interior planes (overlaps the E halo)
         self._wait(self._pend_e); self._pend_e = []
         E.fused_step_part(1)                         # H: top plane (needed the upper ghost E)
         h_new = self._copies_c[self._ccur ^ 1]       # the H launches wrote the other copy; it becomes current in part 2
         self._pend_h = self._exchange_async(h_new, +1, 2)
-        E.fused_step_part(2)                         # fused launch over the interior planes (overlaps the H halo), ++ts
+        E.fused_step_part(2)                         # fused launch, upper half (overlaps the H halo), ++ts
         self._ccur ^= 1
         self._wait(self._pend_h); self._pend_h = []
         E.fused_step_part(3)                         # E: interior PML slabs, plane 0 (lower ghost H_new), top plane; excitation

@@ -94,6 +94,7 @@ struct b200fdtd_ctx {
     // tile from the old values its neighbours are overwriting).  vcur/ccur say which copy holds the current E / H; both are
     // 0 whenever control returns to the caller, so the bound arrays always hold the state.
     float *alt_volt = nullptr, *alt_curr = nullptr;
+    int he_mid = 0;                        // z-slab fused step: plane where the upper half of the fused launch starts (0 = whole)
     bool alt_owned = false;                // allocated by the library (else bound by the caller, b200fdtd_bind_alt_fields)
     int vcur = 0, ccur = 0;
     bool flip = false;                     // volume launches write the other copy instead of updating in place
@@ -2622,7 +2623,9 @@ extern "C" int b200fdtd_half_step_part(b200fdtd_ctx* c, int phase, int part)
 // interior planes [1, nz-1); it reads H_new of plane 0 from the output copy like any other halo cell outside its region.
 //   part 0: Mur pre; H of plane 0 and of the PML slabs of the interior planes            (needs no ghost plane)
 //   part 1: H of the top plane                          (needs the upper ghost E; caller then sends H_new(top) up)
-//   part 2: fused H->E launch over the interior planes; H is new from here on; ++ts      (overlaps that exchange)
+//   part 4: (optional, between 0 and 1) fused H->E launch over the lower half of the interior planes, so that the wait for
+//           the upper ghost E hides behind it
+//   part 2: fused H->E launch over the (rest of the) interior planes; H is new from here on; ++ts   (overlaps that exchange)
 //   part 3: E of the PML slabs of the interior planes, of plane 0 (needs the lower ghost H_new) and of the top plane; E is
 //           new from here on; Mur post, excitation, Mur apply                            (caller then sends E_new(0) down)
 // b200fdtd_current_copy tells which copy (0 = bound arrays, 1 = second copy) holds E and H afterwards.
@@ -2631,7 +2634,7 @@ extern "C" int b200fdtd_fused_step_part(b200fdtd_ctx* c, int part)
     if (!c) return fail("NULL ctx");
     if (!c->volt || !c->vv) return fail("fields/coefficients not bound");
     if (!c->alt_volt || !c->alt_curr) return fail("bind the second field copy first (b200fdtd_bind_alt_fields)");
-    if (part < 0 || part > 3) return fail("part must be 0..3");
+    if (part < 0 || part > 4) return fail("part must be 0..4");
     CK(cudaSetDevice(c->device));
     if (!c->plan.valid) if (build_plan(c)) return 1;
     if (c->pml.n > 0) return fail("fused steps need every PML box fused into the volume launches");
@@ -2656,8 +2659,13 @@ extern "C" int b200fdtd_fused_step_part(b200fdtd_ctx* c, int part)
         c->flip = false;
         return rc;
     }
+    if (part == 4) {                                         // optional: lower half of the interior planes first
+        c->he_mid = 1 + (nz - 2) / 2;
+        return launch_he(c, c->stream, 1, c->he_mid);
+    }
     if (part == 2) {
-        if (launch_he(c, c->stream, 1, nz - 1)) return 1;
+        if (launch_he(c, c->stream, c->he_mid > 0 ? c->he_mid : 1, nz - 1)) return 1;
+        c->he_mid = 0;
         c->ccur ^= 1;
         if (launch_ts_add(c, 1)) return 1;
         c->ts += 1;

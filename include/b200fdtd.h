@@ -162,7 +162,8 @@ int b200fdtd_half_step_part(b200fdtd_ctx* ctx, int phase, int part);
 /* Fused H->E steps on a z-slab rank (see b200fdtd_run for the single-slab case).  The caller owns the second copy of the
  * fields ([3][nz+2][ny][px] each, zero-initialised) and does the halo exchange on whichever copy is current (ghost planes
  * that are never exchanged must hold the same values in both copies).  One step = parts 0..3 in order:
- *   0: Mur pre, H of plane 0 and of the interior PML slabs   1: H of the top plane (after the upper ghost E has arrived;
+ *   0: Mur pre, H of plane 0 and of the interior PML slabs   [4: optional, fused launch over the lower half of the
+ *   interior planes, hides the wait for the upper ghost E]   1: H of the top plane (after the upper ghost E has arrived;
  *   then send H_new(top) up from the NOT yet current H copy)   2: fused launch over planes [1,nz-1), H copy flips, ++ts
  *   3: E of the interior PML slabs, plane 0 (after the lower ghost H_new has arrived in the current H copy) and top
  *      plane, E copy flips, Mur post / excitation / Mur apply (then send E_new(0) down from the current E copy).
