@@ -1480,10 +1480,14 @@ static int slab_kz(int kz, int planes, long long ctas_per_chunk)
 }
 
 // narrow x-slab launches (MODE 2): PML pre/update/post on the slab columns of the plain rows
-static int launch_volume_xslabs(b200fdtd_ctx* c, int which, int k0, int k1, cudaStream_t stream)
+// sel: 0 = both slabs, 1 = only the slab at the low end of x, 2 = only the one at the high end
+static int launch_volume_xslabs(b200fdtd_ctx* c, int which, int k0, int k1, cudaStream_t stream, int sel = 0)
 {
-    const VolumePlan& P = c->plan;
+    VolumePlan P = c->plan;
     if (!P.xedge) return 0;
+    if (sel == 1) P.has_hi = 0;
+    if (sel == 2) P.has_lo = 0;
+    if (!P.has_lo && !P.has_hi) return 0;
     RowParams e; memset(&e, 0, sizeof(e));
     const FusedBox& L = P.xlo; const FusedBox& H = P.xhi;
     const FusedBox& any = P.has_lo ? L : H;
@@ -1511,11 +1515,17 @@ static int launch_volume_xslabs(b200fdtd_ctx* c, int which, int k0, int k1, cuda
 }
 
 // volume launches over the fused PML slabs (pre -> update -> post in registers)
-static int launch_volume_fused(b200fdtd_ctx* c, int which, int k0, int k1, cudaStream_t stream)
+// sel: 0 = all slabs, 1 = only the slabs at the low end of their axis (z0 = 0 / y0 = 0), 2 = only those at the high end
+static int launch_volume_fused(b200fdtd_ctx* c, int which, int k0, int k1, cudaStream_t stream, int sel = 0)
 {
     const VolumePlan& P = c->plan;
     for (int q = 0; q < P.nfused; ++q) {
         const FusedBox& B = P.fb[q];
+        if (sel) {
+            const bool zslab = B.y0 == 0 && B.by == c->ny;
+            const bool lo = zslab ? B.z0 == 0 : B.y0 == 0;
+            if ((sel == 1) != lo) continue;
+        }
         RowParams f; memset(&f, 0, sizeof(f));
         f.j0 = B.y0; f.j1 = B.y0 + B.by; f.y0 = B.y0; f.z0 = B.z0; f.by = B.by; f.bz = B.bz;
         f.flux = which == 0 ? B.flux_v : B.flux_i;
@@ -1579,13 +1589,13 @@ static int launch_he(b200fdtd_ctx* c, cudaStream_t stream, int zc0 = -1, int zc1
     const bool v2 = cmp && (c->variant & 512) == 0 && xs_bytes <= 96 * 1024;
     const bool v3 = v2 && (c->variant & (1 << 18)) == 0;
 #define LAUNCH_HE(TYV) do { \
-        if (v3 && (c->variant & (1 << 19)) != 0) { const size_t sm4 = sizeof(He4Smem<TYV>) + xs_bytes; \
+        if (v3 && (c->variant & (1 << 19)) != 0 && sizeof(He4Smem<TYV>) + xs_bytes <= 220 * 1024) { const size_t sm4 = sizeof(He4Smem<TYV>) + xs_bytes; \
                   CK(cudaFuncSetAttribute(update_he4_kernel<TYV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4)); \
                   update_he4_kernel<TYV><<<grid, block, sm4, stream>>>(p); } \
-        else if (v3) { const size_t sm3 = sizeof(He3Smem<TYV>) + xs_bytes; \
+        else if (v3 && sizeof(He3Smem<TYV>) + xs_bytes <= 220 * 1024) { const size_t sm3 = sizeof(He3Smem<TYV>) + xs_bytes; \
                   CK(cudaFuncSetAttribute(update_he3_kernel<TYV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3)); \
                   update_he3_kernel<TYV><<<grid, block, sm3, stream>>>(p); } \
-        else if (v2) { if (xs_bytes > 8 * 1024) CK(cudaFuncSetAttribute(update_he2_kernel<TYV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xs_bytes)); \
+        else if (v2 && 2 * sizeof(float4) * (TYV + 1) * 70 + xs_bytes <= 220 * 1024) { if (xs_bytes > 8 * 1024) CK(cudaFuncSetAttribute(update_he2_kernel<TYV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xs_bytes)); \
                   update_he2_kernel<TYV><<<grid, block, xs_bytes, stream>>>(p); } \
         else if (staged) { \
             const size_t sm = sizeof(HeSmem<TYV>); \
@@ -2444,7 +2454,31 @@ static int he_step(b200fdtd_ctx* c, int off)
     if (launch_mur(c, 0)) return 1;              // Mur reads the old E
     c->flip = true;
     int rc = 0;
+    const bool overlap = side && (c->variant & (1 << 20)) != 0;      // experiment (measured 1.5 % slower: the fused launch fills every SM)
     do {
+        if (overlap) {
+            // Only the slabs at the LOW ends feed the fused launch (its halo cells outside the region are at i-1, j-1, k-1), and
+            // their E update needs nothing from it (their own low-side neighbours are low-end slabs again).  So: low-end H,
+            // then the fused launch with the high-end H and the low-end E launches beside it, then the high-end E.
+            if ((rc = fork_side(c))) break;
+            if ((rc = launch_volume_xslabs(c, 1, 0, c->nz, c->side, 1))) break;
+            if ((rc = launch_volume_fused(c, 1, 0, c->nz, slab_stream(c), 1))) break;
+            if ((rc = join_side(c))) break;
+            if ((rc = fork_side(c))) break;                                  // side streams continue from here, not from the fused launch
+            if ((rc = launch_volume_xslabs(c, 1, 0, c->nz, c->side, 2))) break;
+            if ((rc = launch_volume_fused(c, 1, 0, c->nz, slab_stream(c), 2))) break;
+            if ((rc = launch_he(c, c->stream))) break;
+            c->ccur ^= 1;                                                    // pointers of the launches below: H is new
+            if ((rc = launch_volume_xslabs(c, 0, 0, c->nz, c->side, 1))) break;
+            if ((rc = launch_volume_fused(c, 0, 0, c->nz, slab_stream(c), 1))) break;
+            if ((rc = join_side(c))) break;
+            if ((rc = fork_side(c))) break;
+            if ((rc = launch_volume_xslabs(c, 0, 0, c->nz, c->side, 2))) break;
+            if ((rc = launch_volume_fused(c, 0, 0, c->nz, slab_stream(c), 2))) break;
+            if ((rc = join_side(c))) break;
+            c->vcur ^= 1;
+            break;
+        }
         if (side) { if ((rc = fork_side(c))) break; }
         if ((rc = launch_volume_xslabs(c, 1, 0, c->nz, side ? c->side : c->stream))) break;
         if ((rc = launch_volume_fused(c, 1, 0, c->nz, side ? slab_stream(c) : c->stream))) break;
