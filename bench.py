@@ -28,9 +28,11 @@ for _p in (ROOT, PKG):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
-# stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION in some images) out of it
-if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-    os.environ["NCCL_DEBUG"] = "WARN"
+# stdout carries exactly one JSON line: NCCL's own log lines (e.g. the version banner some images switch on through
+# NCCL_DEBUG) go to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+    os.environ.pop("NCCL_DEBUG")
 
 import numpy as np  # noqa: E402
 
