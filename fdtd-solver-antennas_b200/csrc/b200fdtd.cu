@@ -350,11 +350,11 @@ __global__ void __launch_bounds__(32 * TY, MODE ? (16 / TY > 0 ? 16 / TY : 1) : 
     const bool hi_slab = MODE == 2 && (blockIdx.x == 1 || r.xw0 == 0);
     const int xw = hi_slab ? r.xw1 : r.xw0, xx0 = hi_slab ? r.xx1 : 0;
     if (MODE == 2) {
-        const int xs = hi_slab ? r.xs1 : r.xs0;             // float4 slots per row (power of two), 32/xs rows per warp
-        const int c4 = lane & (xs - 1);
-        j = r.j0 + (blockIdx.y * TY + threadIdx.y) * (32 / xs) + lane / xs;
+        const int xs = hi_slab ? r.xs1 : r.xs0;             // float4 slots per row, 32/xs rows per warp (12 columns: 10 rows, 2 idle lanes)
+        const int c4 = lane % xs, rw = lane / xs;
+        j = r.j0 + (blockIdx.y * TY + threadIdx.y) * (32 / xs) + rw;
         i0 = xx0 + c4 * 4;
-        if (j >= r.j1 || c4 * 4 >= xw) return;              // per lane (no warp collectives in this mode)
+        if (rw >= 32 / xs || j >= r.j1 || c4 * 4 >= xw) return;   // per lane (no warp collectives in this mode)
         act = true;
     } else {
         i0 = (blockIdx.x * 32 + lane) * 4;
@@ -472,11 +472,11 @@ __global__ void __launch_bounds__(32 * TY, MODE ? (16 / TY > 0 ? 16 / TY : 1) : 
     const bool hi_slab = MODE == 2 && (blockIdx.x == 1 || r.xw0 == 0);
     const int xw = hi_slab ? r.xw1 : r.xw0, xx0 = hi_slab ? r.xx1 : 0;
     if (MODE == 2) {
-        const int xs = hi_slab ? r.xs1 : r.xs0;             // float4 slots per row (power of two), 32/xs rows per warp
-        const int c4 = lane & (xs - 1);
-        j = r.j0 + (blockIdx.y * TY + threadIdx.y) * (32 / xs) + lane / xs;
+        const int xs = hi_slab ? r.xs1 : r.xs0;             // float4 slots per row, 32/xs rows per warp (12 columns: 10 rows, 2 idle lanes)
+        const int c4 = lane % xs, rw = lane / xs;
+        j = r.j0 + (blockIdx.y * TY + threadIdx.y) * (32 / xs) + rw;
         i0 = xx0 + c4 * 4;
-        if (j >= r.j1 || c4 * 4 >= xw) return;              // per lane (no warp collectives in this mode)
+        if (rw >= 32 / xs || j >= r.j1 || c4 * 4 >= xw) return;   // per lane (no warp collectives in this mode)
         act = true;
     } else {
         i0 = (blockIdx.x * 32 + lane) * 4;
@@ -1465,7 +1465,7 @@ static int launch_volume_plain(b200fdtd_ctx* c, int which, int k0, int k1, cudaS
 }
 
 static int slab_ty(const b200fdtd_ctx* c) { const int t = (c->variant >> 8) & 31; return t ? t : c->ty; }
-static int slots_for(int w) { int s = 1; while (s * 4 < w) s *= 2; return s; }
+static int slots_for(int w) { return (w + 3) / 4; }
 
 // planes marched per CTA of a thin slab launch: enough CTAs to fill the machine several times over (the march is a
 // serial chain of DRAM round trips, so small launches need their parallelism from the grid), chunks of equal length
