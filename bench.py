@@ -305,7 +305,7 @@ def run_b200(args):
     peak, peak_src = measured_peak()
     if fused_he:
         k_ms, bytes_per_cell_launch = kms[0], BYTES_PER_CELL_STEP
-        kname = "update_he3_kernel<7> fused H->E launch over the plain region (one launch = both passes)"
+        kname = "update_he5_kernel<7> fused H->E launch over the plain region (one launch = both passes)"
         kernel_ms = {"HE": round(kms[0], 4)}
     else:
         k_ms, bytes_per_cell_launch = 0.5 * (kms[0] + kms[1]), BYTES_PER_CELL_PASS

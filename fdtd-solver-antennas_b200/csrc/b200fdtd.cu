@@ -1331,6 +1331,196 @@ __global__ void __launch_bounds__(32 * (TY + 1), 16 / (TY + 1)) update_he4_kerne
 }
 
 
+
+// ---- update_he3_kernel with the planes staged by the TMA engine (cp.async.bulk + mbarrier) ----
+// The row segments a CTA stages are contiguous in global memory (33 float4 of E, 32 of H per row and component), so one
+// elected lane per warp hands them to the TMA engine as 1-D bulk copies that complete on an mbarrier; the 256 threads no
+// longer spend ~25 instructions each per plane on LDGSTS and their addresses.  Out-of-grid parts of the ring are zeroed
+// once at the start and never written again (a bulk copy only covers the in-grid part of its row).
+// full[b]: completion of the copies issued during iteration t (consumed in iteration t+1), b = (t+1) & 1.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}"
+        :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, unsigned bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(smem)), "l"(gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int TY>
+struct He5Smem {
+    float4 es[3][3][TY + 2][33];
+    float4 hs[2][3][TY + 1][32];
+    float4 xb[2][TY + 1][2][32];
+    float4 ms[2][TY + 1][4];
+    unsigned long long full[2];
+    float4 xs[1];                                            // [nv_h + nv_e][32], sized at launch
+};
+
+template <int TY>
+__global__ void __launch_bounds__(32 * (TY + 1), 16 / (TY + 1)) update_he5_kernel(const HeParams p)
+{
+    extern __shared__ __align__(16) unsigned char he5_raw[];
+    He5Smem<TY>& S = *reinterpret_cast<He5Smem<TY>*>(he5_raw);
+    const int lane = threadIdx.x, r = threadIdx.y;
+    const int i_seg = p.X0 - 4 + HE_SEG * (int)blockIdx.x;  // column of lane 0
+    const int i0 = i_seg + 4 * lane;
+    const int j = p.Y0 - 1 + TY * (int)blockIdx.y + r;
+    const int kbeg = p.Z0 + (int)blockIdx.z * p.kz;
+    const int kend = min(kbeg + p.kz, p.Z1);
+    const bool col_ok = i0 >= 0 && i0 < p.px;
+    {   // x-vector slices; zero the rings (the out-of-grid parts stay zero for the whole launch)
+        for (int v = r; v < p.nv_h + p.nv_e; v += TY + 1) {
+            const float* src = v < p.nv_h ? p.xv_h + (size_t)v * p.px : p.xv_e + (size_t)(v - p.nv_h) * p.px;
+            S.xs[v * 32 + lane] = col_ok ? __ldg(reinterpret_cast<const float4*>(src + i0)) : zero4();
+        }
+        float4* z = &S.es[0][0][0][0];
+        const int nz4 = (int)((sizeof(S.es) + sizeof(S.hs)) / sizeof(float4));
+        for (int q = r * 32 + lane; q < nz4; q += 32 * (TY + 1)) z[q] = zero4();
+        if (r == 0 && lane == 0) { mbar_init(&S.full[0], TY + 1); mbar_init(&S.full[1], TY + 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the zeros are ordered before the TMA writes
+    }
+    __syncthreads();
+    const float4* xsh = S.xs + lane;
+    const float4* xse = S.xs + p.nv_h * 32 + lane;
+    const bool in_grid = col_ok && j >= 0 && j < p.Y1;
+    const bool reg_x = (i0 >= p.X0 && i0 < p.X1) || i0 >= p.XT0;
+    const bool ext = in_grid && (!reg_x || j < p.Y0);
+    const bool calc = in_grid && !ext;
+    const bool own = calc && lane >= 1 && r >= 1;
+    const bool row_ok = j >= 0 && j < p.Y1;
+    // warp-uniform staging plan: in-grid float4 range [c_lo, c_hi) of the 33-wide E row segment (32-wide for H)
+    const int c_lo = i_seg < 0 ? (-i_seg + 3) / 4 : 0;
+    const int c_hi_e = min(33, (p.px - i_seg) / 4), c_hi_h = min(32, (p.px - i_seg) / 4);
+    const bool e_row = j >= 0 && j < p.ny && j <= p.Y1 && c_hi_e > c_lo;         // this warp's own row of E
+    const bool e_top = r == TY && j + 1 >= 0 && j + 1 < p.ny && j + 1 <= p.Y1 && c_hi_e > c_lo;   // +1 row (top warp)
+    const bool h_row = j >= p.Y0 && j < p.Y1 && c_hi_h > c_lo;                    // H_old where H_new is computed (j >= Y0 >= 0)
+    const unsigned nb_e = (unsigned)(c_hi_e - c_lo) * 16u, nb_h = (unsigned)(c_hi_h - c_lo) * 16u;
+    const int kfirst = kbeg > p.Z0 ? kbeg - 1 : kbeg;
+    const long long base0 = (long long)(kfirst + 1) * p.sz + (long long)j * p.px + i0;
+    const long long mrow0 = ((long long)(kfirst + 1) * p.ny + j) * 32;
+    const char* pe = reinterpret_cast<const char*>(p.ein + base0);
+    const char* ph = reinterpret_cast<const char*>(p.hin + base0);
+    char* qe = reinterpret_cast<char*>(p.eout + base0);
+    char* qh = reinterpret_cast<char*>(p.hout + base0);
+    // lane 0's view: start of the in-grid part of this warp's row segment in plane k
+    const long long seg0 = (long long)(kfirst + 1) * p.sz + (long long)j * p.px + i_seg + 4 * c_lo;
+    const char* ge = reinterpret_cast<const char*>(p.ein + seg0);
+    const char* gh = reinterpret_cast<const char*>(p.hin + seg0);
+    const char* mrec = (lane < 2 ? reinterpret_cast<const char*>(p.meta_h) : reinterpret_cast<const char*>(p.meta_e)) + mrow0 + (lane & 1) * 16;
+    const char* safe = reinterpret_cast<const char*>(p.ein);
+
+    // lane 0 of every warp: hand the warp's rows of E_old(plane k + de) and H_old(plane k + dh) to the TMA engine
+    auto stage = [&](unsigned long long* bar, int se, bool with_e, long long de, int se_b, bool with_e2, long long de2,
+                     int shs, bool with_h, long long dh) {
+        if (lane != 0) return;
+        unsigned bytes = 0;
+        if (with_e) bytes += (e_row ? 3u * nb_e : 0u) + (e_top ? 2u * nb_e : 0u);
+        if (with_e2) bytes += (e_row ? 3u * nb_e : 0u) + (e_top ? 2u * nb_e : 0u);
+        if (with_h && h_row) bytes += 3u * nb_h;
+        mbar_arrive_expect(bar, bytes);
+        auto rows_e = [&](int slot, long long d) {
+            if (e_row) {
+                bulk_g2s(&S.es[slot][0][r][c_lo], ge + d, nb_e, bar);
+                bulk_g2s(&S.es[slot][1][r][c_lo], ge + d + p.b_cs, nb_e, bar);
+                bulk_g2s(&S.es[slot][2][r][c_lo], ge + d + p.b_2cs, nb_e, bar);
+            }
+            if (e_top) {
+                bulk_g2s(&S.es[slot][0][TY + 1][c_lo], ge + d + p.b_row, nb_e, bar);
+                bulk_g2s(&S.es[slot][2][TY + 1][c_lo], ge + d + p.b_row_2cs, nb_e, bar);
+            }
+        };
+        if (with_e) rows_e(se, de);
+        if (with_e2) rows_e(se_b, de2);
+        if (with_h && h_row) {
+            bulk_g2s(&S.hs[shs][0][r][c_lo], gh + dh, nb_h, bar);
+            bulk_g2s(&S.hs[shs][1][r][c_lo], gh + dh + p.b_cs, nb_h, bar);
+            bulk_g2s(&S.hs[shs][2][r][c_lo], gh + dh + p.b_2cs, nb_h, bar);
+        }
+    };
+
+    int se = 0, sh = 0;
+    stage(&S.full[0], 0, true, 0, 1, true, p.b_sz, 0, true, 0);              // planes kfirst, kfirst+1 of E, kfirst of H
+    if (lane < 4) cp_async16(&S.ms[0][r][lane], row_ok ? mrec : safe, row_ok);
+    cp_async_commit();
+    float4 hx_km = zero4(), hy_km = zero4();
+    if (kfirst == kbeg && own) { hx_km = ldb4(qh - p.b_sz); hy_km = ldb4(qh - p.b_sz + p.b_cs); }
+    cp_async_wait<0>();
+    __syncwarp();
+
+    for (int k = kfirst; k < kend; ++k, pe += p.b_sz, ph += p.b_sz, qe += p.b_sz, qh += p.b_sz, ge += p.b_sz, gh += p.b_sz, mrec += p.meta_step) {
+        const bool pro = k < kbeg;
+        const int t = k - kfirst;
+        const int se1 = se == 2 ? 0 : se + 1, se2 = se1 == 2 ? 0 : se1 + 1, mb = t & 1;
+        // next iteration's new data: E(k+2) -> slot se2, H_old(k+1) -> slot sh^1 (every warp arrives, with or without bytes)
+        stage(&S.full[(t + 1) & 1], se2, k + 1 < kend, 2 * p.b_sz, 0, false, 0, sh ^ 1, k + 1 < kend, p.b_sz);
+        if (k + 1 < kend && lane < 4) cp_async16(&S.ms[mb ^ 1][r][lane], row_ok ? mrec + p.meta_step : safe, row_ok);
+        cp_async_commit();
+        mbar_wait(&S.full[t & 1], (unsigned)(t >> 1) & 1u);  // this plane's staged rows have landed (all warps' copies)
+        float4 hx = zero4(), hy = zero4(), hz = zero4();
+        float4 ax = zero4(), ay = zero4(), az = zero4(), bx = zero4(), by = zero4(), bz = zero4();
+        const float4 ex = S.es[se][0][r][lane], ey = S.es[se][1][r][lane], ez = S.es[se][2][r][lane];
+        if (calc) {
+            hx = S.hs[sh][0][r][lane]; hy = S.hs[sh][1][r][lane]; hz = S.hs[sh][2][r][lane];
+            row_coefs(S.ms[mb][r][0], S.ms[mb][r][1], xsh, p.ii, p.iv, p.xv_h,
+                      (long long)((ph - reinterpret_cast<const char*>(p.hin)) >> 2), p.cs, i0, p.px, ax, ay, az, bx, by, bz);
+        } else if (ext) {
+            hx = ldb4(qh); hy = ldb4(qh + p.b_cs); hz = ldb4(qh + p.b_2cs);
+        }
+        float ez_r = __shfl_down_sync(0xffffffffu, ez.x, 1);
+        float ey_r = __shfl_down_sync(0xffffffffu, ey.x, 1);
+        if (lane == 31) { ez_r = S.es[se][2][r][32].x; ey_r = S.es[se][1][r][32].x; }
+        if (calc) {
+            const float4 ex1 = S.es[se1][0][r][lane], ey1 = S.es[se1][1][r][lane];
+            const float4 ex_jp = S.es[se][0][r + 1][lane], ez_jp = S.es[se][2][r + 1][lane];
+            const float4 ez_ip = make_float4(ez.y, ez.z, ez.w, ez_r);
+            const float4 ey_ip = make_float4(ey.y, ey.z, ey.w, ey_r);
+            hx = upd4(ax, hx, bx, ez, ez_jp, ey, ey1);
+            hy = upd4(ay, hy, by, ex, ex1, ez, ez_ip);
+            hz = upd4(az, hz, bz, ey, ey_ip, ex, ex_jp);
+        }
+        if (own && !pro) {
+            stb4(qh, hx); stb4(qh + p.b_cs, hy); stb4(qh + p.b_2cs, hz);
+            row_coefs(S.ms[mb][r][2], S.ms[mb][r][3], xse, p.vv, p.vi, p.xv_e,
+                      (long long)((pe - reinterpret_cast<const char*>(p.ein)) >> 2), p.cs, i0, p.px, ax, ay, az, bx, by, bz);
+        }
+        S.xb[mb][r][0][lane] = hz; S.xb[mb][r][1][lane] = hx;
+        cp_async_wait<0>();                                  // next plane's records (this warp's own copies)
+        __syncthreads();                                     // H_new rows visible; everybody is done with slots se2 / sh^1's old planes
+        const float hz_l = __shfl_up_sync(0xffffffffu, hz.w, 1);
+        const float hy_l = __shfl_up_sync(0xffffffffu, hy.w, 1);
+        if (own && !pro) {
+            const float4 hz_jm = S.xb[mb][r - 1][0][lane], hx_jm = S.xb[mb][r - 1][1][lane];
+            const float4 hz_im = make_float4(hz_l, hz.x, hz.y, hz.z);
+            const float4 hy_im = make_float4(hy_l, hy.x, hy.y, hy.z);
+            const float4 exn = upd4(ax, ex, bx, hz, hz_jm, hy, hy_km);
+            const float4 eyn = upd4(ay, ey, by, hx, hx_km, hz, hz_im);
+            const float4 ezn = upd4(az, ez, bz, hy, hy_im, hx, hx_jm);
+            stb4(qe, exn); stb4(qe + p.b_cs, eyn); stb4(qe + p.b_2cs, ezn);
+        }
+        hx_km = hx; hy_km = hy;
+        se = se1; sh ^= 1;
+    }
+}
+
 template <int MODE>
 static int launch_volume_one(b200fdtd_ctx* c, int which, int k0, int k1, const RowParams& r, cudaStream_t stream, int kz, int nchunks, int grid_y = 0)
 {
@@ -1592,6 +1782,9 @@ static int launch_he(b200fdtd_ctx* c, cudaStream_t stream, int zc0 = -1, int zc1
         if (v3 && (c->variant & (1 << 19)) != 0 && sizeof(He4Smem<TYV>) + xs_bytes <= 220 * 1024) { const size_t sm4 = sizeof(He4Smem<TYV>) + xs_bytes; \
                   CK(cudaFuncSetAttribute(update_he4_kernel<TYV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4)); \
                   update_he4_kernel<TYV><<<grid, block, sm4, stream>>>(p); } \
+        else if (v3 && (c->variant & (1 << 21)) == 0 && sizeof(He5Smem<TYV>) + xs_bytes <= 220 * 1024) { const size_t sm5 = sizeof(He5Smem<TYV>) + xs_bytes; \
+                  CK(cudaFuncSetAttribute(update_he5_kernel<TYV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm5)); \
+                  update_he5_kernel<TYV><<<grid, block, sm5, stream>>>(p); } \
         else if (v3 && sizeof(He3Smem<TYV>) + xs_bytes <= 220 * 1024) { const size_t sm3 = sizeof(He3Smem<TYV>) + xs_bytes; \
                   CK(cudaFuncSetAttribute(update_he3_kernel<TYV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3)); \
                   update_he3_kernel<TYV><<<grid, block, sm3, stream>>>(p); } \
@@ -1930,6 +2123,9 @@ static void drop_graph(b200fdtd_ctx* c) { if (c->graph) { cudaGraphExecDestroy(c
 // ------------------------------------------------------------------------------------
 // C-ABI
 // ------------------------------------------------------------------------------------
+// experiment switches for a whole test run: B200FDTD_VARIANT_OR is OR-ed into every variant word
+static int env_variant_or() { static const int v = [] { const char* e = getenv("B200FDTD_VARIANT_OR"); return e ? atoi(e) : 0; }(); return v; }
+
 extern "C" int b200fdtd_create(b200fdtd_ctx** out, int device, int nx, int ny, int nz, int px, void* stream)
 {
     if (!out) return fail("out is NULL");
@@ -1956,6 +2152,7 @@ extern "C" int b200fdtd_create(b200fdtd_ctx** out, int device, int nx, int ny, i
     CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     CK(cudaMalloc((void**)&c->d_ts, sizeof(int)));
     CK(cudaMemsetAsync(c->d_ts, 0, sizeof(int), c->stream));
+    c->variant = env_variant_or();
     if (const char* e = getenv("B200FDTD_HE_TY")) { const int t = atoi(e); if (t == 3 || t == 7 || t == 15) c->he_ty = t; }
     if (const char* e = getenv("B200FDTD_HE_KZ")) { const int t = atoi(e); if (t >= 1) c->he_kz = t; }
     c->n_partials = 148 * 8;
@@ -2015,7 +2212,7 @@ extern "C" int b200fdtd_set_tuning(b200fdtd_ctx* c, int kz, int ty, int variant)
     if (kz < 1) return fail("kz must be >= 1");
     if (!(ty == 1 || ty == 2 || ty == 4 || ty == 8 || ty == 16)) return fail("ty must be 1,2,4,8 or 16");
     { const int t = (variant >> 8) & 31; if (!(t == 0 || t == 1 || t == 2 || t == 4 || t == 8 || t == 16)) return fail("slab ty (variant bits 8-12) must be 0,1,2,4,8 or 16"); }
-    c->kz = kz; c->ty = ty; c->variant = variant; drop_graph(c);
+    c->kz = kz; c->ty = ty; c->variant = variant | env_variant_or(); drop_graph(c);
     c->side = (variant & 32) ? c->side_hi : c->side_lo;
     c->plan.valid = false;
     return 0;

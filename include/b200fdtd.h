@@ -73,7 +73,8 @@ int b200fdtd_expand_rows(b200fdtd_ctx* ctx, int which, int nvec, const float* xv
  * 32 = slab side stream at highest priority, 64 = one side stream for all slab launches, 128 = no fused H->E launches,
  * bits 8-12 = rows per CTA of the slab launches (0 = ty), bits 16-17 = prefetch distance of the register-march fused
  * kernels (0 = default 1, 3 = off), 256 / 512 / bit 18 = older generations of the fused H->E kernel (experiments:
- * cp.async ring v1 / plain fusion / register march v2 instead of the staged v3), bit 19 = barrier-free v4,
+ * cp.async ring v1 / plain fusion / register march v2 instead of the staged v3), bit 19 = barrier-free v4, bit 21 = per-thread cp.async staging (v3)
+ * instead of TMA bulk copies (v5, default),
  * bit 20 = high-end H / low-end E slab launches beside the fused launch instead of before / after it */
 int b200fdtd_set_tuning(b200fdtd_ctx* ctx, int kz, int ty, int variant);
 

@@ -187,12 +187,26 @@ def test_fused_h_to_e_launches_bit_exact(shape, layout, interval, tile):
     _assert_fields_equal(R, G, "unfused chunk after fused chunks")
 
 
-def test_fused_h_to_e_with_row_compression():
-    P = synth.make_problem(37, 29, 23, 40, seed=9, fused_pml=True, compress=True, interval=4)
+@pytest.mark.parametrize("shape", [(37, 29, 23, 40), (261, 21, 14, 288), (130, 12, 9, 160)])
+@pytest.mark.parametrize("layout", ["slabs", "mur"])
+@pytest.mark.parametrize("interval,tile,variant", [(4, (7, 32), 0), (3, (3, 2), 0), (5, (15, 5), 0), (2, (5, 1), 0),
+                                                   (4, (7, 32), 1 << 18), (3, (7, 4), 1 << 19), (4, (7, 3), 1 << 21),
+                                                   (3, (7, 32), 256), (4, (7, 32), 512), (5, (7, 32), 1 << 20)])
+def test_fused_h_to_e_with_row_compression(shape, layout, interval, tile, variant):
+    """the compressed-operator generations of the fused launch (default: planes staged by TMA bulk copies; bit 21 by
+    per-thread cp.async, bit 18 register march, bit 19 barrier-free, 256/512 the first two versions, bit 20 the overlapped
+    slab schedule) on
+    one and several x-segments, with rows whose compression claims are false (demoted on the device)"""
+    nx, ny, nz, px = shape
+    P = synth.make_problem(nx, ny, nz, px, seed=9 + nx, with_pml=layout == "slabs", fused_pml=layout == "slabs",
+                           compress=True, interval=interval, with_nf2ff=False)
     R, G = _engines(P)
-    R.run(13); G.run(13, use_graph=True)
+    G.set_tuning(variant=variant)
+    G.set_he_tuning(*tile)
+    n = 2 * interval + 1
+    R.run(n); G.run(n, use_graph=True)
     assert G.he_active
-    _assert_fields_equal(R, G, "fused H->E with row compression")
+    _assert_fields_equal(R, G, f"fused H->E with row compression, variant {variant}")
 
 
 @pytest.mark.parametrize("layout", ["slabs", "mur"])

@@ -11,7 +11,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__byte
     --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_launches_$TAG.log 2>&1
 python tools/summarize_launches.py gpurun_out/launches_$TAG.csv
 # the dominant kernel (fused H->E launch over the plain region) and one launch of each slab kind
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:update_he2_kernel -s 2 -c 1 -f -o gpurun_out/prof_he2_$TAG $CMD > gpurun_out/ncu_he2_$TAG.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:update_he5_kernel -s 2 -c 1 -f -o gpurun_out/prof_he5_$TAG $CMD > gpurun_out/ncu_he5_$TAG.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"update_[eh]_kernel<\(int\)4, \(int\)[12]" -s 10 -c 5 -f \
     -o gpurun_out/prof_slabs_$TAG $CMD > gpurun_out/ncu_slabs_$TAG.log 2>&1
 ls -la gpurun_out | grep -E "ncu-rep|csv"
