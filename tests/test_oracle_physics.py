@@ -90,3 +90,72 @@ def test_running_dft_matches_host_dft_of_the_series():
         host = dft_time2freq(pr["t"], pr["val"], pf)
         dev = 2.0 * (pr["t"][1] - pr["t"][0]) * pr["dft"]
         assert np.abs(host - dev).max() < 1e-9 * np.abs(host).max()
+
+
+def _layered_cavity_tm_modes(a, b, c, d, eps_r, fmax, mn=((1, 1), (2, 1), (1, 2), (2, 2), (3, 1))):
+    """TM-to-z resonances of a PEC box a x b x c whose lower part 0 <= z <= d is filled with eps_r (closed form):
+    psi continuous and (1/eps) dpsi/dz continuous at z = d give
+        (kz1/eps_r) tan(kz1 d) + kz2 tan(kz2 (c - d)) = 0,   kz1^2 = eps_r k0^2 - kt^2,  kz2^2 = k0^2 - kt^2"""
+    from scipy.optimize import brentq
+
+    def g(f, kt2):
+        k0 = 2 * np.pi * f / C0
+        out = 0.0
+        for eps, t in ((eps_r, d), (1.0, c - d)):
+            q = eps * k0 * k0 - kt2
+            if q >= 0:
+                kz = np.sqrt(q)
+                out += kz / eps * np.tan(kz * t)
+            else:
+                al = np.sqrt(-q)
+                out += -al / eps * np.tanh(al * t)
+        return out
+
+    roots = []
+    for m, n in mn:
+        kt2 = (m * np.pi / a) ** 2 + (n * np.pi / b) ** 2
+        fs = np.linspace(0.2e9, fmax, 6000)
+        v = np.array([g(f, kt2) for f in fs])
+        for i in range(len(fs) - 1):
+            if np.isfinite(v[i]) and np.isfinite(v[i + 1]) and v[i] * v[i + 1] < 0 and abs(v[i]) + abs(v[i + 1]) < 50 * (abs(v).min() + 1.0):
+                r = brentq(g, fs[i], fs[i + 1], args=(kt2,))
+                if abs(g(r, kt2)) < 1e-3 * (1 + np.sqrt(kt2)):           # a root, not a pole of tan
+                    roots.append(r)
+    return sorted(roots)
+
+
+def test_partially_filled_cavity_resonances():
+    """dielectric slab + air in one PEC box: pins the operator build at a material interface (permittivity averaging of
+    the tangential edges in the interface plane, full permittivity of the normal edges below it) against the closed form"""
+    from CSXCAD import ContinuousStructure
+    from openEMS import openEMS
+    a, b, c, d, eps_r = 0.06, 0.05, 0.03, 0.01, 4.3
+    n = (31, 26, 31)                                     # 2 mm x 2 mm x 1 mm cells, 10 cells in the slab
+    F = openEMS(NrTS=9000, EndCriteria=1e-12)
+    F.SetGaussExcite(4e9, 2.5e9)
+    F.SetBoundaryCond(["PEC"] * 6)
+    csx = ContinuousStructure(); F.SetCSX(csx)
+    g = csx.GetGrid(); g.SetDeltaUnit(1.0)
+    lines = [np.linspace(0, L, m) for L, m in zip((a, b, c), n)]
+    for ax, l in enumerate(lines):
+        g.AddLine("xyz"[ax], l)
+    csx.AddMaterial("slab", epsilon=eps_r).AddBox([0, 0, 0], [a, b, d])
+    x, y, z = lines
+    ex = csx.AddExcitation("src", 0, [0, 0, 1])
+    ex.AddBox([x[7], y[6], z[2]], [x[7], y[6], z[6]])    # z-directed source inside the slab: TM-to-z modes only
+    pr = csx.AddProbe("ut_cav", 0)
+    pr.AddBox([x[19], y[15], z[3]], [x[19], y[15], z[8]])
+    F.Run(scenes.tmp_sim_path("layered"), cleanup=True)
+    rec = F.results["probes"]["ut_cav"]
+    f = np.linspace(1.5e9, 6.5e9, 5001)
+    fp, sp = _peak_freqs(rec["t"], rec["val"], f)
+    expected = _layered_cavity_tm_modes(a, b, c, d, eps_r, 7e9)
+    assert len(expected) >= 4 and len(fp) >= 3
+    # every strong peak is a TM-to-z mode of the layered box, and the lowest one is found
+    for fpk in fp[:5]:
+        rel = min(abs(fpk - fe) / fe for fe in expected)
+        assert rel < 8e-3, f"peak {fpk / 1e9:.4f} GHz matches no layered-cavity mode (rel {rel:.4f}); expected {np.round(np.array(expected[:8]) / 1e9, 4)}"
+    assert abs(fp[0] - expected[0]) / expected[0] < 6e-3
+    # the same box filled uniformly (eps_r everywhere / air everywhere) would put the lowest mode elsewhere by > 10 %
+    f_air = C0 / 2 * np.sqrt(1 / a ** 2 + 1 / b ** 2)
+    assert abs(expected[0] - f_air) / f_air > 0.1 and abs(expected[0] - f_air / np.sqrt(eps_r)) / expected[0] > 0.1
