@@ -159,3 +159,39 @@ def test_partially_filled_cavity_resonances():
     # the same box filled uniformly (eps_r everywhere / air everywhere) would put the lowest mode elsewhere by > 10 %
     f_air = C0 / 2 * np.sqrt(1 / a ** 2 + 1 / b ** 2)
     assert abs(expected[0] - f_air) / f_air > 0.1 and abs(expected[0] - f_air / np.sqrt(eps_r)) / expected[0] > 0.1
+
+
+def test_lossy_fill_decay_rate():
+    """a PEC box filled with a conductive dielectric loses energy as exp(-sigma t / eps) whatever the modal content:
+    pins the conductivity terms of the operator (vv = (1 - s)/(1 + s), vi ~ 1/(1 + s), s = sigma dt / 2 eps; the reference
+    scene turns tan(delta) into such a kappa, antenna_sim/solver_fdtd_openems_microstrip_3d.py:111)"""
+    from CSXCAD import ContinuousStructure
+    from openEMS import openEMS
+    from b200fdtd.constants import EPS0
+    a, b, c, eps_r, kappa = 0.05, 0.04, 0.03, 4.3, 0.05
+    F = openEMS(NrTS=5000, EndCriteria=1e-30)
+    F.SetGaussExcite(2.5e9, 1.5e9)
+    F.SetBoundaryCond(["PEC"] * 6)
+    csx = ContinuousStructure(); F.SetCSX(csx)
+    g = csx.GetGrid(); g.SetDeltaUnit(1.0)
+    lines = [np.linspace(0, L, m) for L, m in zip((a, b, c), (21, 17, 13))]
+    for ax, l in enumerate(lines):
+        g.AddLine("xyz"[ax], l)
+    csx.AddMaterial("fill", epsilon=eps_r, kappa=kappa).AddBox([0, 0, 0], [a, b, c])
+    x, y, z = lines
+    csx.AddExcitation("src", 0, [0, 0, 1]).AddBox([x[6], y[5], z[3]], [x[6], y[5], z[5]])
+    csx.AddProbe("ut_cav", 0).AddBox([x[13], y[10], z[6]], [x[13], y[10], z[8]])
+    F.Run(scenes.tmp_sim_path("lossy"), cleanup=True)
+    rec = F.results["probes"]["ut_cav"]
+    t, v = np.asarray(rec["t"]), np.asarray(rec["val"])
+    t_free = 2.2 * 9.0 / (2 * np.pi * 1.5e9)                    # the Gaussian pulse is over (2 t0, SURVEY.md §8 a8)
+    sel = t > t_free
+    t, v = t[sel], v[sel]
+    nwin = 12
+    edges = np.linspace(0, len(t), nwin + 1).astype(int)
+    tc = np.array([t[edges[i]:edges[i + 1]].mean() for i in range(nwin)])
+    p = np.array([np.mean(v[edges[i]:edges[i + 1]] ** 2) for i in range(nwin)])
+    assert p[-1] > 0 and p[0] / p[-1] > 1e3, "no measurable decay"
+    slope = np.polyfit(tc, np.log(p), 1)[0]
+    expected = -kappa / (eps_r * EPS0)
+    assert abs(slope - expected) / abs(expected) < 0.03, (slope, expected)
