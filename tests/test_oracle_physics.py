@@ -195,3 +195,43 @@ def test_lossy_fill_decay_rate():
     slope = np.polyfit(tc, np.log(p), 1)[0]
     expected = -kappa / (eps_r * EPS0)
     assert abs(slope - expected) / abs(expected) < 0.03, (slope, expected)
+
+
+def test_graded_mesh_cavity_resonances():
+    """the same PEC box on a strongly graded mesh (neighbour ratio up to 1.4, what SmoothMeshLines allows): pins the edge /
+    dual-edge lengths and areas of the operator build on non-uniform lines, which every reference scene uses"""
+    from CSXCAD import ContinuousStructure
+    from openEMS import openEMS
+    a, b, c = 0.05, 0.04, 0.03
+
+    def graded(L, n, ratio=1.4):
+        w = np.array([ratio ** (2 - abs(i % 4 - 2)) for i in range(n)], float)     # cell sizes 1, 1.4, 1.96, 1.4, 1, ... (triangle wave)
+        return np.concatenate([[0.0], np.cumsum(w)]) * (L / w.sum())
+
+    lines = [graded(a, 24), graded(b, 20), graded(c, 14)]
+    for l in lines:
+        r = np.diff(l)[1:] / np.diff(l)[:-1]
+        assert r.max() <= 1.4001 and r.min() >= 1 / 1.4001 and (np.abs(r - 1) > 0.3).any()
+    F = openEMS(NrTS=9000, EndCriteria=1e-12)
+    F.SetGaussExcite(5e9, 3e9)
+    F.SetBoundaryCond(["PEC"] * 6)
+    csx = ContinuousStructure(); F.SetCSX(csx)
+    g = csx.GetGrid(); g.SetDeltaUnit(1.0)
+    for ax, l in enumerate(lines):
+        g.AddLine("xyz"[ax], l)
+    x, y, z = lines
+    csx.AddExcitation("src", 0, [0, 0, 1]).AddBox([x[7], y[6], z[4]], [x[7], y[6], z[6]])
+    csx.AddProbe("ut_cav", 0).AddBox([x[15], y[12], z[6]], [x[15], y[12], z[9]])
+    F.Run(scenes.tmp_sim_path("graded"), cleanup=True)
+    rec = F.results["probes"]["ut_cav"]
+    f = np.linspace(3e9, 9e9, 3001)
+    fp, sp = _peak_freqs(rec["t"], rec["val"], f)
+
+    def fm(m, n, p):
+        return C0 / 2 * np.sqrt((m / a) ** 2 + (n / b) ** 2 + (p / c) ** 2)
+    expected = sorted(fm(m, n, p) for m in range(1, 4) for n in range(1, 4) for p in range(0, 3))
+    assert len(fp) >= 3
+    for fpk in fp[:4]:
+        rel = min(abs(fpk - fe) / fe for fe in expected)
+        assert rel < 8e-3, f"peak {fpk / 1e9:.4f} GHz matches no cavity mode (rel {rel:.4f})"
+    assert abs(fp[0] - fm(1, 1, 0)) / fm(1, 1, 0) < 5e-3
