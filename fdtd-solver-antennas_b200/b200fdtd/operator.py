@@ -13,6 +13,7 @@ The arithmetic is float64 torch (CPU or CUDA tensor ops), stored as float32 like
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -450,9 +451,15 @@ class OperatorBuilder:
         return m
 
     def _rates(self, comp, rng, ec, field_kind):
-        """PML rates r_a = g_a(position) * c_local for a = comp, nP, nPP at the positions of E (0) or H (1) comp"""
+        """PML rates r_a = g_a(position) * c0 for a = comp, nP, nPP at the positions of E (0) or H (1) comp.
+        The stretching of a coordinate is a property of the coordinate, not of the material it runs through: with the
+        local phase velocity instead of c0 the stretch factor jumps at a material interface that enters the PML (a
+        substrate under a microstrip line) and the layer goes unstable (tests/test_oracle_physics.py::
+        test_microstrip_line_impedance_and_effective_permittivity blows up within 4000 steps).  In vacuum, i.e. in every
+        reference scene (substrate and ground plane end inside the domain), both choices are the same number.
+        B200FDTD_PML_LOCAL_C=1 restores the material-dependent rates for comparison."""
         eps = ec["epsE"][comp] if field_kind == 0 else ec["epsH"][comp]
-        c_loc = C0 / torch.sqrt(eps)
+        c_loc = C0 / torch.sqrt(eps) if os.environ.get("B200FDTD_PML_LOCAL_C") else torch.full_like(eps, C0)
         r = {}
         for a in range(3):
             on_mid = (a == comp) if field_kind == 0 else (a != comp)

@@ -235,3 +235,44 @@ def test_graded_mesh_cavity_resonances():
         rel = min(abs(fpk - fe) / fe for fe in expected)
         assert rel < 8e-3, f"peak {fpk / 1e9:.4f} GHz matches no cavity mode (rel {rel:.4f})"
     assert abs(fp[0] - fm(1, 1, 0)) / fm(1, 1, 0) < 5e-3
+
+
+def test_microstrip_line_impedance_and_effective_permittivity():
+    """50-ohm microstrip of the reference's own design rule (er 4.3, h 1.6 mm, w 3.114 mm from calculate_microstrip_width,
+    antenna_sim/solver_fdtd_openems_microstrip.py:84-112) between a lumped port and a PML: the travelling wave must show
+    Z = U/I near 50 ohm and a phase velocity of c/sqrt(eps_eff) (Hammerstad: 50.2 ohm, eps_eff 3.27).  Pins PEC sheets on
+    a substrate, the lumped port, voltage/current probe geometry and signs, and PML under a dielectric, in one scene."""
+    from CSXCAD import ContinuousStructure
+    from openEMS import openEMS
+    er, h, w = 4.3, 1.6, 3.114396
+    F = openEMS(NrTS=6000, EndCriteria=1e-5)
+    F.SetGaussExcite(2.5e9, 1.5e9)
+    F.SetBoundaryCond(["PML_8", "PML_8", "PML_8", "PML_8", "PEC", "PML_8"])
+    csx = ContinuousStructure(); F.SetCSX(csx)
+    g = csx.GetGrid(); g.SetDeltaUnit(1e-3)
+    dy = w / 6
+    g.AddLine("x", np.arange(-40.0, 40.5, 1.0))
+    g.AddLine("y", np.arange(-24, 25) * dy)
+    g.AddLine("z", [0, 0.4, 0.8, 1.2, 1.6, 2.1, 2.8, 3.8, 5.2, 7.0, 9.0, 11.0, 13.0, 15.0, 17.0, 19.0, 21.0, 23.0])
+    csx.AddMaterial("sub", epsilon=er).AddBox([-40, -24 * dy, 0], [40, 24 * dy, h], priority=0)
+    csx.AddMetal("strip").AddBox([-30, -w / 2, h], [40, w / 2, h], priority=10)
+    F.AddLumpedPort(1, 50.0, [-30, 0, 0], [-30, 0, h], "z", 1.0, priority=5)
+    # voltage strip - ground at two stations (weight -1: U = -int E dl from the ground up), current in +x around the strip
+    for name, xs in (("ut_a", 0.0), ("ut_b", 20.0)):
+        csx.AddProbe(name, 0, weight=-1).AddBox([xs, 0, 0], [xs, 0, h])
+    csx.AddProbe("it_a", 1, norm_dir=0).AddBox([0.5, -w / 2 - 0.3, h - 0.1], [0.5, w / 2 + 0.3, h + 0.1])
+    F.Run(scenes.tmp_sim_path("msl"), cleanup=True)
+    pr = F.results["probes"]
+    f = np.linspace(1.5e9, 3.5e9, 21)
+    U = dft_time2freq(pr["ut_a"]["t"], pr["ut_a"]["val"], f)
+    Ub = dft_time2freq(pr["ut_b"]["t"], pr["ut_b"]["val"], f)
+    I = dft_time2freq(pr["it_a"]["t"], pr["it_a"]["val"], f)
+    Z = U / I
+    # travelling wave towards +x: power U I* flows in +x, impedance real and near the design value over the band
+    assert (np.real(U * np.conj(I)) > 0).all()
+    assert np.abs(np.abs(Z) - 50.2).max() < 0.08 * 50.2, np.round(np.abs(Z), 2)
+    assert np.abs(np.angle(Z)).max() < 0.12                  # half-cell / half-step stagger of U and I only
+    # phase velocity between the two stations 20 mm apart
+    dphi = -np.unwrap(np.angle(Ub / U))
+    eps_eff = (C0 * dphi / (2 * np.pi * f * 20e-3)) ** 2
+    assert np.abs(eps_eff - 3.27).max() < 0.06 * 3.27, np.round(eps_eff, 3)
