@@ -276,3 +276,57 @@ def test_microstrip_line_impedance_and_effective_permittivity():
     dphi = -np.unwrap(np.angle(Ub / U))
     eps_eff = (C0 * dphi / (2 * np.pi * f * 20e-3)) ** 2
     assert np.abs(eps_eff - 3.27).max() < 0.06 * 3.27, np.round(eps_eff, 3)
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_timestep_estimate_is_stable_and_not_wasteful(seed):
+    """dt = 2/sqrt(max(S_x+S_y+S_z)) (operator.py:estimate_timestep) on a random non-uniform mesh (ratio <= 1.4) filled
+    with random dielectric blocks in a lossless PEC box: the field stays bounded over thousands of steps, and a step
+    1.35x larger blows up, so the estimate is neither unsafe nor far from the limit"""
+    from CSXCAD import ContinuousStructure
+    from openEMS import openEMS
+    rng = np.random.default_rng(seed)
+
+    def lines(L, n):
+        w = [1.0]
+        for _ in range(n - 1):
+            w.append(float(np.clip(w[-1] * rng.choice([1 / 1.4, 1.0, 1.4]), 0.4, 2.5)))
+        w = np.array(w)
+        return np.concatenate([[0.0], np.cumsum(w)]) * (L / w.sum())
+
+    def build(factor, nrts):
+        F = openEMS(NrTS=nrts, EndCriteria=1e-30)
+        F.SetGaussExcite(6e9, 4e9)
+        F.SetBoundaryCond(["PEC"] * 6)
+        F.SetTimeStepFactor(factor)
+        csx = ContinuousStructure(); F.SetCSX(csx)
+        g = csx.GetGrid(); g.SetDeltaUnit(1.0)
+        for ax, l in enumerate(ls):
+            g.AddLine("xyz"[ax], l)
+        for q, (lo, hi, er) in enumerate(blocks):
+            csx.AddMaterial(f"m{q}", epsilon=er).AddBox(lo, hi, priority=q)
+        x, y, z = ls
+        csx.AddExcitation("src", 0, [1, 1, 1]).AddBox([x[5], y[4], z[3]], [x[7], y[6], z[5]])
+        csx.AddProbe("ut", 0).AddBox([x[11], y[9], z[4]], [x[11], y[9], z[8]])
+        return F
+
+    ls = [lines(0.04, 18), lines(0.035, 16), lines(0.03, 14)]
+    dims = np.array([0.04, 0.035, 0.03])
+    blocks = []
+    for _ in range(6):
+        lo = rng.uniform(0, 0.6, 3) * dims
+        blocks.append((list(lo), list(lo + rng.uniform(0.2, 0.4, 3) * dims), float(rng.uniform(1.5, 9.0))))
+    F = build(1.0, 6000)
+    F.Run(scenes.tmp_sim_path(f"dt{seed}"), cleanup=True)
+    v = np.asarray(F.results["probes"]["ut"]["val"])
+    n = len(v)
+    early, late = np.abs(v[n // 6:n // 3]).max(), np.abs(v[-n // 6:]).max()
+    assert np.isfinite(v).all() and early > 0 and late < 3.0 * early, (early, late)     # lossless box: rings, does not grow
+    F2 = build(1.35, 3000)
+    try:
+        F2.Run(scenes.tmp_sim_path(f"dt{seed}b"), cleanup=True)
+        v2 = np.asarray(F2.results["probes"]["ut"]["val"])
+        grew = (not np.isfinite(v2).all()) or np.abs(v2[-len(v2) // 6:]).max() > 1e3 * early
+    except FloatingPointError:
+        grew = True
+    assert grew, "a 35 % larger time step is still stable: the estimate wastes time steps"
