@@ -268,12 +268,15 @@ class Simulation:
             self._gpu = self._tv.is_cuda
             self._pend_e, self._pend_h = [], []
             # fused H->E steps (second field copy, C-ABI b200fdtd_fused_step_part): CUDA engine with >= 3 planes per slab
-            self._fused = bool(self._gpu and self.fused_multi and hasattr(E, "fused_step_part") and self.nz >= 3)
+            # (the CPU oracle engine of the tests emulates the protocol so that gloo runs cover this host logic too)
+            self._fused = bool((self._gpu or getattr(E, "emulates_fused_steps", False)) and self.fused_multi
+                               and hasattr(E, "fused_step_part") and self.nz >= 3)
             self._copies_v, self._copies_c = [self._tv], [self._tc]
             if self._fused:
                 try:
                     E.bind_alt_fields()
-                    self._copies_v.append(E.volt2); self._copies_c.append(E.curr2)
+                    as_t = lambda a: torch.from_numpy(a) if isinstance(a, np.ndarray) else a      # noqa: E731
+                    self._copies_v.append(as_t(E.volt2)); self._copies_c.append(as_t(E.curr2))
                 except Exception:            # e.g. out of memory: keep the separate half steps
                     self._fused = False
             self._vcur = self._ccur = 0

@@ -210,7 +210,8 @@ class openEMS:
             pass
         log = (lambda msg: (print(msg), sys.stdout.flush())) if verbose else None
         sim = Simulation(S, device=self.device, rank=rank, world=world, group=group, engine_factory=self.engine_factory,
-                         log=log, nf2ff_freqs=self.nf2ff_freqs, probe_freqs=S.probe_freqs)
+                         log=log, nf2ff_freqs=self.nf2ff_freqs, probe_freqs=S.probe_freqs,
+                         fused_multi=getattr(self, "fused_multi", True))
         sim.prepare()
         self.sim = sim
         if verbose and rank == 0:

@@ -219,16 +219,92 @@ class RefEngine:
         lib().ref_half_step(C.byref(self.e), int(phase))
 
     def half_step_part(self, phase, part):
+        self._load_current()
         lib().ref_half_step_part(C.byref(self.e), int(phase), int(part))
+        self._store_current()
 
     def half_step_raw(self, phase):
+        self._load_current()
         self.half_step(phase)
+        self._store_current()
+
+    # --- protocol emulation of the CUDA engine's fused steps on a z-slab rank (b200fdtd_fused_step_part) ---------------
+    # The C oracle always updates volt/curr in place.  To let the CPU gloo tests exercise the HOST side of the protocol
+    # (simulation.py:_fused_step: which field copy is current, which copy is sent / received when), this keeps a second
+    # copy on the python side and moves the state between the copies exactly where the CUDA launches read and write them.
+    # A copy that does not hold the state is filled with NaN, so reading or sending the wrong copy cannot go unnoticed.
+    emulates_fused_steps = True
+
+    def bind_alt_fields(self):
+        self.volt2 = np.zeros_like(self.volt); self.curr2 = np.zeros_like(self.curr)
+        self._vcur = self._ccur = 0
+
+    def current_copy(self):
+        return self._vcur, self._ccur
+
+    def reset_current_copy(self):
+        self._vcur = self._ccur = 0
+
+    def _load_current(self):
+        """engine arrays <- the copies that hold the state, ghost planes included (halos land in the current copy)"""
+        if getattr(self, "volt2", None) is None:
+            return
+        if self._vcur:
+            self.volt[...] = self.volt2
+        if self._ccur:
+            self.curr[...] = self.curr2
+
+    def _store_current(self):
+        """owned planes back into the copies that hold the state; the engine arrays' owned planes are poisoned then"""
+        if getattr(self, "volt2", None) is None:
+            return
+        o = slice(1, self.nz + 1)
+        if self._vcur:
+            self.volt2[:, o] = self.volt[:, o]; self.volt[:, o] = np.nan
+        if self._ccur:
+            self.curr2[:, o] = self.curr[:, o]; self.curr[:, o] = np.nan
+
+    def fused_step_part(self, part):
+        nz = self.nz
+        o = slice(1, nz + 1)
+        if part == 0:                                   # H of planes 0 .. nz-2 (CUDA engine: plane 0 + slabs here, interior in part 4/2)
+            self._load_current()
+            lib().ref_half_step_part(C.byref(self.e), 1, 0)
+        elif part == 4:
+            pass
+        elif part == 1:                                 # H of the top plane: needs the upper ghost E of the CURRENT E copy
+            if self._vcur:
+                self.volt[:, nz + 1] = self.volt2[:, nz + 1]
+            lib().ref_half_step_part(C.byref(self.e), 1, 1)
+            if self._ccur == 0:                         # the new H belongs in copy 1: the caller sends it from there
+                self.curr2[:, o] = self.curr[:, o]; self.curr[:, o] = np.nan
+            else:                                       # it belongs in copy 0 (the engine array); copy 1 is stale from here on
+                self.curr2[:, o] = np.nan
+        elif part == 2:
+            self._ccur ^= 1
+        elif part == 3:                                 # E: needs the new H with its freshly received lower ghost plane
+            if self._ccur:
+                self.curr[...] = self.curr2             # owned planes parked in part 1 + ghost plane 0 received since
+            lib().ref_half_step_part(C.byref(self.e), 0, 0)
+            lib().ref_half_step_part(C.byref(self.e), 0, 1)
+            if self._ccur:
+                self.curr[:, o] = np.nan                # H was only read: copy 1 still holds it
+            if self._vcur == 0:                         # the new E belongs in copy 1
+                self.volt2[:, o] = self.volt[:, o]; self.volt[:, o] = np.nan
+            else:                                       # it belongs in copy 0 (the engine array)
+                self.volt2[:, o] = np.nan
+            self._vcur ^= 1
+        else:
+            raise ValueError("part must be 0..4")
 
     def update_only(self, which):
         (lib().ref_update_e if which == 0 else lib().ref_update_h)(C.byref(self.e))
 
     def energy(self):
-        return float(lib().ref_energy(C.byref(self.e)))
+        self._load_current()
+        e = float(lib().ref_energy(C.byref(self.e)))
+        self._store_current()
+        return e
 
     @property
     def ts(self):

@@ -15,7 +15,7 @@ import torch.multiprocessing as mp
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def _worker(rank, world, port, boundary, q):
+def _worker(rank, world, port, boundary, fused, q):
     sys.path[:0] = [os.path.dirname(HERE), HERE, os.path.join(os.path.dirname(HERE), "fdtd-solver-antennas_b200")]
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -24,7 +24,9 @@ def _worker(rank, world, port, boundary, q):
         import scenes
         scenes.use_oracle_engine(threads=1)
         F, nf, prt = scenes.dipole(boundary, cells=(20, 20, 30), nrts=300, end=1e-12)
+        F.fused_multi = fused
         F.Run(scenes.tmp_sim_path(f"slab{rank}"), cleanup=True)
+        assert F.sim._fused == fused, "the run did not take the requested stepping protocol"
         res = F.results
         if rank == 0:
             q.put(dict(ut=res["probes"]["port_ut_1"]["val"], it=res["probes"]["port_it_1"]["val"],
@@ -34,8 +36,10 @@ def _worker(rank, world, port, boundary, q):
 
 
 @pytest.mark.parametrize("boundary", ["PML_8", "MUR"])
-@pytest.mark.parametrize("world", [2, 3])
-def test_slabs_equal_single(boundary, world):
+@pytest.mark.parametrize("world,fused", [(2, True), (3, True), (2, False)])
+def test_slabs_equal_single(boundary, world, fused):
+    """fused=True: the fused-step protocol of the CUDA engine (simulation.py:_fused_step; the oracle engine emulates the two
+    field copies and poisons the stale one with NaN); fused=False: separate half steps with one exchange each"""
     import scenes
     scenes.use_oracle_engine(threads=1)
     F, nf, prt = scenes.dipole(boundary, cells=(20, 20, 30), nrts=300, end=1e-12)
@@ -44,8 +48,8 @@ def test_slabs_equal_single(boundary, world):
     scenes.use_cuda_engine()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000) + world
-    procs = [ctx.Process(target=_worker, args=(r, world, port, boundary, q)) for r in range(world)]
+    port = 29500 + (os.getpid() % 2000) + world + (10 if fused else 0)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, boundary, fused, q)) for r in range(world)]
     for p in procs:
         p.start()
     got = None
