@@ -330,3 +330,38 @@ def test_timestep_estimate_is_stable_and_not_wasteful(seed):
     except FloatingPointError:
         grew = True
     assert grew, "a 35 % larger time step is still stable: the estimate wastes time steps"
+
+
+def test_two_port_microstrip_through_line():
+    """the same 50-ohm line between two lumped ports (port 2 passive, R = 50): little comes back to port 1, and what port 1
+    delivers is absorbed by port 2 (openEMS S-parameter convention: s21 = uf_ref(2) / uf_inc(1)).  Pins the lumped
+    resistor of a passive port and the port wave definitions (App. A5) on a structure with a known answer."""
+    from CSXCAD import ContinuousStructure
+    from openEMS import openEMS
+    er, h, w = 4.3, 1.6, 3.114396
+    F = openEMS(NrTS=8000, EndCriteria=1e-5)
+    F.SetGaussExcite(2.5e9, 1.5e9)
+    F.SetBoundaryCond(["PML_8", "PML_8", "PML_8", "PML_8", "PEC", "PML_8"])
+    csx = ContinuousStructure(); F.SetCSX(csx)
+    g = csx.GetGrid(); g.SetDeltaUnit(1e-3)
+    dy = w / 6
+    g.AddLine("x", np.arange(-40.0, 40.5, 1.0))
+    g.AddLine("y", np.arange(-24, 25) * dy)
+    g.AddLine("z", [0, 0.4, 0.8, 1.2, 1.6, 2.1, 2.8, 3.8, 5.2, 7.0, 9.0, 11.0, 13.0, 15.0, 17.0, 19.0, 21.0, 23.0])
+    csx.AddMaterial("sub", epsilon=er).AddBox([-30, -12 * dy, 0], [30, 12 * dy, h], priority=0)      # substrate ends inside the domain
+    csx.AddMetal("strip").AddBox([-25, -w / 2, h], [25, w / 2, h], priority=10)
+    p1 = F.AddLumpedPort(1, 50.0, [-25, 0, 0], [-25, 0, h], "z", 1.0, priority=5)
+    p2 = F.AddLumpedPort(2, 50.0, [25, 0, 0], [25, 0, h], "z", 0.0, priority=5)
+    path = scenes.tmp_sim_path("thru")
+    F.Run(path, cleanup=True)
+    assert F.results["stop_reason"] == "EndCriteria"
+    f = np.linspace(1.5e9, 3.5e9, 21)
+    p1.CalcPort(path, f); p2.CalcPort(path, f)
+    s11 = 20 * np.log10(np.abs(p1.uf_ref / p1.uf_inc))
+    s21 = 20 * np.log10(np.abs(p2.uf_ref / p1.uf_inc))
+    assert s11.max() < -14.0, np.round(s11, 1)              # line of ~47.5 ohm, port parasitics: measured -16 .. -33 dB
+    assert s21.min() > -0.5 and s21.max() < 0.05, np.round(s21, 2)          # measured -0.01 .. -0.14 dB
+    # power accepted at port 1 ends up in port 2's resistor (lossless substrate and metal; the rest radiates)
+    assert (p1.P_acc > 0).all() and (p2.P_acc < 0).all()
+    ratio = -p2.P_acc / p1.P_acc
+    assert ratio.min() > 0.95 and ratio.max() < 1.01, np.round(ratio, 3)    # measured 0.986 .. 0.997

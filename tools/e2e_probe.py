@@ -1,5 +1,5 @@
 import sys, os, time
-ROOT="/root/repo"
+ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0]=[ROOT, os.path.join(ROOT,"fdtd-solver-antennas_b200")]
 import torch
 from b200fdtd import scenes
