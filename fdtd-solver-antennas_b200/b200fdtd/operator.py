@@ -701,9 +701,17 @@ class OperatorBuilder:
         lo = [_snap(self.x[a], nf["start"][a]) for a in range(3)]
         hi = [_snap(self.x[a], nf["stop"][a]) for a in range(3)]
         faces = []
+        # a face that lies on a PEC / PMC boundary is dropped and the far field takes the image of the remaining faces in
+        # that wall instead (openEMS nf2ff 'mirror', App. A6): self.nf2ff_mirrors = [(axis, wall coordinate, bc type)]
+        self.nf2ff_mirrors = []
         for n in range(3):
             a, b = (n + 1) % 3, (n + 2) % 3
             for side, plane in ((0, lo[n]), (1, hi[n])):
+                bc = self.s.bc[2 * n + side]
+                on_wall = plane == (0 if side == 0 else self.n[n] - 1)
+                if bc in (BC_PEC, BC_PMC) and on_wall:
+                    self.nf2ff_mirrors.append((n, float(self.x[n][plane]), int(bc)))
+                    continue
                 faces.append(dict(normal=n, side=side, plane=plane, coord=float(self.x[n][plane]), a0=lo[a], a1=hi[a], b0=lo[b], b1=hi[b]))
         return faces
 

@@ -52,8 +52,21 @@ def surface_currents(nf, fidx, center):
         M[a] = s * Eb * dA;  M[b] = -s * Ea * dA                    # M = -n x E
         prad += 0.5 * s * np.sum(np.real(Ea * np.conj(Hb) - Eb * np.conj(Ha)) * dA)
         pos.append(P.reshape(3, -1)); Jl.append(J.reshape(3, -1)); Ml.append(M.reshape(3, -1))
-    pos = np.concatenate(pos, 1) - np.asarray(center, np.float64).reshape(3, 1)
-    return pos, np.concatenate(Jl, 1), np.concatenate(Ml, 1), float(prad)
+    c = np.asarray(center, np.float64).reshape(3)
+    pos = np.concatenate(pos, 1) - c.reshape(3, 1)
+    J, M = np.concatenate(Jl, 1), np.concatenate(Ml, 1)
+    # image theory for box faces dropped on PEC / PMC walls (openEMS nf2ff 'mirror'): the image of an electric current in a
+    # PEC wall keeps its normal and flips its tangential components, a magnetic current the other way round (PMC: swapped)
+    for (n, wall, kind) in nf.get("mirrors", []):
+        pm, Jm, Mm = pos.copy(), J.copy(), M.copy()
+        pm[n] = 2.0 * (wall - c[n]) - pos[n]
+        tang = [a for a in range(3) if a != n]
+        if kind == 0:          # PEC
+            Jm[tang] *= -1.0; Mm[n] *= -1.0
+        else:                  # PMC
+            Jm[n] *= -1.0; Mm[tang] *= -1.0
+        pos, J, M = np.concatenate([pos, pm], 1), np.concatenate([J, Jm], 1), np.concatenate([M, Mm], 1)
+    return pos, J, M, float(prad)
 
 
 def far_field(nf, freq, theta_deg, phi_deg, center=(0, 0, 0), radius=1.0, farfield_fn=None, device=0):

@@ -469,7 +469,7 @@ class Simulation:
                 full = [f[..., 0] + 1j * f[..., 1] for f in full]
             scale = 2.0 * self.interval * self.dt          # single-sided pulse spectrum, like DFT_time2freq (App. A5/A6)
             full = [f * scale for f in full]
-            res["nf2ff"] = dict(faces=self.faces, acc=full, freqs=self.nf2ff_freqs,
+            res["nf2ff"] = dict(faces=self.faces, acc=full, freqs=self.nf2ff_freqs, mirrors=list(getattr(self.builder, "nf2ff_mirrors", [])),
                                 weights=[self.builder.face_weights(F) for F in self.faces])
         self.results = res
         return res

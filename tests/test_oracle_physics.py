@@ -365,3 +365,46 @@ def test_two_port_microstrip_through_line():
     assert (p1.P_acc > 0).all() and (p2.P_acc < 0).all()
     ratio = -p2.P_acc / p1.P_acc
     assert ratio.min() > 0.95 and ratio.max() < 1.01, np.round(ratio, 3)    # measured 0.986 .. 0.997
+
+
+def test_probe_fed_patch_of_the_reference_design_rule():
+    """a textbook probe-fed patch with the reference's own dimensions (L, W from physics.py for 2.45 GHz on er 4.3, h 1.6 mm:
+    tests/golden/closed_form.json) over an infinite ground plane (PEC boundary): the fundamental resonance sits a few per
+    cent below the Hammerstad design frequency on this mesh (2.320 GHz at 20 cells per L, 2.355 GHz at 40: first-order
+    convergence towards ~2.39 GHz), broadside pattern with the directivity of a patch, a null along the ground in the H
+    plane (image theory of the NF2FF box in the PEC wall), radiated power = accepted power"""
+    from CSXCAD import ContinuousStructure
+    from openEMS import openEMS
+    er, h = 4.3, 1.6
+    L, W = 29.138326, 37.583886
+    f_design = 2.45e9
+    F = openEMS(NrTS=20000, EndCriteria=1e-4)
+    F.SetGaussExcite(f_design, 0.8e9)
+    F.SetBoundaryCond(["PML_8"] * 4 + ["PEC", "PML_8"])
+    csx = ContinuousStructure(); F.SetCSX(csx)
+    g = csx.GetGrid(); g.SetDeltaUnit(1e-3)
+    dx, dy = L / 20, W / 26
+    g.AddLine("x", np.arange(-41, 42) * dx); g.AddLine("y", np.arange(-41, 42) * dy)
+    g.AddLine("z", [0, 0.4, 0.8, 1.2, 1.6, 2.1, 2.8, 3.8, 5.2, 7.0, 9.5, 12.5, 16, 20, 24, 28, 32, 36, 40, 44, 48])
+    csx.AddMaterial("sub", epsilon=er).AddBox([-31 * dx, -31 * dy, 0], [31 * dx, 31 * dy, h], priority=0)
+    csx.AddMetal("patch").AddBox([-L / 2, -W / 2, h], [L / 2, W / 2, h], priority=10)
+    port = F.AddLumpedPort(1, 50.0, [-4 * dx, 0, 0], [-4 * dx, 0, h], "z", 1.0, priority=5)
+    f_nf = 2.32e9
+    nf = F.CreateNF2FFBox(frequency=[f_nf])
+    path = scenes.tmp_sim_path("patch")
+    F.Run(path, cleanup=True)
+    assert F.results["stop_reason"] == "EndCriteria"
+    f = np.linspace(2.0e9, 3.0e9, 401)
+    port.CalcPort(path, f)
+    s11 = 20 * np.log10(np.abs(port.uf_ref / port.uf_inc))
+    f_res = f[np.argmin(s11)]
+    assert s11.min() < -10.0
+    assert 0.93 * f_design < f_res < 0.97 * f_design, f_res          # 2.320 GHz on this mesh
+    theta = np.arange(0.0, 91.0, 5.0)
+    res = nf.CalcNF2FF(path, f_nf, theta, np.array([0.0, 90.0]))
+    e = res.E_norm[0]
+    assert np.argmax(e[:, 0]) == 0 and np.argmax(e[:, 1]) == 0       # broadside
+    assert 5.3 < 10 * np.log10(res.Dmax[0]) < 7.5, res.Dmax[0]       # 6.04 dBi
+    assert 20 * np.log10(e[0, 1] / e[-1, 1]) > 20.0                  # H plane: tangential E vanishes on the ground plane
+    port.CalcPort(path, np.array([f_nf]))
+    assert 0.9 < res.Prad[0] / port.P_acc[0] < 1.02, (res.Prad[0], port.P_acc[0])
