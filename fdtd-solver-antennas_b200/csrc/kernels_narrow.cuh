@@ -1,0 +1,245 @@
+// kernels_narrow.cuh - K3..K11: excitation, Mur, separate PML passes, probes, NF2FF running DFT, energy, far field
+// Part of libb200fdtd (textually included by b200fdtd.cu; see that file for the data layout and the arithmetic contract).
+#pragma once
+
+// ------------------------------------------------------------------------------------
+// narrow-band kernels
+// ------------------------------------------------------------------------------------
+// K5 excitation (Apply2Voltages): volt[idx] += amp * signal[ts - delay]
+__global__ void excite_kernel(float* __restrict__ volt, const int64_t* __restrict__ idx,
+                              const float* __restrict__ amp, const int* __restrict__ delay,
+                              const float* __restrict__ sig, int siglen, int64_t n,
+                              const int* __restrict__ d_ts, int ts_off)
+{
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const int pos = *d_ts + ts_off - delay[e];
+    if (pos < 0 || pos >= siglen) return;
+    const int64_t q = idx[e];
+    volt[q] = __fmaf_rn(amp[e], sig[pos], volt[q]);
+}
+
+// K3 Mur (App. A3): pre: tmp = volt[src] - k volt[dst]; post: tmp += k volt[src]; apply: volt[dst] = tmp
+__global__ void mur_kernel(float* __restrict__ volt, const int64_t* __restrict__ dst,
+                           const int64_t* __restrict__ src, const float* __restrict__ coeff,
+                           float* __restrict__ tmp, int64_t n, int phase)
+{
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    if (phase == 0) {
+        tmp[e] = __fmaf_rn(-coeff[e], volt[dst[e]], volt[src[e]]);
+    } else if (phase == 1) {
+        tmp[e] = __fmaf_rn(coeff[e], volt[src[e]], tmp[e]);
+    } else {
+        volt[dst[e]] = tmp[e];
+    }
+}
+
+// K4 PML_8 (App. A4): split-flux UPML, pre and post passes over one slab box (the boxes that are not fused
+// into the volume kernels: the narrow x-slabs).  blockIdx = (row chunk, z, component); threadIdx = (x, row).
+//   pre : h = a*f - fo*flux ; f = flux ; flux = h
+//   post: h = flux ; flux = f ; f = h + fn*flux
+__global__ void pml_kernel(float* __restrict__ field, const PmlBoxDev B, int which, int post,
+                           int px, long long sz, long long cs)
+{
+    const int y = blockIdx.x * blockDim.y + threadIdx.y;
+    if (y >= B.by) return;
+    const int z = blockIdx.y, comp = blockIdx.z;
+    const long long lrow = (((long long)comp * B.bz + z) * B.by + y) * B.bx;
+    const long long grow = comp * cs + (long long)(B.z0 + z + 1) * sz + (long long)(B.y0 + y) * px + B.x0;
+    float* __restrict__ flux = which == 0 ? B.flux_v : B.flux_i;
+    const float* __restrict__ a = which == 0 ? B.vv : B.ii;
+    const float* __restrict__ fo = which == 0 ? B.vvfo : B.iifo;
+    const float* __restrict__ fn = which == 0 ? B.vvfn : B.iifn;
+    for (int x = threadIdx.x; x < B.bx; x += blockDim.x) {
+        const long long l = lrow + x, q = grow + x;
+        if (!post) {
+            const float fl = flux[l];
+            const float h = __fmaf_rn(a[l], field[q], -__fmul_rn(fo[l], fl));
+            field[q] = fl;
+            flux[l] = h;
+        } else {
+            const float h = flux[l];
+            const float v = field[q];
+            flux[l] = v;
+            field[q] = __fmaf_rn(fn[l], v, h);
+        }
+    }
+}
+
+// tiny: advance the device step counter
+__global__ void ts_add_kernel(int* d_ts, int n) { if (threadIdx.x == 0 && blockIdx.x == 0) *d_ts += n; }
+
+// K6+K7 probes: weighted line/loop sums with a warp-shuffle reduction, time series and running DFT
+__global__ void __launch_bounds__(128) probe_kernel(const float* __restrict__ volt, const float* __restrict__ curr,
+        const int* __restrict__ kind, const int64_t* __restrict__ off, const int64_t* __restrict__ idx,
+        const float* __restrict__ w, int interval, int max_samples, float* __restrict__ series,
+        int nfreq, const double* __restrict__ freqs, float* __restrict__ dft, double dt,
+        const int* __restrict__ d_ts, int ts_off)
+{
+    const int p = blockIdx.x;
+    const int ts = *d_ts + ts_off;                 // completed steps
+    const int s = ts / interval - 1;
+    if (s < 0 || s >= max_samples) return;
+    const float* fld = kind[p] == 0 ? volt : curr;
+    float acc = 0.f;
+    for (int64_t e = off[p] + threadIdx.x; e < off[p + 1]; e += blockDim.x) acc = __fmaf_rn(w[e], fld[idx[e]], acc);
+    __shared__ float red[4];
+    __shared__ float total;
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const float t = (red[0] + red[1]) + (red[2] + red[3]);
+        total = t;
+        series[(int64_t)p * max_samples + s] = t;
+    }
+    __syncthreads();
+    const float val = total;
+    const double tm = (kind[p] == 0 ? (double)ts : (double)ts + 0.5) * dt;
+    for (int q = threadIdx.x; q < nfreq; q += blockDim.x) {
+        double ph = freqs[q] * tm; ph -= floor(ph);
+        double sn, cn; sincospi(2.0 * ph, &sn, &cn);
+        float* a = dft + ((int64_t)p * nfreq + q) * 2;
+        a[0] = __fmaf_rn(val, (float)cn, a[0]);
+        a[1] = __fmaf_rn(-val, (float)sn, a[1]);
+    }
+}
+
+// K8 NF2FF: running DFT of node-interpolated tangential E/H on the Huygens box faces (App. A6)
+struct Nf2ffParams {
+    const float* volt; const float* curr;
+    int ny, px; long long sz, cs;
+    const float* il[3]; const float* idl[3];     // inverse primal / dual edge lengths (z arrays offset by one entry)
+    int nfreq; const double* freqs; double dt;
+    const int* d_ts; int ts_off;
+};
+__global__ void __launch_bounds__(128) nf2ff_kernel(const FaceTable* __restrict__ tab, const Nf2ffParams P)
+{
+    extern __shared__ float tw[];                  // [nfreq][4] = cosE, sinE, cosH, sinH
+    const FaceDev& F = tab->f[blockIdx.y];
+    const int na = F.a1 - F.a0 + 1, nb = F.b1 - F.b0 + 1;
+    const long long nn = (long long)na * nb;
+    if ((long long)blockIdx.x * blockDim.x >= nn) return;
+    const int ts = *P.d_ts + P.ts_off;
+    for (int q = threadIdx.x; q < P.nfreq; q += blockDim.x) {
+        double sn, cn;
+        double ph = P.freqs[q] * ((double)ts * P.dt); ph -= floor(ph);
+        sincospi(2.0 * ph, &sn, &cn); tw[4 * q] = (float)cn; tw[4 * q + 1] = (float)sn;
+        ph = P.freqs[q] * (((double)ts + 0.5) * P.dt); ph -= floor(ph);
+        sincospi(2.0 * ph, &sn, &cn); tw[4 * q + 2] = (float)cn; tw[4 * q + 3] = (float)sn;
+    }
+    __syncthreads();
+    const long long node = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (node >= nn) return;
+    const int n = F.normal, a = (n + 1) % 3, b = (n + 2) % 3;
+    const int ia = F.a0 + (int)(node % na), ib = F.b0 + (int)(node / na);
+    int co[3]; co[n] = F.plane; co[a] = ia; co[b] = ib;
+    const long long st[3] = {1, (long long)P.px, P.sz};
+    const long long lin0 = (long long)(co[2] + 1) * P.sz + (long long)co[1] * P.px + co[0];
+    const int oa = (a == 2), ob = (b == 2);
+    const float* va = P.volt + a * P.cs; const float* vb = P.volt + b * P.cs;
+    const float* ca = P.curr + a * P.cs; const float* cb = P.curr + b * P.cs;
+    const float Ea = 0.5f * (va[lin0] * P.il[a][ia + oa] + va[lin0 - st[a]] * P.il[a][ia + oa - 1]);
+    const float Eb = 0.5f * (vb[lin0] * P.il[b][ib + ob] + vb[lin0 - st[b]] * P.il[b][ib + ob - 1]);
+    const float Ha = 0.25f * P.idl[a][ia + oa] *
+        ((ca[lin0] + ca[lin0 - st[b]]) + (ca[lin0 - st[n]] + ca[lin0 - st[b] - st[n]]));
+    const float Hb = 0.25f * P.idl[b][ib + ob] *
+        ((cb[lin0] + cb[lin0 - st[a]]) + (cb[lin0 - st[n]] + cb[lin0 - st[a] - st[n]]));
+    const float v[4] = {Ea, Eb, Ha, Hb};
+    float2* acc = reinterpret_cast<float2*>(F.acc);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        for (int q = 0; q < P.nfreq; ++q) {
+            const float cn = tw[4 * q + (c >= 2 ? 2 : 0)], sn = tw[4 * q + (c >= 2 ? 3 : 1)];
+            float2* d = acc + ((long long)c * P.nfreq + q) * nn + node;
+            float2 t = *d;
+            t.x = __fmaf_rn(v[c], cn, t.x);
+            t.y = __fmaf_rn(-v[c], sn, t.y);
+            *d = t;
+        }
+    }
+}
+
+// K9 energy: deterministic two-stage reduction of sum(f^2) over the owned planes
+__global__ void __launch_bounds__(256) energy_partial_kernel(const float* __restrict__ volt, const float* __restrict__ curr,
+        long long sz, long long cs, long long n_owned, double* __restrict__ partials)
+{
+    // partials[2*block + 0/1] = sum volt^2 / sum curr^2 of this block's grid-stride share
+    double sv = 0.0, sc = 0.0;
+    const long long n4 = n_owned / 4;              // n_owned = nz*sz, multiple of 4
+    for (int c = 0; c < 3; ++c) {
+        const float4* v = reinterpret_cast<const float4*>(volt + c * cs + sz);
+        const float4* h = reinterpret_cast<const float4*>(curr + c * cs + sz);
+        for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n4; q += (long long)gridDim.x * blockDim.x) {
+            const float4 a = v[q], b = h[q];
+            sv += (double)(a.x * a.x + a.y * a.y) + (double)(a.z * a.z + a.w * a.w);
+            sc += (double)(b.x * b.x + b.y * b.y) + (double)(b.z * b.z + b.w * b.w);
+        }
+    }
+    __shared__ double rv[8], rc[8];
+    for (int o = 16; o > 0; o >>= 1) { sv += __shfl_down_sync(0xffffffffu, sv, o); sc += __shfl_down_sync(0xffffffffu, sc, o); }
+    if ((threadIdx.x & 31) == 0) { rv[threadIdx.x >> 5] = sv; rc[threadIdx.x >> 5] = sc; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0, b = 0;
+        for (int i = 0; i < 8; ++i) { a += rv[i]; b += rc[i]; }
+        partials[2 * blockIdx.x] = a; partials[2 * blockIdx.x + 1] = b;
+    }
+}
+__global__ void energy_final_kernel(const double* __restrict__ partials, int n, double* __restrict__ out)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double a = 0, b = 0;
+        for (int i = 0; i < n; ++i) { a += partials[2 * i]; b += partials[2 * i + 1]; }
+        out[0] = a; out[1] = b;
+    }
+}
+
+// K11 far field: N = sum J e^{jk r^.r'}, L = sum M e^{jk r^.r'} projected on theta^/phi^ (App. A6)
+__global__ void __launch_bounds__(256) farfield_kernel(long long npts, const float* __restrict__ pos,
+        const float* __restrict__ J, const float* __restrict__ M, double k, int ndir,
+        const double* __restrict__ theta, const double* __restrict__ phi, float* __restrict__ out)
+{
+    const int d = blockIdx.x;
+    if (d >= ndir) return;
+    double st, ct, sp, cp;
+    sincos(theta[d], &st, &ct); sincos(phi[d], &sp, &cp);
+    const float ux = (float)(k * st * cp), uy = (float)(k * st * sp), uz = (float)(k * ct);
+    double a[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) a[i] = 0.0;
+    for (long long q = threadIdx.x; q < npts; q += blockDim.x) {
+        const float ph = ux * pos[q] + uy * pos[npts + q] + uz * pos[2 * npts + q];
+        float sn, cn; sincosf(ph, &sn, &cn);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float jr = J[(c * npts + q) * 2], ji = J[(c * npts + q) * 2 + 1];
+            const float mr = M[(c * npts + q) * 2], mi = M[(c * npts + q) * 2 + 1];
+            a[2 * c] += (double)(jr * cn - ji * sn); a[2 * c + 1] += (double)(jr * sn + ji * cn);
+            a[6 + 2 * c] += (double)(mr * cn - mi * sn); a[6 + 2 * c + 1] += (double)(mr * sn + mi * cn);
+        }
+    }
+    __shared__ double red[8][12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        double v = a[i];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s[12];
+        for (int i = 0; i < 12; ++i) { s[i] = 0; for (int wv = 0; wv < 8; ++wv) s[i] += red[wv][i]; }
+        // theta^ = (ct cp, ct sp, -st), phi^ = (-sp, cp, 0)
+        for (int part = 0; part < 2; ++part) {         // 0: N from J, 1: L from M
+            const double* v = s + 6 * part;
+            for (int ri = 0; ri < 2; ++ri) {
+                const double vx = v[ri], vy = v[2 + ri], vz = v[4 + ri];
+                out[((long long)d * 4 + 2 * part) * 2 + ri] = (float)(vx * ct * cp + vy * ct * sp - vz * st);
+                out[((long long)d * 4 + 2 * part + 1) * 2 + ri] = (float)(-vx * sp + vy * cp);
+            }
+        }
+    }
+}
+
