@@ -53,6 +53,8 @@ SYMBOLS = {
     "b200fdtd_set_probes": (C.c_int, [vp, C.c_int, c_i32, c_i64, c_i64, c_f, C.c_int, C.c_int, vp, C.c_int, c_d, vp, C.c_double]),
     "b200fdtd_set_nf2ff": (C.c_int, [vp, C.c_int, C.POINTER(Nf2ffFace), C.c_int, c_d, C.c_int, C.c_double,
                                      c_f, c_f, c_f, c_f, c_f, c_f]),
+    "b200fdtd_set_nf2ff_td": (C.c_int, [vp, C.c_int, C.POINTER(vp), C.c_int]),
+    "b200fdtd_nf2ff_td_dft": (C.c_int, [vp, C.c_int, C.c_int, c_d, C.c_int, vp]),
     "b200fdtd_get_timestep": (C.c_int, [vp, c_i64]),
     "b200fdtd_set_timestep": (C.c_int, [vp, C.c_int64]),
     "b200fdtd_run": (C.c_int, [vp, C.c_int64, C.c_int]),

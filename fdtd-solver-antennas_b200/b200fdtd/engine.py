@@ -195,6 +195,29 @@ class Engine:
                                         _ptr(il[0], c_f), _ptr(il[1], c_f), _ptr(il[2], c_f),
                                         _ptr(idl[0], c_f), _ptr(idl[1], c_f), _ptr(idl[2], c_f)))
 
+    def set_nf2ff_td(self, max_samples):
+        """keep the face samples themselves in HBM (openEMS's nf2ff_E/H_n.h5 dumps) so the far field can be evaluated at any
+        frequency after the run; returns the bytes allocated"""
+        self.face_td = [torch.zeros((int(max_samples), 4) + tuple(acc.shape[2:4]), dtype=torch.float32, device=self.device)
+                        for acc in self.face_acc]
+        self.td_max = int(max_samples)
+        arr = (C.c_void_p * max(1, len(self.face_td)))(*[t.data_ptr() for t in self.face_td])
+        self._pre()
+        check(self.L.b200fdtd_set_nf2ff_td(self.h, len(self.face_td), arr, int(max_samples)))
+        return sum(t.numel() * 4 for t in self.face_td)
+
+    def nf2ff_td_dft(self, freqs, nsamples):
+        """DFT of the stored face samples at `freqs`: list of float32 device tensors [4][nfreq][nb][na][2] (accumulator layout)"""
+        freqs = _np(np.atleast_1d(freqs), np.float64)
+        out = []
+        self._pre()
+        for q, acc in enumerate(self.face_acc):
+            o = torch.empty((4, len(freqs)) + tuple(acc.shape[2:4]) + (2,), dtype=torch.float32, device=self.device)
+            check(self.L.b200fdtd_nf2ff_td_dft(self.h, q, len(freqs), _ptr(freqs, c_d), int(min(nsamples, self.td_max)), o.data_ptr()))
+            out.append(o)
+        self._post()
+        return out
+
     # ---- stepping ----
     def _pre(self):
         self.stream.wait_stream(torch.cuda.current_stream(self.device))
@@ -279,15 +302,24 @@ def launch_count():
     return int(_lib.lib().b200fdtd_launch_count())
 
 
-def farfield(pos, J, M, k, theta, phi, device=0):
+class FarfieldSources:
+    """equivalent currents of one (frequency, centre) resident on the device: the reference asks for the far field once per
+    phi (73 calls, …microstrip_3d.py:221-238); the currents are uploaded once and every call is one launch"""
+
+    def __init__(self, pos, J, M, device=0):
+        self.dev = torch.device("cuda", int(device))
+        self.pos = torch.as_tensor(np.ascontiguousarray(pos, np.float32), device=self.dev)
+        self.J = torch.as_tensor(np.ascontiguousarray(np.stack([np.real(J), np.imag(J)], -1), np.float32), device=self.dev)
+        self.M = torch.as_tensor(np.ascontiguousarray(np.stack([np.real(M), np.imag(M)], -1), np.float32), device=self.dev)
+
+
+def farfield(pos, J, M, k, theta, phi, device=0, sources=None):
     """K11 on device.  pos [3][n], J/M [3][n] complex, theta/phi radians ->
     (N_theta, N_phi, L_theta, L_phi) complex128 numpy arrays [ndir]."""
     L = _lib.lib()
-    dev = torch.device("cuda", int(device))
-    pos_t = torch.as_tensor(np.ascontiguousarray(pos, np.float32), device=dev)
+    src = sources if sources is not None else FarfieldSources(pos, J, M, device)
+    dev, pos_t, Jt, Mt = src.dev, src.pos, src.J, src.M
     n = pos_t.shape[1]
-    Jt = torch.as_tensor(np.ascontiguousarray(np.stack([np.real(J), np.imag(J)], -1), np.float32), device=dev)
-    Mt = torch.as_tensor(np.ascontiguousarray(np.stack([np.real(M), np.imag(M)], -1), np.float32), device=dev)
     th, ph = _np(theta, np.float64), _np(phi, np.float64)
     out = torch.zeros((len(th), 4, 2), dtype=torch.float32, device=dev)
     s = torch.cuda.current_stream(dev)

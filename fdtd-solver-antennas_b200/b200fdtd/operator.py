@@ -97,64 +97,73 @@ def _snap(lines, v):
 class RowFactor:
     """Row compression of one pass (E: vv,vi / H: ii,iv), host side of b200fdtd_set_row_compression.
 
-    On a rectilinear mesh most coefficient rows are scale(j,k) * xvec[i] for a handful of x-vectors.  For such rows the
-    float32 coefficients are DEFINED as fl32(fl32(scale) * fl32(xvec[i])) (instead of rounding the float64 value
-    directly; the two differ by at most one unit in the last place), so that the CUDA kernels can rebuild the row
-    from 32 bytes of metadata and a cached x-vector and still be bit-identical to a run from the full arrays."""
-    TOL = 1e-11
+    On a rectilinear mesh most coefficient rows are scale(j,k) * xvec[i] for a handful of x-vectors.  The float32 operator
+    is therefore DEFINED row by row in factored form: with i* the first non-zero column of the float64 row,
+        coefficient[i] = fl32( fl32(row[i*]) * fl32(row[i] / row[i*]) )
+    (at most 1.5 ulp from rounding the float64 value directly, exact at i*).  The definition depends on the row alone -
+    not on which rows share an x-vector, on the chunking of the build or on how the grid is cut into z-slabs - so a
+    z-slab rank builds bit for bit the rows the single-GPU run builds.  Compression is then a lossless encoding on top:
+    rows whose normalised float32 vector fl32(row / row[i*]) equals a table entry bit for bit are recorded as
+    (scale, id); the CUDA kernels rebuild them with one multiply and stay bit-identical to a run from the full arrays."""
     MAX_VECS = 250
 
     def __init__(self, nx, px, nzp, ny, dev, nslots=6, rec_bytes=32):
         """nslots scales + nslots ids per row record of rec_bytes (operator passes: 6 / 32; PML slabs: 9 / 48)"""
         self.nx, self.px, self.dev = nx, px, dev
         self.nslots, self.id0 = nslots, 4 * nslots
-        self.vec32 = []                                   # shared table of this pass
-        self.slots = [[] for _ in range(nslots)]          # per slot: list of (global id, xref float64 [nx])
+        self.vec32 = []                                   # shared table of this pass: float32 [px] each
+        self.slots = [[] for _ in range(nslots)]          # per slot: ids of the table entries rows of this slot have used
         self.meta_f = torch.zeros((nzp, ny, rec_bytes // 4), dtype=torch.float32, device=dev)
         self.meta_u8 = self.meta_f.view(torch.uint8)      # [nzp, ny, rec_bytes]
         self.meta_u8[:, :, self.id0:self.id0 + nslots] = 255
         self.rows_total = 0
         self.rows_compressed = 0
 
-    def _match(self, arr, amax, gid, xref, ids, sc, unmatched):
-        s = (arr @ xref) / (xref @ xref)
-        resid = (arr - s.unsqueeze(-1) * xref).abs().amax(-1)
-        ok = unmatched & (resid <= self.TOL * amax)
+    def _match(self, x32, gid, ids, unmatched):
+        ok = unmatched & (x32 == self.vec32[gid][:self.nx]).all(-1)
         ids[ok] = gid
-        sc[ok] = s[ok]
         unmatched &= ~ok
 
     def factor(self, arr, slot, plane0):
         """arr float64 [nk, ny, nx] -> float32 [nk, ny, nx]; records (scale, id) of the rows in meta[plane0:plane0+nk]"""
         nk, ny, nx = arr.shape
-        amax = arr.abs().amax(-1)
+        nzm = arr != 0
+        first = nzm.to(torch.int8).argmax(-1, keepdim=True)              # i*: first non-zero column (0 for an all-zero row)
+        s = arr.gather(-1, first)                                         # row[i*]  (0 for an all-zero row)
+        live = s != 0
+        x32 = torch.where(live, arr / torch.where(live, s, torch.ones_like(s)), torch.zeros_like(arr)).to(torch.float32)
+        s32 = s.to(torch.float32)
+        out = s32 * x32                                                   # float32 multiply, IEEE rn: THE coefficient
+        live = live.squeeze(-1)
         ids = torch.full((nk, ny), 255, dtype=torch.int64, device=self.dev)
-        sc = torch.zeros((nk, ny), dtype=torch.float64, device=self.dev)
-        unmatched = torch.ones((nk, ny), dtype=torch.bool, device=self.dev)
-        for gid, xref in self.slots[slot]:
-            self._match(arr, amax, gid, xref, ids, sc, unmatched)
-        for _ in range(3):                                # learn new x-vectors from rows nothing matched yet
-            cand = unmatched & (amax > 0)
-            if not bool(cand.any()) or len(self.vec32) >= self.MAX_VECS:
+        unmatched = live.clone()
+        for gid in self.slots[slot]:
+            self._match(x32, gid, ids, unmatched)
+        for gid in range(len(self.vec32)):                                # vectors learnt by other slots of this pass
+            if not bool(unmatched.any()):
                 break
-            idx = cand.nonzero()
+            if gid not in self.slots[slot]:
+                n0 = int(unmatched.sum())
+                self._match(x32, gid, ids, unmatched)
+                if int(unmatched.sum()) != n0:
+                    self.slots[slot].append(gid)
+        for _ in range(3):                                # learn new x-vectors from rows nothing matched yet
+            if not bool(unmatched.any()) or len(self.vec32) >= self.MAX_VECS:
+                break
+            idx = unmatched.nonzero()
             kk, jj = idx[len(idx) // 2].tolist()
-            xref = arr[kk, jj] / amax[kk, jj]
             gid = len(self.vec32)
             v32 = torch.zeros(self.px, dtype=torch.float32, device=self.dev)
-            v32[:nx] = xref.to(torch.float32)
+            v32[:nx] = x32[kk, jj]
             self.vec32.append(v32)
-            self.slots[slot].append((gid, xref.clone()))
-            self._match(arr, amax, gid, xref, ids, sc, unmatched)
-        out = arr.to(torch.float32)
-        sc32 = sc.to(torch.float32)
+            self.slots[slot].append(gid)
+            self._match(x32, gid, ids, unmatched)
         if len(self.vec32):
-            table = torch.stack(self.vec32)[:, :nx]       # [nvec, nx] float32
-            m = ids != 255
-            if bool(m.any()):
-                prod = sc32.unsqueeze(-1) * table[ids.clamp(max=len(self.vec32) - 1)]    # float32 multiply, IEEE rn
-                out = torch.where(m.unsqueeze(-1), prod, out)
-        self.meta_f[plane0:plane0 + nk, :, slot] = sc32
+            # all-zero rows (edges that do not exist, PEC rows): scale 0 times a vector without negative entries is +0 everywhere
+            pos = [g for g, v in enumerate(self.vec32) if bool((v >= 0).all())]
+            if pos:
+                ids[~live] = pos[0]
+        self.meta_f[plane0:plane0 + nk, :, slot] = s32.squeeze(-1)
         self.meta_u8[plane0:plane0 + nk, :, self.id0 + slot] = ids.to(torch.uint8)
         self.rows_total += nk * ny
         self.rows_compressed += int((ids != 255).sum())

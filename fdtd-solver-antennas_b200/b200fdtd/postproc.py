@@ -34,15 +34,35 @@ def port_spectrum(probe, freq, probe_freqs=None):
     return dft_time2freq(probe["t"], probe["val"], freq)
 
 
-def surface_currents(nf, fidx, center):
-    """equivalent currents on the Huygens box for frequency index fidx.
+def face_spectra(nf, freq):
+    """per-face [4][nb][na] complex spectra (Ea, Eb, Ha, Hb) at `freq`: the running-DFT accumulators if the frequency was
+    registered, otherwise a DFT of the stored time-domain face samples (what openEMS's CalcNF2FF does with its HDF5 dumps;
+    the reference passes the caller's frequency_hz: antenna_sim/solver_fdtd_openems_microstrip_3d.py:225)"""
+    freqs = np.asarray(nf["freqs"], np.float64)
+    hit = np.where(np.isclose(freqs, freq, rtol=1e-9, atol=0.0))[0]
+    if len(hit):
+        return [acc[:, int(hit[0])] for acc in nf["acc"]]
+    key = float(freq)
+    extra = nf.setdefault("extra", {})
+    if key not in extra:
+        fn = nf.get("spectra_fn")
+        if fn is None:
+            raise ValueError(f"NF2FF frequency {freq:g} Hz was not registered for the running DFT (available: {freqs.tolist()}) "
+                             "and the time-domain face samples were not kept (memory budget B200FDTD_NF2FF_TD_GB); "
+                             "pass frequency=[...] to CreateNF2FFBox")
+        extra[key] = [a[:, 0] for a in fn([key])]
+    return extra[key]
+
+
+def surface_currents(nf, freq, center):
+    """equivalent currents on the Huygens box at frequency `freq`.
     Returns pos [3][N] (relative to center, m), J [3][N], M [3][N] (already times dA), Prad."""
     pos, Jl, Ml = [], [], []
     prad = 0.0
-    for F, acc, (xa, xb, wa, wb) in zip(nf["faces"], nf["acc"], nf["weights"]):
+    for F, acc, (xa, xb, wa, wb) in zip(nf["faces"], face_spectra(nf, freq), nf["weights"]):
         n = F["normal"]; a, b = (n + 1) % 3, (n + 2) % 3
         s = 1.0 if F["side"] == 1 else -1.0
-        Ea, Eb, Ha, Hb = (acc[c, fidx] for c in range(4))           # [nb][na]
+        Ea, Eb, Ha, Hb = (acc[c] for c in range(4))                 # [nb][na]
         dA = wb[:, None] * wa[None, :]
         XA, XB = np.meshgrid(xa, xb)                                 # [nb][na]
         P = np.zeros((3,) + dA.shape)
@@ -71,20 +91,25 @@ def surface_currents(nf, fidx, center):
 
 def far_field(nf, freq, theta_deg, phi_deg, center=(0, 0, 0), radius=1.0, farfield_fn=None, device=0):
     """E_theta/E_phi on the theta x phi grid (degrees) for one frequency of the box spectra."""
-    freqs = np.asarray(nf["freqs"], np.float64)
-    hit = np.where(np.isclose(freqs, freq, rtol=1e-9, atol=0.0))[0]
-    if len(hit) == 0:
-        raise ValueError(f"NF2FF frequency {freq:g} Hz was not registered for the running DFT "
-                         f"(available: {freqs.tolist()}); pass frequency=[...] to CreateNF2FFBox")
-    fidx = int(hit[0])
-    pos, J, M, prad = surface_currents(nf, fidx, center)
+    # the reference calls CalcNF2FF once per phi with the same frequency and centre (73 calls): the equivalent currents are
+    # formed once per (frequency, centre) and, on the CUDA path, stay on the device between the calls
+    key = (float(freq), tuple(np.asarray(center, np.float64).reshape(3).tolist()))
+    cache = nf.setdefault("sources", {})
+    if key not in cache:
+        if len(cache) >= 8:
+            cache.clear()
+        cache[key] = dict(cur=surface_currents(nf, float(freq), center), dev=None)
+    ent = cache[key]
+    pos, J, M, prad = ent["cur"]
     th = np.deg2rad(np.atleast_1d(np.asarray(theta_deg, np.float64)))
     ph = np.deg2rad(np.atleast_1d(np.asarray(phi_deg, np.float64)))
     TH, PH = np.meshgrid(th, ph, indexing="ij")
     k = 2.0 * np.pi * float(freq) / C0
     if farfield_fn is None:
-        from .engine import farfield as farfield_fn     # CUDA kernel K11
-        Nt, Np_, Lt, Lp = farfield_fn(pos, J, M, k, TH.ravel(), PH.ravel(), device=device)
+        from .engine import farfield as farfield_fn, FarfieldSources     # CUDA kernel K11
+        if ent["dev"] is None:
+            ent["dev"] = FarfieldSources(pos, J, M, device)
+        Nt, Np_, Lt, Lp = farfield_fn(None, None, None, k, TH.ravel(), PH.ravel(), device=device, sources=ent["dev"])
     else:
         Nt, Np_, Lt, Lp = farfield_fn(pos, J, M, k, TH.ravel(), PH.ravel())
     fac = 1j * k * np.exp(-1j * k * radius) / (4.0 * np.pi * radius)

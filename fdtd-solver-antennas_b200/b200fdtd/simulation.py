@@ -46,7 +46,7 @@ def _default_engine_factory(nx, ny, nz, px, device):
 class Simulation:
     def __init__(self, setup: Setup, device=0, rank=0, world=1, group=None, engine_factory=None,
                  build_device=None, px_align=32, log=None, nf2ff_freqs=None, probe_freqs=None, align_x_slabs=True, compress_pml=True,
-                 fused_multi=True):
+                 fused_multi=True, nf2ff_td=None):
         self.setup = setup
         self.rank, self.world, self.group = int(rank), int(world), group
         self.device = device
@@ -57,6 +57,9 @@ class Simulation:
         self.align_x_slabs = bool(align_x_slabs)
         self.compress_pml = bool(compress_pml)
         self.fused_multi = bool(fused_multi)
+        # time-domain store of the NF2FF face samples (far field at any frequency after the run): None = if it fits the
+        # memory budget (B200FDTD_NF2FF_TD_GB, default 8 GB per GPU and at most 30 % of the free HBM), False = never
+        self.nf2ff_td = nf2ff_td
         self.nf2ff_freqs = None if nf2ff_freqs is None else np.atleast_1d(np.asarray(nf2ff_freqs, np.float64))
         self.probe_freqs = None if probe_freqs is None else np.atleast_1d(np.asarray(probe_freqs, np.float64))
         self.engine = None
@@ -192,9 +195,68 @@ class Simulation:
                 il = [1.0 / B.len_p[0], 1.0 / B.len_p[1], self._z_slice(1.0 / B.len_p[2])]
                 idl = [1.0 / B.len_d[0], 1.0 / B.len_d[1], self._z_slice(1.0 / B.len_d[2])]
                 E.set_nf2ff(loc, self.nf2ff_freqs, self.interval, dt, il, idl)
+            self._setup_td_store()
         self.prepare_s = time.time() - t0
         self.cells = nx * ny * nz
         return self
+
+    def _setup_td_store(self):
+        """openEMS keeps the face samples themselves (HDF5 dumps) and CalcNF2FF transforms them at whatever frequency the caller
+        names (…microstrip_3d.py:225).  Here the samples stay in HBM when they fit; all ranks decide alike."""
+        import os
+        E = self.engine
+        self.td_bytes = 0
+        want = self.nf2ff_td is not False and hasattr(E, "set_nf2ff_td")
+        nodes = sum((L["a1"] - L["a0"] + 1) * (L["b1"] - L["b0"] + 1) for L in self.local_faces)
+        need = nodes * 16 * self.max_samples
+        ok = want
+        if want and self.nf2ff_td is None:
+            budget = float(os.environ.get("B200FDTD_NF2FF_TD_GB", "8")) * 2 ** 30
+            if torch.cuda.is_available() and isinstance(getattr(E, "device", None), torch.device):
+                budget = min(budget, 0.3 * torch.cuda.mem_get_info(E.device)[0])
+            ok = need <= budget
+        if self.world > 1:
+            t = torch.tensor([1.0 if ok else 0.0], dtype=torch.float64)
+            if torch.distributed.get_backend(self.group) == "nccl":
+                t = t.cuda(self.device)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MIN, group=self.group)
+            ok = bool(t.item() > 0.5)
+        if ok and self.local_faces:
+            self.td_bytes = E.set_nf2ff_td(self.max_samples)
+        self.td_store = bool(ok)
+
+    def _assemble_faces(self, local, nf):
+        """local per-face arrays [4][nf][nb_loc][na_loc][2] (this slab's part) -> global complex faces, summed over the slabs"""
+        full = []
+        for F in self.faces:
+            na, nb = F["a1"] - F["a0"] + 1, F["b1"] - F["b0"] + 1
+            full.append(np.zeros((4, nf, nb, na), np.complex128))
+        for q, L in enumerate(self.local_faces):
+            acc = _np(local[q]).astype(np.float64)
+            acc = acc[..., 0] + 1j * acc[..., 1]
+            F = self.faces[L["face"]]
+            n = F["normal"]; a = (n + 1) % 3
+            if n == 2:
+                full[L["face"]][...] = acc
+            elif a == 2:      # a-axis is z
+                o = L["z_off"]; full[L["face"]][:, :, :, o:o + acc.shape[3]] = acc
+            else:             # b-axis is z
+                o = L["z_off"]; full[L["face"]][:, :, o:o + acc.shape[2], :] = acc
+        if self.world > 1:
+            full = [self._allreduce_np(np.stack([f.real, f.imag], -1)) for f in full]
+            full = [f[..., 0] + 1j * f[..., 1] for f in full]
+        scale = 2.0 * self.interval * self.dt          # single-sided pulse spectrum, like DFT_time2freq (App. A5/A6)
+        return [f * scale for f in full]
+
+    def nf2ff_spectra(self, freqs):
+        """face spectra at arbitrary frequencies from the stored time-domain samples (collective on z-slab runs)"""
+        if not getattr(self, "td_store", False):
+            raise ValueError("the NF2FF face samples were not kept (they did not fit the memory budget B200FDTD_NF2FF_TD_GB); "
+                             "register the frequency before the run: CreateNF2FFBox(frequency=[...]) or FDTD.nf2ff_freqs")
+        freqs = np.atleast_1d(np.asarray(freqs, np.float64))
+        ns = self.results["n_samples"]
+        local = self.engine.nf2ff_td_dft(freqs, ns) if self.local_faces else []
+        return self._assemble_faces(local, len(freqs))
 
     def _z_slice(self, arr):
         """global per-line array -> local array with nz+2 entries (entry 0 = plane K0-1)"""
@@ -273,6 +335,10 @@ class Simulation:
                                and hasattr(E, "fused_step_part") and self.nz >= 3)
             self._copies_v, self._copies_c = [self._tv], [self._tc]
             if self._fused:
+                # b200fdtd_fused_step_part needs every PML box inside the volume launches (no separate pre/post boxes)
+                if hasattr(E, "plan_info") and E.plan_info()[2] != 0:
+                    self._fused = False
+            if self._fused:
                 try:
                     E.bind_alt_fields()
                     as_t = lambda a: torch.from_numpy(a) if isinstance(a, np.ndarray) else a      # noqa: E731
@@ -343,6 +409,10 @@ class Simulation:
         import contextlib
         E = self.engine
         self._views()
+        if self._gpu:
+            # everything torch did on its current stream so far (zero fills of the second field copy, of the probe series and
+            # of the NF2FF accumulators, operator uploads) is ordered before the first launch on the engine stream
+            E._pre()
         ctx = torch.cuda.stream(E.stream) if self._gpu else contextlib.nullcontext()
         sampling = bool(self.faces) or bool(self.probe_names)
         with ctx:
@@ -448,29 +518,10 @@ class Simulation:
                                            dft=(dft[p, :, 0] + 1j * dft[p, :, 1]) if len(self.probe_freqs) else None)
             res["probe_freqs"] = self.probe_freqs
         if self.faces:
-            nf = len(self.nf2ff_freqs)
-            full = []
-            for F in self.faces:
-                na, nb = F["a1"] - F["a0"] + 1, F["b1"] - F["b0"] + 1
-                full.append(np.zeros((4, nf, nb, na), np.complex128))
-            for q, L in enumerate(self.local_faces):
-                acc = _np(E.face_acc[q]).astype(np.float64)
-                acc = acc[..., 0] + 1j * acc[..., 1]
-                F = self.faces[L["face"]]
-                n = F["normal"]; a = (n + 1) % 3
-                if n == 2:
-                    full[L["face"]][...] = acc
-                elif a == 2:      # a-axis is z
-                    o = L["z_off"]; full[L["face"]][:, :, :, o:o + acc.shape[3]] = acc
-                else:             # b-axis is z
-                    o = L["z_off"]; full[L["face"]][:, :, o:o + acc.shape[2], :] = acc
-            if self.world > 1:
-                full = [self._allreduce_np(np.stack([f.real, f.imag], -1)) for f in full]
-                full = [f[..., 0] + 1j * f[..., 1] for f in full]
-            scale = 2.0 * self.interval * self.dt          # single-sided pulse spectrum, like DFT_time2freq (App. A5/A6)
-            full = [f * scale for f in full]
+            full = self._assemble_faces(E.face_acc, len(self.nf2ff_freqs))
             res["nf2ff"] = dict(faces=self.faces, acc=full, freqs=self.nf2ff_freqs, mirrors=list(getattr(self.builder, "nf2ff_mirrors", [])),
-                                weights=[self.builder.face_weights(F) for F in self.faces])
+                                weights=[self.builder.face_weights(F) for F in self.faces],
+                                spectra_fn=self.nf2ff_spectra if getattr(self, "td_store", False) else None, extra={}, sources={})
         self.results = res
         return res
 

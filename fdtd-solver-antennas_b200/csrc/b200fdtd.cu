@@ -40,7 +40,7 @@ static int fail(const char* fmt, ...) {
     if (e_ != cudaSuccess) return fail("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 
 extern "C" const char* b200fdtd_last_error(void) { return g_err; }
-extern "C" int b200fdtd_version(void) { return 2; }
+extern "C" int b200fdtd_version(void) { return 3; }
 extern "C" int64_t b200fdtd_launch_count(void) { return g_launches.load(); }
 
 // ------------------------------------------------------------------------------------
@@ -73,6 +73,7 @@ struct VolumePlan {
 struct FaceDev {
     int normal, plane, a0, a1, b0, b1;
     float* acc;
+    float* td;                     // optional time-domain store [td_max][4][nb][na] (b200fdtd_set_nf2ff_td)
 };
 #define MAX_FACES 8
 struct FaceTable { int n; FaceDev f[MAX_FACES]; };
@@ -124,7 +125,7 @@ struct b200fdtd_ctx {
     // nf2ff
     FaceTable faces{}; int nf_nfreq = 0; double* nf_freqs = nullptr; int nf_interval = 0; double nf_dt = 0.0;
     float* inv_len[3] = {nullptr, nullptr, nullptr}; float* inv_dual[3] = {nullptr, nullptr, nullptr};
-    int nf_max_nodes = 0;
+    int nf_max_nodes = 0; int nf_td_max = 0;
     // energy
     double* d_partials = nullptr; int n_partials = 0; double* d_energy = nullptr;
     // graph
@@ -908,11 +909,11 @@ extern "C" int b200fdtd_set_nf2ff(b200fdtd_ctx* c, int nfaces, const b200fdtd_nf
             F.b0 < lo_b || F.b1 >= dims[b] || F.b0 > F.b1)
             return fail("NF2FF face %d outside the grid", q);
         FaceDev& D = c->faces.f[q];
-        D.normal = F.normal; D.plane = F.plane; D.a0 = F.a0; D.a1 = F.a1; D.b0 = F.b0; D.b1 = F.b1; D.acc = F.acc;
+        D.normal = F.normal; D.plane = F.plane; D.a0 = F.a0; D.a1 = F.a1; D.b0 = F.b0; D.b1 = F.b1; D.acc = F.acc; D.td = nullptr;
         const int nn = (F.a1 - F.a0 + 1) * (F.b1 - F.b0 + 1);
         if (nn > max_nodes) max_nodes = nn;
     }
-    c->nf_max_nodes = max_nodes; c->nf_nfreq = nfreq; c->nf_interval = interval; c->nf_dt = dt;
+    c->nf_max_nodes = max_nodes; c->nf_nfreq = nfreq; c->nf_interval = interval; c->nf_dt = dt; c->nf_td_max = 0;
     if (upload(&c->nf_freqs, freqs, nfreq, c->stream)) return 1;
     const float* il[3] = {ilx, ily, ilz}; const float* id[3] = {idx_, idy, idz};
     for (int a = 0; a < 3; ++a) {
@@ -923,6 +924,47 @@ extern "C" int b200fdtd_set_nf2ff(b200fdtd_ctx* c, int nfaces, const b200fdtd_nf
     if (!c->d_faces) CK(cudaMalloc((void**)&c->d_faces, sizeof(FaceTable)));
     CK(cudaMemcpyAsync(c->d_faces, &c->faces, sizeof(FaceTable), cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int b200fdtd_set_nf2ff_td(b200fdtd_ctx* c, int nfaces, float* const* td, int max_samples)
+{
+    if (!c) return fail("NULL ctx");
+    if (nfaces != c->faces.n) return fail("set_nf2ff_td: %d faces given, %d registered (call b200fdtd_set_nf2ff first)", nfaces, c->faces.n);
+    if (nfaces > 0 && (!td || max_samples < 1)) return fail("bad time-domain store arguments");
+    CK(cudaSetDevice(c->device));
+    drop_graph(c);
+    for (int q = 0; q < nfaces; ++q) {
+        if (!td[q] || ((uintptr_t)td[q] & 3)) return fail("time-domain store of face %d is NULL or misaligned", q);
+        c->faces.f[q].td = td[q];
+    }
+    c->nf_td_max = max_samples;
+    if (nfaces > 0) {
+        CK(cudaMemcpyAsync(c->d_faces, &c->faces, sizeof(FaceTable), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+extern "C" int b200fdtd_nf2ff_td_dft(b200fdtd_ctx* c, int face, int nfreq, const double* freqs, int nsamples, float* out)
+{
+    if (!c) return fail("NULL ctx");
+    if (face < 0 || face >= c->faces.n) return fail("face %d out of range", face);
+    const FaceDev& F = c->faces.f[face];
+    if (!F.td) return fail("no time-domain store bound for face %d (b200fdtd_set_nf2ff_td)", face);
+    if (nfreq < 1 || !freqs || !out) return fail("bad arguments");
+    if (nsamples < 0 || nsamples > c->nf_td_max) return fail("nsamples=%d outside the store (max %d)", nsamples, c->nf_td_max);
+    CK(cudaSetDevice(c->device));
+    double* d_f = nullptr;
+    CK(cudaMalloc((void**)&d_f, sizeof(double) * nfreq));
+    CK(cudaMemcpyAsync(d_f, freqs, sizeof(double) * nfreq, cudaMemcpyHostToDevice, c->stream));
+    const long long nn = (long long)(F.a1 - F.a0 + 1) * (F.b1 - F.b0 + 1);
+    nf2ff_td_dft_kernel<<<(unsigned)((4 * nn + 255) / 256), 256, 0, c->stream>>>(F.td, nn, nsamples, c->nf_interval, c->nf_dt, nfreq, d_f, out);
+    g_launches.fetch_add(1);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_f);
+    if (e != cudaSuccess) return fail("nf2ff_td_dft failed: %s", cudaGetErrorString(e));
     return 0;
 }
 
@@ -984,6 +1026,7 @@ static int launch_sampling(b200fdtd_ctx* c, int ts_off)
         P.volt = cur_volt(c); P.curr = cur_curr(c); P.ny = c->ny; P.px = c->px; P.sz = c->sz; P.cs = c->cs;
         for (int a = 0; a < 3; ++a) { P.il[a] = c->inv_len[a]; P.idl[a] = c->inv_dual[a]; }
         P.nfreq = c->nf_nfreq; P.freqs = c->nf_freqs; P.dt = c->nf_dt; P.d_ts = c->d_ts; P.ts_off = ts_off;
+        P.interval = c->nf_interval; P.td_max = c->nf_td_max;
         dim3 grid((c->nf_max_nodes + 127) / 128, c->faces.n);
         nf2ff_kernel<<<grid, 128, sizeof(float) * 4 * c->nf_nfreq, c->stream>>>(c->d_faces, P);
         CKL();
@@ -1437,16 +1480,19 @@ extern "C" int b200fdtd_farfield(int device, void* stream, int64_t npts, const f
     if (npts <= 0 || ndir <= 0 || !pos || !J || !M || !theta || !phi || !out) return fail("bad far-field arguments");
     CK(cudaSetDevice(device));
     cudaStream_t s = (cudaStream_t)stream;
-    double *d_th = nullptr, *d_ph = nullptr;
-    CK(cudaMalloc((void**)&d_th, sizeof(double) * ndir));
-    CK(cudaMalloc((void**)&d_ph, sizeof(double) * ndir));
-    CK(cudaMemcpyAsync(d_th, theta, sizeof(double) * ndir, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(d_ph, phi, sizeof(double) * ndir, cudaMemcpyHostToDevice, s));
-    farfield_kernel<<<ndir, 256, 0, s>>>(npts, pos, J, M, k, ndir, d_th, d_ph, out);
-    g_launches.fetch_add(1);
-    cudaError_t e = cudaGetLastError();
-    cudaStreamSynchronize(s);
-    cudaFree(d_th); cudaFree(d_ph);
-    if (e != cudaSuccess) return fail("farfield launch failed: %s", cudaGetErrorString(e));
+    // direction buffer of the calling thread, grown on demand and kept (the reference calls CalcNF2FF once per phi: 73 calls)
+    static thread_local double* d_dir = nullptr; static thread_local int d_cap = 0, d_dev = -1;
+    if (d_dev != device || d_cap < ndir) {
+        if (d_dir && d_dev >= 0) { cudaSetDevice(d_dev); cudaFree(d_dir); cudaSetDevice(device); }
+        d_dir = nullptr; d_cap = 0; d_dev = device;
+        const int cap = ndir < 8192 ? 8192 : ndir;
+        CK(cudaMalloc((void**)&d_dir, sizeof(double) * 2 * cap));
+        d_cap = cap;
+    }
+    CK(cudaMemcpyAsync(d_dir, theta, sizeof(double) * ndir, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_dir + d_cap, phi, sizeof(double) * ndir, cudaMemcpyHostToDevice, s));
+    farfield_kernel<<<ndir, 256, 0, s>>>(npts, pos, J, M, k, ndir, d_dir, d_dir + d_cap, out);
+    CKL();
+    CK(cudaStreamSynchronize(s));                 // theta/phi are pageable host arrays of the caller
     return 0;
 }

@@ -113,6 +113,7 @@ struct Nf2ffParams {
     const float* il[3]; const float* idl[3];     // inverse primal / dual edge lengths (z arrays offset by one entry)
     int nfreq; const double* freqs; double dt;
     const int* d_ts; int ts_off;
+    int interval, td_max;                        // time-domain store: sample s = ts/interval - 1 goes to td[s] if s < td_max
 };
 __global__ void __launch_bounds__(128) nf2ff_kernel(const FaceTable* __restrict__ tab, const Nf2ffParams P)
 {
@@ -147,6 +148,14 @@ __global__ void __launch_bounds__(128) nf2ff_kernel(const FaceTable* __restrict_
     const float Hb = 0.25f * P.idl[b][ib + ob] *
         ((cb[lin0] + cb[lin0 - st[a]]) + (cb[lin0 - st[n]] + cb[lin0 - st[a] - st[n]]));
     const float v[4] = {Ea, Eb, Ha, Hb};
+    if (F.td != nullptr) {                         // what openEMS writes to nf2ff_E/H_n.h5: the samples themselves
+        const int s = ts / P.interval - 1;
+        if (s >= 0 && s < P.td_max) {
+            float* d = F.td + (long long)s * 4 * nn + node;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) __stcs(d + c * nn, v[c]);
+        }
+    }
     float2* acc = reinterpret_cast<float2*>(F.acc);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -158,6 +167,44 @@ __global__ void __launch_bounds__(128) nf2ff_kernel(const FaceTable* __restrict_
             t.y = __fmaf_rn(-v[c], sn, t.y);
             *d = t;
         }
+    }
+}
+
+// K8b NF2FF at any frequency after the run: DFT of the stored face samples (openEMS's nf2ff reads its time-domain HDF5 dumps
+// and does the same).  One thread per (component, node); twiddles of a chunk of samples are formed once per block in fp64
+// and shared; accumulation in fp64.  td [ns][4][nn] f32, out [4][nfreq][nn][2] f32 (the layout of the running-DFT accumulators).
+#define TD_CHUNK 128
+__global__ void __launch_bounds__(256) nf2ff_td_dft_kernel(const float* __restrict__ td, long long nn, int ns, int interval, double dt,
+        int nfreq, const double* __restrict__ freqs, float* __restrict__ out)
+{
+    __shared__ float2 tw[2][TD_CHUNK];             // [E | H time stamps][sample] = (cos, sin)
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // over 4*nn
+    const bool ok = q < 4 * nn;
+    const int c = ok ? (int)(q / nn) : 0;
+    const int hs = c >= 2 ? 1 : 0;
+    for (int f = 0; f < nfreq; ++f) {
+        double re = 0.0, im = 0.0;
+        for (int s0 = 0; s0 < ns; s0 += TD_CHUNK) {
+            __syncthreads();
+            for (int t = threadIdx.x; t < 2 * TD_CHUNK; t += blockDim.x) {
+                const int s = s0 + (t % TD_CHUNK), h = t / TD_CHUNK;
+                const double tm = ((double)(s + 1) * interval + (h ? 0.5 : 0.0)) * dt;
+                double ph = freqs[f] * tm; ph -= floor(ph);
+                double sn, cn; sincospi(2.0 * ph, &sn, &cn);
+                tw[h][t % TD_CHUNK] = make_float2((float)cn, (float)sn);
+            }
+            __syncthreads();
+            if (ok) {
+                const int m = min(TD_CHUNK, ns - s0);
+                const float* src = td + (long long)s0 * 4 * nn + q;
+                for (int s = 0; s < m; ++s) {
+                    const float v = __ldcs(src + (long long)s * 4 * nn);
+                    const float2 w = tw[hs][s];
+                    re += (double)(v * w.x); im -= (double)(v * w.y);
+                }
+            }
+        }
+        if (ok) reinterpret_cast<float2*>(out)[((long long)c * nfreq + f) * nn + (q - (long long)c * nn)] = make_float2((float)re, (float)im);
     }
 }
 
@@ -205,13 +252,15 @@ __global__ void __launch_bounds__(256) farfield_kernel(long long npts, const flo
     if (d >= ndir) return;
     double st, ct, sp, cp;
     sincos(theta[d], &st, &ct); sincos(phi[d], &sp, &cp);
-    const float ux = (float)(k * st * cp), uy = (float)(k * st * sp), uz = (float)(k * ct);
+    // phase in turns, formed and reduced in fp64 (k r can be hundreds of radians on a large box), then one fp32 sincospi
+    const double ux = k * st * cp * 0.15915494309189535, uy = k * st * sp * 0.15915494309189535, uz = k * ct * 0.15915494309189535;
     double a[12];
 #pragma unroll
     for (int i = 0; i < 12; ++i) a[i] = 0.0;
     for (long long q = threadIdx.x; q < npts; q += blockDim.x) {
-        const float ph = ux * pos[q] + uy * pos[npts + q] + uz * pos[2 * npts + q];
-        float sn, cn; sincosf(ph, &sn, &cn);
+        double tn = ux * (double)pos[q] + uy * (double)pos[npts + q] + uz * (double)pos[2 * npts + q];
+        tn -= rint(tn);
+        float sn, cn; sincospif(2.0f * (float)tn, &sn, &cn);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const float jr = J[(c * npts + q) * 2], ji = J[(c * npts + q) * 2 + 1];

@@ -6,9 +6,16 @@ _RESULTS = {}
 _LOCK = threading.Lock()
 
 
+MAX_KEPT = 4        # a result keeps device memory alive (DFT accumulators, stored NF2FF face samples): only the latest runs
+
+
 def store(sim_path, res):
     with _LOCK:
-        _RESULTS[os.path.abspath(str(sim_path))] = res
+        key = os.path.abspath(str(sim_path))
+        _RESULTS.pop(key, None)
+        _RESULTS[key] = res
+        while len(_RESULTS) > MAX_KEPT:
+            _RESULTS.pop(next(iter(_RESULTS)))
 
 
 def results_for(sim_path, fdtd=None):

@@ -60,6 +60,7 @@ class openEMS:
         self.device = int(os.environ.get("B200FDTD_DEVICE", os.environ.get("LOCAL_RANK", "0")))
         self.port_dft_freqs = None
         self.nf2ff_freqs = None
+        self.nf2ff_td = None          # None: keep the NF2FF face samples in HBM if they fit (far field at any frequency); False: never
         self.engine_factory = type(self).default_engine_factory
         self.farfield_fn = type(self).default_farfield_fn
 
@@ -211,7 +212,7 @@ class openEMS:
         log = (lambda msg: (print(msg), sys.stdout.flush())) if verbose else None
         sim = Simulation(S, device=self.device, rank=rank, world=world, group=group, engine_factory=self.engine_factory,
                          log=log, nf2ff_freqs=self.nf2ff_freqs, probe_freqs=S.probe_freqs,
-                         fused_multi=getattr(self, "fused_multi", True))
+                         fused_multi=getattr(self, "fused_multi", True), nf2ff_td=self.nf2ff_td)
         sim.prepare()
         self.sim = sim
         if verbose and rank == 0:

@@ -144,6 +144,16 @@ int b200fdtd_set_nf2ff(b200fdtd_ctx* ctx, int nfaces, const b200fdtd_nf2ff_face*
                        const float* inv_len_x, const float* inv_len_y, const float* inv_len_z,
                        const float* inv_dual_x, const float* inv_dual_y, const float* inv_dual_z);
 
+/* Time-domain store of the face samples (optional; what openEMS dumps to nf2ff_E_n.h5 / nf2ff_H_n.h5 and CalcNF2FF reads
+ * back, so that the far field can be asked for at ANY frequency after the run: …microstrip_3d.py:225 passes the caller's
+ * frequency_hz).  td[q] = dev [max_samples][4][nb][na] f32 for face q of the last b200fdtd_set_nf2ff (same order); sample
+ * s is taken at step (s+1)*interval.  The running DFT at the registered frequencies continues unchanged. */
+int b200fdtd_set_nf2ff_td(b200fdtd_ctx* ctx, int nfaces, float* const* td /*host array of dev pointers*/, int max_samples);
+/* DFT of the first `nsamples` stored samples of one face at nfreq frequencies (host array):
+ * out = dev [4][nfreq][nb][na][2] f32, the layout and scaling of the running-DFT accumulators (sum x(t) exp(-j 2 pi f t),
+ * E stamped ts*dt, H stamped (ts+1/2)*dt).  Synchronises the stream. */
+int b200fdtd_nf2ff_td_dft(b200fdtd_ctx* ctx, int face, int nfreq, const double* freqs /*host*/, int nsamples, float* out);
+
 /* ---- time stepping (FDTD.Run, …microstrip_3d.py:214) ---------------------------- */
 /* current time-step counter (number of completed steps) */
 int b200fdtd_get_timestep(b200fdtd_ctx* ctx, int64_t* ts);

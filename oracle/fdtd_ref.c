@@ -44,6 +44,8 @@ typedef struct {
 typedef struct {
     int32_t normal, plane, a0, a1, b0, b1;
     double* acc;                 /* [4][nfreq][nb][na][2] double */
+    float* td;                   /* optional time-domain store [td_max][4][nb][na] (openEMS: nf2ff_E/H_n.h5 dumps) */
+    int32_t td_max;
 } ref_face;
 
 typedef struct {
@@ -225,6 +227,21 @@ void ref_nf2ff(ref_engine* e)
         const int oa = (a == 2), ob = (b == 2);
         const float* va = e->volt + a * cs; const float* vb = e->volt + b * cs;
         const float* ca = e->curr + a * cs; const float* cb = e->curr + b * cs;
+        const int64_t smp = e->ts / e->interval - 1;
+        if (F->td && smp >= 0 && smp < F->td_max) {
+            /* the dump itself: fp32 node-interpolated samples, formed in fp32 exactly like the CUDA kernel forms them */
+            for (int ib = F->b0; ib <= F->b1; ++ib)
+                for (int ia = F->a0; ia <= F->a1; ++ia) {
+                    int co[3]; co[n] = F->plane; co[a] = ia; co[b] = ib;
+                    const int64_t l0 = (int64_t)(co[2] + 1) * sz + (int64_t)co[1] * px + co[0];
+                    const int64_t node = (int64_t)(ib - F->b0) * na + (ia - F->a0);
+                    float* d = F->td + smp * 4 * nn + node;
+                    d[0] = 0.5f * (va[l0] * e->inv_len[a][ia + oa] + va[l0 - st[a]] * e->inv_len[a][ia + oa - 1]);
+                    d[nn] = 0.5f * (vb[l0] * e->inv_len[b][ib + ob] + vb[l0 - st[b]] * e->inv_len[b][ib + ob - 1]);
+                    d[2 * nn] = 0.25f * e->inv_dual[a][ia + oa] * ((ca[l0] + ca[l0 - st[b]]) + (ca[l0 - st[n]] + ca[l0 - st[b] - st[n]]));
+                    d[3 * nn] = 0.25f * e->inv_dual[b][ib + ob] * ((cb[l0] + cb[l0 - st[a]]) + (cb[l0 - st[n]] + cb[l0 - st[a] - st[n]]));
+                }
+        }
         for (int q = 0; q < e->nf_nfreq; ++q) {
             double cE, sE, cH, sH;
             twiddle(e->nf_freqs[q], (double)e->ts * e->dt, &cE, &sE);

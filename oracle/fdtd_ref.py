@@ -32,7 +32,7 @@ class _PmlBox(C.Structure):
 
 class _Face(C.Structure):
     _fields_ = [("normal", C.c_int32), ("plane", C.c_int32), ("a0", C.c_int32), ("a1", C.c_int32),
-                ("b0", C.c_int32), ("b1", C.c_int32), ("acc", c_d)]
+                ("b0", C.c_int32), ("b1", C.c_int32), ("acc", c_d), ("td", c_f), ("td_max", C.c_int32)]
 
 
 class _Engine(C.Structure):
@@ -203,6 +203,35 @@ class RefEngine:
         for a in range(3):
             e.inv_len[a] = _p(k["il"][a], c_f); e.inv_dual[a] = _p(k["idl"][a], c_f)
         e.interval = int(interval); e.dt = float(dt)
+
+    def set_nf2ff_td(self, max_samples):
+        """time-domain store of the face samples (mirrors b200fdtd_set_nf2ff_td)"""
+        arr = self._keep["faces"]
+        self.face_td = [np.zeros((int(max_samples), 4) + acc.shape[2:4], np.float32) for acc in self.face_acc]
+        self.td_max = int(max_samples)
+        for q, t in enumerate(self.face_td):
+            arr[q].td = _p(t, c_f); arr[q].td_max = int(max_samples)
+        return sum(t.nbytes for t in self.face_td)
+
+    def nf2ff_td_dft(self, freqs, nsamples):
+        """double-precision DFT of the stored samples (mirrors b200fdtd_nf2ff_td_dft): list of [4][nfreq][nb][na][2]"""
+        freqs = np.atleast_1d(np.asarray(freqs, np.float64))
+        ns = int(min(nsamples, self.td_max))
+        iv, dt = int(self.e.interval), float(self.e.dt)
+        s = np.arange(1, ns + 1, dtype=np.float64) * iv
+        out = []
+        for t in self.face_td:
+            o = np.zeros((4, len(freqs)) + t.shape[2:4] + (2,), np.float64)
+            x = t[:ns].astype(np.float64)
+            for fi, f in enumerate(freqs):
+                for c in range(4):
+                    tm = (s + (0.5 if c >= 2 else 0.0)) * dt
+                    ph = f * tm; ph -= np.floor(ph)
+                    w = np.exp(-2j * np.pi * ph)
+                    z = np.tensordot(w, x[:, c], axes=(0, 0))
+                    o[c, fi, ..., 0] = z.real; o[c, fi, ..., 1] = z.imag
+            out.append(o)
+        return out
 
     # --- stepping ---
     def run(self, nsteps, use_graph=False):

@@ -161,6 +161,23 @@ def main():
                theta=prep.theta.tolist(), phi=prep.phi.tolist(), nf_center=np.asarray(prep.nf_center).tolist())
     json.dump(out, open(os.path.join(HERE, "trace_multi2_mur_q2.json"), "w"))
     print("trace_multi2_mur_q2", len(Rec._log), "calls")
+    # BASELINE.json configs[2]: 4x4 array of PatchInstances (multi_patch_designer.py:18-28), pitch 60 mm (~ lambda0/2), all
+    # elements fed from -x; quality 1 + MUR for the parity tests, quality 4 + PML_8 as the base of the ~1 B-cell bench mesh
+    for name, bc, q in (("trace_array16_mur_q1", "MUR", 1), ("trace_array16_pml8_q4", "PML_8", 4)):
+        saved = install_mocks()
+        try:
+            pitch = 0.060
+            patches = [PatchInstance(f"P{r}{c}", P, center_x_m=(c - 1.5) * pitch, center_y_m=(r - 1.5) * pitch, feed_direction=FD.NEG_X)
+                       for r in range(4) for c in range(4)]
+            prep = m["solver_fdtd_openems_microstrip_multi_3d"].prepare_openems_microstrip_multi_3d(
+                patches, dll_dir=refload.DLL_DIR, boundary=bc, mesh_quality=q, theta_step_deg=5.0, phi_step_deg=15.0)
+        finally:
+            restore(saved)
+        assert prep.ok, prep.message
+        out = dict(case=name, log=Rec._log, fdtd=prep.FDTD._id, nf=prep.nf._id,
+                   theta=prep.theta.tolist(), phi=prep.phi.tolist(), nf_center=np.asarray(prep.nf_center).tolist())
+        json.dump(out, open(os.path.join(HERE, name + ".json"), "w"))
+        print(name, len(Rec._log), "calls")
 
 
 if __name__ == "__main__":

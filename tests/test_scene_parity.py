@@ -105,15 +105,6 @@ def test_config4_broadband_multi_frequency():
         assert np.abs(20 * np.log10(ec[sel] / eo[sel])).max() <= GAIN_TOL_DB
 
 
-def test_calcnf2ff_rejects_unregistered_frequency():
-    scenes.use_cuda_engine()
-    F, nf, port = scenes.dipole("MUR", cells=(16, 16, 20), nrts=60, end=1e-12)
-    path = scenes.tmp_sim_path("unreg")
-    F.Run(path, cleanup=True)
-    with pytest.raises(ValueError):
-        nf.CalcNF2FF(path, 7.77e9, np.array([0.0]), np.array([0.0]))
-
-
 def test_compressed_operator_host_round_trip():
     """export the operator in its compressed host form, wipe the device arrays, reload: bit-identical arrays,
     no row demoted, and a run from the reloaded operator equals the oracle"""
