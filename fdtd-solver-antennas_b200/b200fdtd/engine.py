@@ -218,6 +218,20 @@ class Engine:
         self._post()
         return out
 
+    def reset_state(self):
+        """fields, PML flux, probe series / DFT and NF2FF accumulators back to zero, step counter to 0 (a new run of the same scene)"""
+        self._pre()
+        with torch.cuda.stream(self.stream):
+            for t in (self.volt, self.curr, getattr(self, "volt2", None), getattr(self, "curr2", None), self.series, self.probe_dft):
+                if t is not None:
+                    t.zero_()
+            for d in self._keep.get("pml", []):
+                d["flux_v"].zero_(); d["flux_i"].zero_()
+            for t in list(self.face_acc) + list(getattr(self, "face_td", [])):
+                t.zero_()
+        self.set_timestep(0)
+        self._post()
+
     # ---- stepping ----
     def _pre(self):
         self.stream.wait_stream(torch.cuda.current_stream(self.device))

@@ -154,6 +154,7 @@ class Simulation:
         if boxes:
             E.set_pml(boxes)
         # probes
+        self.nrts_sized = s.nrts
         self.max_samples = s.nrts // self.interval + 2
         self.probe_names, kinds, offs, idxs, ws = [], [], [0], [], []
         for (name, kind, comp, i, j, k, w) in B.probe_lists():
@@ -315,6 +316,25 @@ class Simulation:
                     arr[idx[:, 0], idx[:, 1]] = H["full_rows"][slot].to(dev, non_blocking=True)
             res[which] = E.set_row_compression(which, xv, meta)
         return res
+
+    def keep_host_operator(self):
+        """FDTD.Run(setup_only=True): keep the operator on the HOST in the form the host builder produces it (pinned), so a later
+        Run of the same scene ships it to the device instead of rebuilding it"""
+        if hasattr(self.engine, "expand_rows") and all(f"cmp{w}" in self.engine._keep for w in (0, 1)):
+            self.host_op = self.export_operator(pin=True)
+        return self
+
+    def restart(self):
+        """a new run of the prepared scene: operator host -> device (if a host copy is kept), all state back to zero"""
+        E = self.engine
+        self.reloaded = None
+        if getattr(self, "host_op", None) is not None:
+            self.reloaded = self.load_operator(self.host_op)
+        E.reset_state()
+        if getattr(self, "_tv", None) is not None:
+            self._vcur = self._ccur = 0
+        self.results = None
+        return self
 
     # ------------------------------------------------------------------ halo exchange (z-slabs)
     # Data dependence (SURVEY.md §8e): the E update of my plane 0 reads (Hx,Hy) of the lower neighbour's top plane;

@@ -1201,8 +1201,10 @@ extern "C" int b200fdtd_run(b200fdtd_ctx* c, int64_t nsteps, int use_graph)
     CK(cudaSetDevice(c->device));
     if (!c->plan.valid) if (build_plan(c)) return 1;        // never inside a stream capture
     c->he_fused = false;
-    if (!use_graph || c->stream == nullptr) return run_eager(c, nsteps);   // the NULL stream cannot be captured
     const int iv = sample_interval(c);
+    // the NULL stream cannot be captured; a sampling interval of thousands of steps (tiny cells -> tiny time step) is not
+    // worth a graph of that many nodes
+    if (!use_graph || c->stream == nullptr || iv > 4096) return run_eager(c, nsteps);
     const int chunk = iv > 0 ? iv : 16;
     int64_t left = nsteps;
     // align to a chunk boundary

@@ -56,6 +56,7 @@ class openEMS:
         self.nf2ff_boxes = []
         self.results = None
         self.sim = None
+        self._prepared = None         # (scene key, Simulation) left by Run(setup_only=True)
         # engine options of the shim (not part of openEMS): GPU index, frequency lists for the running DFTs
         self.device = int(os.environ.get("B200FDTD_DEVICE", os.environ.get("LOCAL_RANK", "0")))
         self.port_dft_freqs = None
@@ -193,6 +194,32 @@ class openEMS:
                          else np.linspace(max(f0 - fc, 0.0), f0 + fc, 201))
         return S
 
+    def _scene_key(self, S, world):
+        """fingerprint of everything the operator and the run length depend on (a prepared set-up is reused only for this scene)"""
+        import hashlib
+        h = hashlib.sha1()
+        for l in S.lines:
+            h.update(np.ascontiguousarray(l, np.float64).tobytes())
+        def box(p):
+            t = p.prim.GetTransform()
+            tr = b"" if t is None else np.ascontiguousarray(t.M, np.float64).tobytes() + np.ascontiguousarray(t.t, np.float64).tobytes()
+            return (np.ascontiguousarray(p.prim.start, np.float64).tobytes() + np.ascontiguousarray(p.prim.stop, np.float64).tobytes() + tr)
+        for m in S.materials:
+            h.update(repr((m["eps"], m["kappa"], m["priority"], m["order"])).encode() + box(m["prim"]))
+        for m in S.metals:
+            h.update(repr((m["priority"], m["order"])).encode() + box(m["prim"]))
+        for m in S.lumped:
+            h.update(repr((m["ny"], m["R"], m["caps"], np.asarray(m["lo"]).tolist(), np.asarray(m["hi"]).tolist())).encode())
+        for m in S.excitations:
+            h.update(repr((np.asarray(m["vec"]).tolist(), m["delay"], np.asarray(m["lo"]).tolist(), np.asarray(m["hi"]).tolist())).encode())
+        for m in S.probes:
+            h.update(repr((m["name"], m["p_type"], m["weight"], m["norm_dir"], np.asarray(m["start"]).tolist(), np.asarray(m["stop"]).tolist())).encode())
+        nf = None if not S.nf2ff else (np.asarray(S.nf2ff["start"]).tolist(), np.asarray(S.nf2ff["stop"]).tolist(), repr(S.nf2ff.get("frequency")))
+        h.update(repr((S.bc, S.pml_cells, S.f0, S.fc, S.timestep_factor, S.oversampling, nf, world, self.device,
+                       None if self.nf2ff_freqs is None else np.asarray(self.nf2ff_freqs).tolist(),
+                       np.asarray(S.probe_freqs).tolist(), repr(self.nf2ff_td), id(self.engine_factory))).encode())
+        return h.hexdigest()
+
     # ---- the hot path ----
     def Run(self, sim_path, cleanup=False, setup_only=False, debug_material=False, debug_pec=False, debug_operator=False,
             debug_boxes=False, debug_csx=False, verbose=None, **kw):
@@ -210,10 +237,20 @@ class openEMS:
         except Exception:
             pass
         log = (lambda msg: (print(msg), sys.stdout.flush())) if verbose else None
-        sim = Simulation(S, device=self.device, rank=rank, world=world, group=group, engine_factory=self.engine_factory,
-                         log=log, nf2ff_freqs=self.nf2ff_freqs, probe_freqs=S.probe_freqs,
-                         fused_multi=getattr(self, "fused_multi", True), nf2ff_td=self.nf2ff_td)
-        sim.prepare()
+        key = self._scene_key(S, world)
+        if self._prepared is not None and self._prepared[0] == key and S.nrts <= self._prepared[1].nrts_sized:
+            # the scene was set up before (Run(..., setup_only=True)): ship the kept host operator to the device, reset the state
+            # (buffers and the excitation signal were sized for at least this many steps)
+            sim = self._prepared[1]
+            sim.log = log or (lambda *a: None)
+            sim.setup.nrts, sim.setup.end_criteria = S.nrts, S.end_criteria
+            sim.restart()
+        else:
+            self._prepared = None
+            sim = Simulation(S, device=self.device, rank=rank, world=world, group=group, engine_factory=self.engine_factory,
+                             log=log, nf2ff_freqs=self.nf2ff_freqs, probe_freqs=S.probe_freqs,
+                             fused_multi=getattr(self, "fused_multi", True), nf2ff_td=self.nf2ff_td)
+            sim.prepare()
         self.sim = sim
         if verbose and rank == 0:
             nx, ny, nz = sim.nx, sim.ny, sim.nz_glob
@@ -221,6 +258,7 @@ class openEMS:
                   f"Nyquist {sim.nyquist} TS, excitation {sim.exc_len} TS, max {S.nrts} TS, "
                   f"{world} GPU(s); operator build {sim.prepare_s:.2f} s")
         if setup_only:
+            self._prepared = (key, sim.keep_host_operator())
             return
         sim.run(verbose=verbose)
         res = sim.results

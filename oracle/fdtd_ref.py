@@ -233,6 +233,16 @@ class RefEngine:
             out.append(o)
         return out
 
+    def reset_state(self):
+        for a in [self.volt, self.curr, self.series, self.probe_dft] + list(self.face_acc) + list(getattr(self, "face_td", [])):
+            a[...] = 0
+        if "pml" in self._keep:
+            for d in self._keep["pml"][1]:
+                d["flux_v"][...] = 0; d["flux_i"][...] = 0
+        if "mur_tmp" in self._keep:
+            self._keep["mur_tmp"][...] = 0
+        self.e.ts = 0
+
     # --- stepping ---
     def run(self, nsteps, use_graph=False):
         lib().ref_run(C.byref(self.e), int(nsteps))

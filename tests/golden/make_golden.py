@@ -8,6 +8,12 @@
       …multi_3d.py:98-593), captured with recording stand-ins.  tests replay these against the shim, so the
       GPU box (which has no /root/reference) still drives the shim with the reference's own inputs.
 
+3. run_prepared_*.npz — OUTPUTS of the UNMODIFIED live run functions (run_prepared_openems_microstrip_3d,
+      …microstrip_3d.py:199-256; run_prepared_openems_microstrip_multi_3d, …multi_3d.py:596-663) executed here on the shim
+      with the CPU oracle engine, at a frequency_hz that differs from the design frequency (2.40 GHz vs f0 = 2.45 GHz),
+      time steps cut to keep the fixture run short.  The GPU box replays the same scene on the CUDA engine and must
+      reproduce these dBi grids (tests/test_scene_parity.py::test_unmodified_run_prepared_outputs).
+
 Usage:  python tests/golden/make_golden.py
 """
 import json
@@ -162,8 +168,8 @@ def main():
     json.dump(out, open(os.path.join(HERE, "trace_multi2_mur_q2.json"), "w"))
     print("trace_multi2_mur_q2", len(Rec._log), "calls")
     # BASELINE.json configs[2]: 4x4 array of PatchInstances (multi_patch_designer.py:18-28), pitch 60 mm (~ lambda0/2), all
-    # elements fed from -x; quality 1 + MUR for the parity tests, quality 4 + PML_8 as the base of the ~1 B-cell bench mesh
-    for name, bc, q in (("trace_array16_mur_q1", "MUR", 1), ("trace_array16_pml8_q4", "PML_8", 4)):
+    # elements fed from -x; quality 1 + MUR for the parity tests, quality 2 + PML_8 as the base of the ~1 B-cell bench mesh
+    for name, bc, q in (("trace_array16_mur_q1", "MUR", 1), ("trace_array16_pml8_q2", "PML_8", 2)):
         saved = install_mocks()
         try:
             pitch = 0.060
@@ -180,5 +186,47 @@ def main():
         print(name, len(Rec._log), "calls")
 
 
+RUN_PREPARED_F = 2.40e9
+RUN_PREPARED_STEPS = {"single_mur_q1": 3000, "multi2_mur_q2": 1200}
+
+
+def run_prepared_outputs():
+    """the unmodified run_prepared_* functions on the real shim + oracle engine -> tests/golden/run_prepared_*.npz"""
+    root = os.path.dirname(os.path.dirname(HERE))
+    for p_ in (root, os.path.join(root, "fdtd-solver-antennas_b200")):
+        if p_ not in sys.path:
+            sys.path.insert(0, p_)
+    import scenes
+    scenes.use_oracle_engine(threads=os.cpu_count() or 4)
+    m = refload.load()
+    P = m["models"].PatchAntennaParams.from_user_units(frequency_ghz=2.45, er=4.3, h_mm=1.6, loss_tangent=0.02, metal="copper")
+    FD = m["solver_fdtd_openems_microstrip"].FeedDirection
+    s3, sm = m["solver_fdtd_openems_microstrip_3d"], m["solver_fdtd_openems_microstrip_multi_3d"]
+    prep = s3.prepare_openems_microstrip_patch_3d(P, dll_dir=refload.DLL_DIR, boundary="MUR", mesh_quality=1, feed_direction=FD.NEG_X,
+                                                  theta_step_deg=2.0, phi_step_deg=5.0)
+    assert prep.ok, prep.message
+    prep.FDTD.SetNumberOfTimeSteps(RUN_PREPARED_STEPS["single_mur_q1"])
+    res = s3.run_prepared_openems_microstrip_3d(prep, frequency_hz=RUN_PREPARED_F, verbose=0)
+    assert res.ok, res.message
+    np.savez_compressed(os.path.join(HERE, "run_prepared_single_mur_q1.npz"), intensity=res.intensity.astype(np.float32),
+                        theta=res.theta, phi=res.phi, frequency_hz=RUN_PREPARED_F, steps=prep.FDTD.sim.timesteps)
+    print("run_prepared_single_mur_q1", res.intensity.shape, float(res.intensity.max()), prep.FDTD.sim.timesteps, prep.FDTD.sim.stop_reason)
+    patches = [PatchInstance("P1", P, center_x_m=-0.035, feed_direction=FD.NEG_X),
+               PatchInstance("P2", P, center_x_m=0.035, rot_z_deg=90.0, feed_direction=FD.NEG_X)]
+    prep = sm.prepare_openems_microstrip_multi_3d(patches, dll_dir=refload.DLL_DIR, boundary="MUR", mesh_quality=2,
+                                                  theta_step_deg=5.0, phi_step_deg=15.0)
+    assert prep.ok, prep.message
+    prep.FDTD.SetNumberOfTimeSteps(RUN_PREPARED_STEPS["multi2_mur_q2"])
+    prep.FDTD.SetEndCriteria(1e-30)
+    res = sm.run_prepared_openems_microstrip_multi_3d(prep, frequency_hz=RUN_PREPARED_F, verbose=0)
+    assert res.ok, res.message
+    np.savez_compressed(os.path.join(HERE, "run_prepared_multi2_mur_q2.npz"), intensity=res.intensity.astype(np.float32),
+                        theta=res.theta, phi=res.phi, frequency_hz=RUN_PREPARED_F, steps=prep.FDTD.sim.timesteps)
+    print("run_prepared_multi2_mur_q2", res.intensity.shape, float(res.intensity.max()), prep.FDTD.sim.timesteps)
+    scenes.use_cuda_engine()
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) < 2 or sys.argv[1] != "outputs":
+        main()
+    run_prepared_outputs()

@@ -128,3 +128,55 @@ def test_sibling_callers_run_unmodified_end_to_end():
             assert res.intensity is not None and np.all(np.isfinite(np.asarray(res.intensity)))
     finally:
         scenes.use_cuda_engine()
+
+
+@pytest.mark.skipif(not refload.available(), reason="reference tree not present (GPU box)")
+def test_live_run_prepared_functions_run_unmodified(tmp_path, monkeypatch):
+    """SURVEY.md §8 a2/a3: the two LIVE run functions (run_prepared_openems_microstrip_3d, …microstrip_3d.py:199-256;
+    run_prepared_openems_microstrip_multi_3d, …multi_3d.py:596-663) executed unmodified on the shim, at the design
+    frequency and at a frequency_hz that was never registered (2.40 GHz; served from the stored NF2FF face samples).
+    They must return ok=True and exactly what the test-side restatement of their loop (replay.reference_postprocess,
+    used by the GPU parity tests) returns; the committed fixtures run_prepared_*.npz are outputs of these same calls."""
+    import scenes
+    from dataclasses import dataclass
+    monkeypatch.chdir(tmp_path)                       # the reference creates its sim_path relative to the cwd
+    scenes.use_oracle_engine(threads=os.cpu_count() or 4)
+    try:
+        m = refload.load()
+        P = m["models"].PatchAntennaParams.from_user_units(frequency_ghz=2.45, er=4.3, h_mm=1.6, loss_tangent=0.02, metal="copper")
+        FD = m["solver_fdtd_openems_microstrip"].FeedDirection
+        s3, sm = m["solver_fdtd_openems_microstrip_3d"], m["solver_fdtd_openems_microstrip_multi_3d"]
+        prep = s3.prepare_openems_microstrip_patch_3d(P, dll_dir=refload.DLL_DIR, boundary="MUR", mesh_quality=1, feed_direction=FD.NEG_X,
+                                                      theta_step_deg=10.0, phi_step_deg=45.0)
+        assert prep.ok, prep.message
+        prep.FDTD.SetNumberOfTimeSteps(1500)
+        for f in (P.frequency_hz, 2.40e9):
+            res = s3.run_prepared_openems_microstrip_3d(prep, frequency_hz=f, verbose=0)
+            assert res.ok, res.message
+            assert res.is_dBi and res.intensity.shape == (len(prep.theta), len(prep.phi)) and np.isfinite(res.intensity).all()
+            dbi, dmax = replay.reference_postprocess(prep.nf, res.sim_path, f, prep.theta, prep.phi, prep.nf_center)
+            assert np.array_equal(dbi, res.intensity)
+            assert np.allclose(res.theta, np.deg2rad(prep.theta)) and np.allclose(res.phi, np.deg2rad(prep.phi))
+
+        @dataclass
+        class PI:
+            name: str
+            params: object
+            center_x_m: float = 0.0
+            center_y_m: float = 0.0
+            center_z_m: float = 0.0
+            rot_x_deg: float = 0.0
+            rot_y_deg: float = 0.0
+            rot_z_deg: float = 0.0
+            feed_direction: object = None
+        patches = [PI("P1", P, center_x_m=-0.035, feed_direction=FD.NEG_X), PI("P2", P, center_x_m=0.035, rot_z_deg=90.0, feed_direction=FD.NEG_X)]
+        prep = sm.prepare_openems_microstrip_multi_3d(patches, dll_dir=refload.DLL_DIR, boundary="MUR", mesh_quality=1,
+                                                      theta_step_deg=15.0, phi_step_deg=45.0)
+        assert prep.ok, prep.message
+        prep.FDTD.SetNumberOfTimeSteps(500); prep.FDTD.SetEndCriteria(1e-30)
+        res = sm.run_prepared_openems_microstrip_multi_3d(prep, frequency_hz=2.40e9, verbose=0)
+        assert res.ok, res.message
+        dbi, dmax = replay.reference_postprocess(prep.nf, res.sim_path, 2.40e9, prep.theta, prep.phi, prep.nf_center)
+        assert np.array_equal(dbi, res.intensity)
+    finally:
+        scenes.use_cuda_engine()
