@@ -111,9 +111,10 @@ class Engine:
     def set_tuning(self, kz=16, ty=4, variant=0):
         check(self.L.b200fdtd_set_tuning(self.h, int(kz), int(ty), int(variant)))
 
-    def set_he_tuning(self, rows=0, planes=0):
-        """tile of the fused H->E launch: rows per CTA in {3, 7, 15}, planes marched per CTA (0 = keep)"""
-        check(self.L.b200fdtd_set_he_tuning(self.h, int(rows), int(planes)))
+    def set_he_tuning(self, rows=0, planes=0, de=0):
+        """tile of the fused H->E launch: rows per CTA in {3, 7, 15}, planes marched per CTA, E planes landing ahead of the two
+        in use in {1, 2} (0 = keep / automatic)"""
+        check(self.L.b200fdtd_set_he_tuning(self.h, int(rows), int(planes) | (int(de) << 24)))
 
     @property
     def he_active(self):

@@ -59,7 +59,8 @@ struct PmlTable { int n; long long total; PmlBoxDev b[MAX_PML_BOXES]; };
 
 // launch plan of the volume kernels: PML boxes spanning whole x-rows are fused into the volume launches
 struct FusedBox { int y0, by, z0, bz; float *flux_v, *flux_i; const float *vv, *vvfo, *vvfn, *ii, *iifo, *iifn;
-                  const float *xv_v, *xv_i; const unsigned char *meta_v, *meta_i; };
+                  const float *xv_v, *xv_i; const unsigned char *meta_v, *meta_i;
+                  float* flux_i_alt; };                      // second copy of the current flux (library-owned, see flux_pp)
 struct VolumePlan {
     bool valid = false;
     int nseg = 0; int seg0[3], seg1[3];          // plane ranges of the plain launches (complement of fused z-slabs)
@@ -100,6 +101,11 @@ struct b200fdtd_ctx {
     int vcur = 0, ccur = 0;
     bool flip = false;                     // volume launches write the other copy instead of updating in place
     int he_ty = 7, he_kz = 32;             // fused launch: rows per CTA (+1 halo row), planes marched per CTA
+    int he_de = 0;                         // E planes landing ahead of the two in use (0 = as many as shared memory allows, max 2)
+    // The fused launch sweeps the whole-row PML slabs too and recomputes H_new on tile halos from the OLD current flux, so
+    // the current flux of those slabs is double buffered: every H pass reads copy fcur and writes the other one.
+    bool flux_pp = false; int fcur = 0;
+    float* flux_alt[4] = {nullptr, nullptr, nullptr, nullptr};
     const float *vv = nullptr, *vi = nullptr, *ii = nullptr, *iv = nullptr;
     int kz = 16, ty = 4, variant = 0;
     const float* cmp_xv[2] = {nullptr, nullptr};          // row compression tables of the E and H pass (caller-owned)
@@ -191,8 +197,10 @@ static int launch_volume_one(b200fdtd_ctx* c, int which, int k0, int k1, const R
 
 // Split the PML boxes into fused slabs (whole x-rows; handled inside the volume launches) and boxes for the
 // separate pre/post kernel.  z-slabs (all rows of some planes) and y-slabs (some rows of all remaining planes) qualify.
+static int normalize_flux(b200fdtd_ctx* c);
 static int build_plan(b200fdtd_ctx* c)
 {
+    if (c->plan.valid && c->flux_pp && c->fcur) if (normalize_flux(c)) return 1;   // the old plan's second flux copy holds the state
     VolumePlan P;
     PmlTable rest; memset(&rest, 0, sizeof(rest));
     const PmlTable& A = c->pml_all;
@@ -234,7 +242,7 @@ static int build_plan(b200fdtd_ctx* c)
             const bool aligned = !(((uintptr_t)B.flux_v | (uintptr_t)B.flux_i | (uintptr_t)B.vv | (uintptr_t)B.vvfo | (uintptr_t)B.vvfn |
                                     (uintptr_t)B.ii | (uintptr_t)B.iifo | (uintptr_t)B.iifn) & 15);
             if (!shape || !aligned) continue;
-            FusedBox Fb; Fb.y0 = B.y0; Fb.by = B.by; Fb.z0 = B.z0; Fb.bz = B.bz;
+            FusedBox Fb; Fb.flux_i_alt = nullptr; Fb.y0 = B.y0; Fb.by = B.by; Fb.z0 = B.z0; Fb.bz = B.bz;
             Fb.flux_v = B.flux_v; Fb.flux_i = B.flux_i; Fb.vv = B.vv; Fb.vvfo = B.vvfo; Fb.vvfn = B.vvfn; Fb.ii = B.ii; Fb.iifo = B.iifo; Fb.iifn = B.iifn;
             Fb.xv_v = B.xv_v; Fb.xv_i = B.xv_i; Fb.meta_v = B.meta_v; Fb.meta_i = B.meta_i;
             if (B.x0 == 0 && !P.has_lo && (!P.has_hi || B.bx <= P.xx1)) { P.has_lo = 1; P.xlo = Fb; P.xw0 = B.bx; kind[b] = 3; }
@@ -248,7 +256,7 @@ static int build_plan(b200fdtd_ctx* c)
         if (kind[b] == 0 || P.nfused >= 4) {
             PmlBoxDev D = B; D.start = rest.total; rest.b[rest.n++] = D; rest.total += 3LL * B.bx * B.by * B.bz;
         } else {
-            FusedBox& Fb = P.fb[P.nfused++];
+            FusedBox& Fb = P.fb[P.nfused++]; Fb.flux_i_alt = nullptr;
             Fb.y0 = B.y0; Fb.by = B.by; Fb.z0 = B.z0; Fb.bz = B.bz;
             Fb.flux_v = B.flux_v; Fb.flux_i = B.flux_i; Fb.vv = B.vv; Fb.vvfo = B.vvfo; Fb.vvfn = B.vvfn;
             Fb.ii = B.ii; Fb.iifo = B.iifo; Fb.iifn = B.iifn;
@@ -260,6 +268,9 @@ static int build_plan(b200fdtd_ctx* c)
     P.ym0 = 0; P.ym1 = c->ny;
     for (int q = 0; q < P.nskip; ++q) { if (P.sj0[q] == 0) P.ym0 = P.sj1[q]; else P.ym1 = P.sj0[q]; }
     P.valid = true;
+    // a new plan: the second flux copies (if any) belong to the old one
+    for (int q = 0; q < 4; ++q) { if (c->flux_alt[q]) { cudaFree(c->flux_alt[q]); c->flux_alt[q] = nullptr; } }
+    c->flux_pp = false; c->fcur = 0;
     c->plan = P;
     c->pml = rest;
     return 0;
@@ -347,7 +358,9 @@ static int launch_volume_fused(b200fdtd_ctx* c, int which, int k0, int k1, cudaS
         }
         RowParams f; memset(&f, 0, sizeof(f));
         f.j0 = B.y0; f.j1 = B.y0 + B.by; f.y0 = B.y0; f.z0 = B.z0; f.by = B.by; f.bz = B.bz;
-        f.flux = which == 0 ? B.flux_v : B.flux_i;
+        if (which == 0) { f.flux = B.flux_v; f.flux_out = B.flux_v; }
+        else if (c->flux_pp) { f.flux = c->fcur ? B.flux_i_alt : B.flux_i; f.flux_out = c->fcur ? B.flux_i : B.flux_i_alt; }
+        else { f.flux = B.flux_i; f.flux_out = B.flux_i; }
         f.a = which == 0 ? B.vv : B.ii; f.fo = which == 0 ? B.vvfo : B.iifo; f.fn = which == 0 ? B.vvfn : B.iifn;
         if ((c->variant & 16) == 0) { f.pxv = which == 0 ? B.xv_v : B.xv_i; f.pmeta = which == 0 ? B.meta_v : B.meta_i; if (!f.pxv) f.pmeta = nullptr; }
         const int a = k0 > B.z0 ? k0 : B.z0, b = k1 < B.z0 + B.bz ? k1 : B.z0 + B.bz;
@@ -373,12 +386,81 @@ static int launch_volume(b200fdtd_ctx* c, int which, int k0, int k1)
 }
 
 
-// fused H->E launch over the plain region: reads the current copies, writes the other copies (the caller flips)
+// ---- the fused H->E launch ------------------------------------------------------------------------------------------
+// update_he6_kernel needs the row-compressed operator (its x-vector slices live in shared memory); other operators take
+// update_he_kernel, the plain fusion.  he6 also sweeps the whole-row PML slabs (variant bit 22 keeps them as separate launches).
+static size_t he6_smem(int ty, int de, size_t xs_bytes)
+{
+    switch (ty) {
+        case 3: return (de == 2 ? sizeof(He6Smem<3, 2>) : sizeof(He6Smem<3, 1>)) + xs_bytes;
+        case 7: return (de == 2 ? sizeof(He6Smem<7, 2>) : sizeof(He6Smem<7, 1>)) + xs_bytes;
+        case 15: return (de == 2 ? sizeof(He6Smem<15, 2>) : sizeof(He6Smem<15, 1>)) + xs_bytes;
+    }
+    return (size_t)1 << 30;
+}
+struct HeChoice { bool he6; int de; bool pml; };
+static HeChoice he_choice(const b200fdtd_ctx* c)
+{
+    HeChoice h{false, 1, false};
+    const bool cmp = c->cmp_meta[0] != nullptr && c->cmp_meta[1] != nullptr && (c->variant & 4) == 0;
+    const size_t xs_bytes = (size_t)(c->cmp_nvec[0] + c->cmp_nvec[1]) * 32 * sizeof(float4);
+    if (!cmp || (c->variant & 512) != 0 || !(c->he_ty == 3 || c->he_ty == 7 || c->he_ty == 15)) return h;
+    const size_t limit = 227 * 1024, per_sm = 228 * 1024;
+    if (he6_smem(c->he_ty, 1, xs_bytes) > limit) return h;
+    h.he6 = true;
+    // two E planes landing if that does not cost a resident CTA (each CTA also reserves 1 KB)
+    const int ctas1 = (int)(per_sm / (he6_smem(c->he_ty, 1, xs_bytes) + 1024));
+    const int ctas2 = he6_smem(c->he_ty, 2, xs_bytes) <= limit ? (int)(per_sm / (he6_smem(c->he_ty, 2, xs_bytes) + 1024)) : 0;
+    const int reg_ctas = 16 / (c->he_ty + 1) > 0 ? 16 / (c->he_ty + 1) : 1;       // __launch_bounds__ of the kernel
+    const int r1 = ctas1 < reg_ctas ? ctas1 : reg_ctas, r2 = ctas2 < reg_ctas ? ctas2 : reg_ctas;
+    h.de = c->he_de ? c->he_de : ((r2 >= r1 && r2 > 0) ? 2 : 1);
+    if (h.de == 2 && ctas2 == 0) h.de = 1;
+    h.pml = c->plan.nfused > 0 && (c->variant & (1 << 22)) == 0;
+    return h;
+}
+
+// second copies of the current flux of the whole-row slabs (the fused launch reads the old flux on tile halos)
+static int ensure_flux_pp(b200fdtd_ctx* c)
+{
+    if (c->flux_pp || !he_choice(c).pml) return 0;
+    VolumePlan& P = c->plan;
+    for (int q = 0; q < P.nfused; ++q) {
+        const size_t bytes = sizeof(float) * 3 * (size_t)P.fb[q].bz * P.fb[q].by * c->px;
+        if (cudaMalloc((void**)&c->flux_alt[q], bytes) != cudaSuccess) {
+            cudaGetLastError();
+            for (int u = 0; u < q; ++u) { cudaFree(c->flux_alt[u]); c->flux_alt[u] = nullptr; }
+            return 0;                                           // no room: the slabs keep their separate launches
+        }
+        CK(cudaMemsetAsync(c->flux_alt[q], 0, bytes, c->stream));
+    }
+    for (int q = 0; q < P.nfused; ++q) P.fb[q].flux_i_alt = c->flux_alt[q];
+    c->flux_pp = true; c->fcur = 0;
+    return 0;
+}
+// does the fused launch sweep the whole-row PML slabs of this run?
+static bool he_pml(const b200fdtd_ctx* c) { return c->flux_pp && he_choice(c).pml; }
+
+// the state of the current flux goes back to the caller's arrays (copy 0)
+static int normalize_flux(b200fdtd_ctx* c)
+{
+    if (!c->flux_pp || c->fcur == 0) return 0;
+    const VolumePlan& P = c->plan;
+    for (int q = 0; q < P.nfused; ++q) {
+        const size_t bytes = sizeof(float) * 3 * (size_t)P.fb[q].bz * P.fb[q].by * c->px;
+        CK(cudaMemcpyAsync(P.fb[q].flux_i, P.fb[q].flux_i_alt, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    c->fcur = 0;
+    return 0;
+}
+
+// fused H->E launch: reads the current copies, writes the other copies (the caller flips)
 static int launch_he(b200fdtd_ctx* c, cudaStream_t stream, int zc0 = -1, int zc1 = -1)
 {
     const VolumePlan& P = c->plan;
     const bool clipped = zc0 >= 0;                           // z-slab ranks: interior planes [zc0, zc1) only
-    if (P.nseg != 1) return clipped ? 0 : fail("fused H->E launch without a plain region");
+    const HeChoice hc = he_choice(c);
+    const bool pml = hc.he6 && hc.pml && c->flux_pp;
+    if (P.nseg != 1 && !pml) return clipped ? 0 : fail("fused H->E launch without a plain region");
     HeParams p;
     p.ein = cur_volt(c); p.hin = cur_curr(c); p.eout = oth_volt(c); p.hout = oth_curr(c);
     p.vv = c->vv; p.vi = c->vi; p.ii = c->ii; p.iv = c->iv;
@@ -386,56 +468,61 @@ static int launch_he(b200fdtd_ctx* c, cudaStream_t stream, int zc0 = -1, int zc1
     p.xv_e = c->cmp_xv[0]; p.meta_e = c->cmp_meta[0]; p.xv_h = c->cmp_xv[1]; p.meta_h = c->cmp_meta[1];
     p.ny = c->ny; p.px = c->px; p.sz = c->sz; p.cs = c->cs;
     p.X0 = P.has_lo ? P.xw0 : 0; p.X1 = P.has_hi ? P.xx1 : c->px; p.XT0 = P.has_hi ? P.xx1 + P.xw1 : c->px;
-    p.Y0 = P.ym0; p.Y1 = P.ym1; p.Z0 = P.seg0[0]; p.Z1 = P.seg1[0];
+    p.X0s = p.X0;
+    p.Y0 = P.ym0; p.Y1 = P.ym1; p.Z0 = P.nseg ? P.seg0[0] : 0; p.Z1 = P.nseg ? P.seg1[0] : 0;
+    HePml Q; memset(&Q, 0, sizeof(Q));
+    Q.b_zlo = Q.b_zhi = Q.b_ylo = Q.b_yhi = -1;
+    if (pml) {
+        // the launch covers every row and plane; rows of the whole-row slabs take the PML path
+        Q.zlo = 0; Q.zhi = c->nz; Q.ym0 = 0; Q.ym1 = c->ny;
+        for (int q = 0; q < P.nfused; ++q) {
+            const FusedBox& B = P.fb[q];
+            HePmlBox& D = Q.b[q];
+            D.y0 = B.y0; D.by = B.by; D.z0 = B.z0; D.bz = B.bz;
+            D.gin = c->fcur ? B.flux_i_alt : B.flux_i; D.gout = c->fcur ? B.flux_i : B.flux_i_alt; D.fv = B.flux_v;
+            D.ah = B.ii; D.foh = B.iifo; D.fnh = B.iifn; D.ae = B.vv; D.foe = B.vvfo; D.fne = B.vvfn;
+            const bool pc = (c->variant & 16) == 0;
+            D.xvh = pc ? B.xv_i : nullptr; D.mh = pc && B.xv_i ? B.meta_i : nullptr;
+            D.xve = pc ? B.xv_v : nullptr; D.me = pc && B.xv_v ? B.meta_v : nullptr;
+            if (B.y0 == 0 && B.by == c->ny) { if (B.z0 == 0) { Q.b_zlo = q; Q.zlo = B.bz; } else { Q.b_zhi = q; Q.zhi = B.z0; } }
+            else if (B.y0 == 0) { Q.b_ylo = q; Q.ym0 = B.by; }
+            else { Q.b_yhi = q; Q.ym1 = B.y0; }
+        }
+        p.X0s = 0; p.Y0 = 0; p.Y1 = c->ny; p.Z0 = 0; p.Z1 = c->nz;
+    }
     if (clipped) { if (p.Z0 < zc0) p.Z0 = zc0; if (p.Z1 > zc1) p.Z1 = zc1; if (p.Z1 <= p.Z0) return 0; }
-    if (p.Y1 <= p.Y0 || p.Z1 <= p.Z0 || p.X1 <= p.X0) return fail("fused H->E launch over an empty region");
+    if (p.Y1 <= p.Y0 || p.Z1 <= p.Z0 || (!pml && p.X1 <= p.X0)) return fail("fused H->E launch over an empty region");
     const int ty = c->he_ty;
     int kz = c->he_kz; if (kz > p.Z1 - p.Z0) kz = p.Z1 - p.Z0;
     { const int n = (p.Z1 - p.Z0 + kz - 1) / kz; kz = (p.Z1 - p.Z0 + n - 1) / n; }      // chunks of equal length
     p.kz = kz;
-    p.pf = (c->variant >> 16) & 3;                   // L2 prefetch distance in planes: 0 = default (1), 3 = off
+    p.pf = (c->variant >> 16) & 3;                   // L2 prefetch distance in planes (plain fusion only): 0 = default (1), 3 = off
     p.pf = p.pf == 0 ? 1 : (p.pf == 3 ? 0 : p.pf);
     dim3 block(32, ty + 1);
-    dim3 grid((c->px - p.X0 + HE_SEG - 1) / HE_SEG, (p.Y1 - p.Y0 + ty - 1) / ty, (p.Z1 - p.Z0 + kz - 1) / kz);
+    dim3 grid((c->px - p.X0s + HE_SEG - 1) / HE_SEG, (p.Y1 - p.Y0 + ty - 1) / ty, (p.Z1 - p.Z0 + kz - 1) / kz);
     if (grid.y > 65535 || grid.z > 65535) return fail("grid too large for the fused launch");
     p.b_sz = 4 * p.sz; p.b_cs = 4 * p.cs; p.b_2cs = 8 * p.cs; p.b_sz_cs = 4 * (p.sz + p.cs); p.b_sz_2cs = 4 * (p.sz + 2 * p.cs);
     p.b_row = 4LL * p.px; p.b_row_2cs = 4 * (p.px + 2 * p.cs);
     for (int q = 0; q < 3; ++q) { p.b_pfe[q] = 4 * (2 * p.sz + q * p.cs); p.b_pfh[q] = 4 * (p.sz + q * p.cs); }   // one plane ahead
     p.xv_pitch = 4u * (unsigned)p.px; p.meta_step = 32 * p.ny;
-    const bool staged = (c->variant & 256) != 0;
     p.nv_e = c->cmp_nvec[0]; p.nv_h = c->cmp_nvec[1];
     const size_t xs_bytes = (size_t)(p.nv_e + p.nv_h) * 32 * sizeof(float4);
-    const bool v2 = cmp && (c->variant & 512) == 0 && xs_bytes <= 96 * 1024;
-    const bool v3 = v2 && (c->variant & (1 << 18)) == 0;
+#define LAUNCH_HE6(TYV, DEV, PMLV) do { const size_t sm6 = sizeof(He6Smem<TYV, DEV>) + xs_bytes; \
+        CK(cudaFuncSetAttribute(update_he6_kernel<TYV, DEV, PMLV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm6)); \
+        update_he6_kernel<TYV, DEV, PMLV><<<grid, block, sm6, stream>>>(p, Q); } while (0)
 #define LAUNCH_HE(TYV) do { \
-        if (v3 && (c->variant & (1 << 19)) != 0 && sizeof(He4Smem<TYV>) + xs_bytes <= 220 * 1024) { const size_t sm4 = sizeof(He4Smem<TYV>) + xs_bytes; \
-                  CK(cudaFuncSetAttribute(update_he4_kernel<TYV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4)); \
-                  update_he4_kernel<TYV><<<grid, block, sm4, stream>>>(p); } \
-        else if (v3 && (c->variant & (1 << 21)) == 0 && sizeof(He5Smem<TYV>) + xs_bytes <= 220 * 1024) { const size_t sm5 = sizeof(He5Smem<TYV>) + xs_bytes; \
-                  CK(cudaFuncSetAttribute(update_he5_kernel<TYV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm5)); \
-                  update_he5_kernel<TYV><<<grid, block, sm5, stream>>>(p); } \
-        else if (v3 && sizeof(He3Smem<TYV>) + xs_bytes <= 220 * 1024) { const size_t sm3 = sizeof(He3Smem<TYV>) + xs_bytes; \
-                  CK(cudaFuncSetAttribute(update_he3_kernel<TYV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3)); \
-                  update_he3_kernel<TYV><<<grid, block, sm3, stream>>>(p); } \
-        else if (v2 && 2 * sizeof(float4) * (TYV + 1) * 70 + xs_bytes <= 220 * 1024) { if (xs_bytes > 8 * 1024) CK(cudaFuncSetAttribute(update_he2_kernel<TYV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xs_bytes)); \
-                  update_he2_kernel<TYV><<<grid, block, xs_bytes, stream>>>(p); } \
-        else if (staged) { \
-            const size_t sm = sizeof(HeSmem<TYV>); \
-            if (cmp) { CK(cudaFuncSetAttribute(update_he_staged_kernel<TYV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
-                       update_he_staged_kernel<TYV, true><<<grid, block, sm, stream>>>(p); } \
-            else { CK(cudaFuncSetAttribute(update_he_staged_kernel<TYV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
-                   update_he_staged_kernel<TYV, false><<<grid, block, sm, stream>>>(p); } \
-        } else if (cmp) update_he_kernel<TYV, true><<<grid, block, 0, stream>>>(p); \
+        if (hc.he6) { if (hc.de == 2) { if (pml) LAUNCH_HE6(TYV, 2, true); else LAUNCH_HE6(TYV, 2, false); } \
+                      else { if (pml) LAUNCH_HE6(TYV, 1, true); else LAUNCH_HE6(TYV, 1, false); } } \
+        else if (cmp) update_he_kernel<TYV, true><<<grid, block, 0, stream>>>(p); \
         else update_he_kernel<TYV, false><<<grid, block, 0, stream>>>(p); } while (0)
     switch (ty) {
         case 3: LAUNCH_HE(3); break;
-        case 5: LAUNCH_HE(5); break;
         case 7: LAUNCH_HE(7); break;
-        case 9: LAUNCH_HE(9); break;
         case 15: LAUNCH_HE(15); break;
         default: return fail("unsupported fused-launch tile height %d", ty);
     }
 #undef LAUNCH_HE
+#undef LAUNCH_HE6
     CKL();
     return 0;
 }
@@ -444,9 +531,11 @@ static int launch_he(b200fdtd_ctx* c, cudaStream_t stream, int zc0 = -1, int zc1
 // launches, a plain region, memory for the second copy of the fields)
 static bool he_ready(b200fdtd_ctx* c, int steps)
 {
-    if ((c->variant & 128) || steps < 2 || !c->plan.valid || c->pml.n > 0 || c->plan.nseg != 1) return false;
+    if ((c->variant & 128) || steps < 2 || !c->plan.valid || c->pml.n > 0) return false;
     const VolumePlan& P = c->plan;
-    if (P.ym1 <= P.ym0 || (P.has_hi ? P.xx1 : c->px) <= (P.has_lo ? P.xw0 : 0)) return false;
+    const bool pml_ok = he_choice(c).pml;
+    if (P.nseg != 1 && !pml_ok) return false;
+    if (P.nseg == 1 && !pml_ok && (P.ym1 <= P.ym0 || (P.has_hi ? P.xx1 : c->px) <= (P.has_lo ? P.xw0 : 0))) return false;
     if (!c->alt_volt) {
         const size_t bytes = sizeof(float) * 3 * (size_t)c->cs;
         if (cudaMalloc((void**)&c->alt_volt, bytes) != cudaSuccess) { cudaGetLastError(); c->alt_volt = nullptr; return false; }
@@ -455,6 +544,8 @@ static bool he_ready(b200fdtd_ctx* c, int steps)
         cudaMemsetAsync(c->alt_curr, 0, bytes, c->stream);
         c->alt_owned = true;
     }
+    if (ensure_flux_pp(c)) return false;
+    if (P.nseg != 1 && !he_pml(c)) return false;
     return true;
 }
 
@@ -545,6 +636,7 @@ extern "C" int b200fdtd_create(b200fdtd_ctx** out, int device, int nx, int ny, i
     c->variant = env_variant_or();
     if (const char* e = getenv("B200FDTD_HE_TY")) { const int t = atoi(e); if (t == 3 || t == 7 || t == 15) c->he_ty = t; }
     if (const char* e = getenv("B200FDTD_HE_KZ")) { const int t = atoi(e); if (t >= 1) c->he_kz = t; }
+    if (const char* e = getenv("B200FDTD_HE_DE")) { const int t = atoi(e); if (t == 1 || t == 2) c->he_de = t; }
     c->n_partials = 148 * 8;
     CK(cudaMalloc((void**)&c->d_partials, sizeof(double) * 2 * c->n_partials));
     CK(cudaMalloc((void**)&c->d_energy, sizeof(double) * 2));
@@ -560,6 +652,7 @@ extern "C" int b200fdtd_destroy(b200fdtd_ctx* c)
     drop_graph(c);
     cudaFree(c->d_ts); cudaFree(c->d_partials); cudaFree(c->d_energy);
     if (c->alt_owned) { cudaFree(c->alt_volt); cudaFree(c->alt_curr); }
+    for (int q = 0; q < 4; ++q) cudaFree(c->flux_alt[q]);
     cudaFree(c->exc_idx); cudaFree(c->exc_amp); cudaFree(c->exc_delay); cudaFree(c->exc_sig);
     cudaFree(c->mur_dst); cudaFree(c->mur_src); cudaFree(c->mur_coeff); cudaFree(c->mur_tmp);
     cudaFree(c->pr_kind); cudaFree(c->pr_off); cudaFree(c->pr_idx); cudaFree(c->pr_w); cudaFree(c->pr_freqs);
@@ -1071,6 +1164,7 @@ static int h_half(b200fdtd_ctx* c)
     if (launch_pml(c, 1, 1)) return 1;
     if (side) if (join_side(c)) return 1;
     if (c->flip) c->ccur ^= 1;
+    if (c->flux_pp) c->fcur ^= 1;                 // the whole-row slab launches read one copy of the current flux and wrote the other
     return 0;
 }
 
@@ -1078,12 +1172,13 @@ static int h_half(b200fdtd_ctx* c)
 //   PML slabs: H update into the other copy  ->  fused H->E launch over the plain region  ->  PML slabs: E update
 static int he_step(b200fdtd_ctx* c, int off)
 {
-    const bool slabs = c->plan.nfused > 0 || c->plan.xedge;
+    const bool inhe = he_pml(c);                 // whole-row slabs are swept by the fused launch itself
+    const bool slabs = (c->plan.nfused > 0 && !inhe) || c->plan.xedge;
     const bool side = slabs && (c->variant & 2) == 0;
     if (launch_mur(c, 0)) return 1;              // Mur reads the old E
     c->flip = true;
     int rc = 0;
-    const bool overlap = side && (c->variant & (1 << 20)) != 0;      // experiment (measured 1.5 % slower: the fused launch fills every SM)
+    const bool overlap = side && !inhe && (c->variant & (1 << 20)) != 0;      // experiment (measured 1.5 % slower: the fused launch fills every SM)
     do {
         if (overlap) {
             // Only the slabs at the LOW ends feed the fused launch (its halo cells outside the region are at i-1, j-1, k-1), and
@@ -1098,6 +1193,7 @@ static int he_step(b200fdtd_ctx* c, int off)
             if ((rc = launch_volume_fused(c, 1, 0, c->nz, slab_stream(c), 2))) break;
             if ((rc = launch_he(c, c->stream))) break;
             c->ccur ^= 1;                                                    // pointers of the launches below: H is new
+            if (c->flux_pp) c->fcur ^= 1;
             if ((rc = launch_volume_xslabs(c, 0, 0, c->nz, c->side, 1))) break;
             if ((rc = launch_volume_fused(c, 0, 0, c->nz, slab_stream(c), 1))) break;
             if ((rc = join_side(c))) break;
@@ -1108,12 +1204,22 @@ static int he_step(b200fdtd_ctx* c, int off)
             c->vcur ^= 1;
             break;
         }
+        if (inhe) {
+            // only the narrow x-slabs keep their own launches: H before the fused launch (it reads their H_new), E after it
+            if ((rc = launch_volume_xslabs(c, 1, 0, c->nz, c->stream))) break;
+            if ((rc = launch_he(c, c->stream))) break;
+            c->ccur ^= 1; c->fcur ^= 1;
+            if ((rc = launch_volume_xslabs(c, 0, 0, c->nz, c->stream))) break;
+            c->vcur ^= 1;
+            break;
+        }
         if (side) { if ((rc = fork_side(c))) break; }
         if ((rc = launch_volume_xslabs(c, 1, 0, c->nz, side ? c->side : c->stream))) break;
         if ((rc = launch_volume_fused(c, 1, 0, c->nz, side ? slab_stream(c) : c->stream))) break;
         if (side) { if ((rc = join_side(c))) break; }
         if ((rc = launch_he(c, c->stream))) break;
         c->ccur ^= 1;                            // H is new from here on
+        if (c->flux_pp) c->fcur ^= 1;
         if (side) { if ((rc = fork_side(c))) break; }
         if ((rc = launch_volume_xslabs(c, 0, 0, c->nz, side ? c->side : c->stream))) break;
         if ((rc = launch_volume_fused(c, 0, 0, c->nz, side ? slab_stream(c) : c->stream))) break;
@@ -1139,6 +1245,7 @@ static int run_span(b200fdtd_ctx* c, int n, bool fuse)
             rc = e_half(c, s);
             if (!rc) rc = h_half(c);
         }
+        if (!rc) rc = normalize_flux(c);
         return rc;
     }
     const bool odd = ((n - 1) & 1) != 0;
@@ -1148,6 +1255,7 @@ static int run_span(b200fdtd_ctx* c, int n, bool fuse)
     if (!rc) { c->flip = odd; rc = h_half(c); c->flip = false; }
     if (!rc && (c->vcur || c->ccur)) rc = fail("fused span did not return to the bound field arrays");
     c->vcur = c->ccur = 0; c->flip = false;
+    if (!rc) rc = normalize_flux(c);            // an odd number of H passes: the current flux goes back to the caller's arrays
     return rc;
 }
 
@@ -1276,6 +1384,7 @@ extern "C" int b200fdtd_half_step_part(b200fdtd_ctx* c, int phase, int part)
     }
     if (launch_volume(c, 1, nz - 1, nz)) return 1;
     if (launch_pml(c, 1, 1)) return 1;
+    if (c->flux_pp) c->fcur ^= 1;                 // both parts read one copy of the slabs' current flux and wrote the other
     if (launch_ts_add(c, 1)) return 1;
     c->ts += 1;
     return 0;
@@ -1306,13 +1415,15 @@ extern "C" int b200fdtd_fused_step_part(b200fdtd_ctx* c, int part)
     const int nz = c->nz;
     if (nz < 3) return fail("fused steps need at least 3 planes per slab");
     int rc = 0;
-    const bool side = (c->plan.nfused > 0 || c->plan.xedge) && (c->variant & 2) == 0;    // interior slab launches side by side
+    if (ensure_flux_pp(c)) return 1;
+    const bool inhe = he_pml(c);                 // the fused launch sweeps the whole-row slabs of the interior planes itself
+    const bool side = ((c->plan.nfused > 0 && !inhe) || c->plan.xedge) && (c->variant & 2) == 0;    // interior slab launches side by side
     if (part == 0) {
         if (launch_mur(c, 0)) return 1;
         c->flip = true;
         if (side) rc = fork_side(c);
         if (!rc) rc = launch_volume_xslabs(c, 1, 1, nz - 1, side ? c->side : c->stream);
-        if (!rc) rc = launch_volume_fused(c, 1, 1, nz - 1, side ? slab_stream(c) : c->stream);
+        if (!rc && !inhe) rc = launch_volume_fused(c, 1, 1, nz - 1, side ? slab_stream(c) : c->stream);
         if (!rc) rc = launch_volume(c, 1, 0, 1);
         if (!rc && side) rc = join_side(c);
         c->flip = false;
@@ -1332,6 +1443,7 @@ extern "C" int b200fdtd_fused_step_part(b200fdtd_ctx* c, int part)
         if (launch_he(c, c->stream, c->he_mid > 0 ? c->he_mid : 1, nz - 1)) return 1;
         c->he_mid = 0;
         c->ccur ^= 1;
+        if (c->flux_pp) c->fcur ^= 1;
         if (launch_ts_add(c, 1)) return 1;
         c->ts += 1;
         return 0;
@@ -1339,7 +1451,7 @@ extern "C" int b200fdtd_fused_step_part(b200fdtd_ctx* c, int part)
     c->flip = true;
     if (side) rc = fork_side(c);
     if (!rc) rc = launch_volume_xslabs(c, 0, 1, nz - 1, side ? c->side : c->stream);
-    if (!rc) rc = launch_volume_fused(c, 0, 1, nz - 1, side ? slab_stream(c) : c->stream);
+    if (!rc && !inhe) rc = launch_volume_fused(c, 0, 1, nz - 1, side ? slab_stream(c) : c->stream);
     if (!rc) rc = launch_volume(c, 0, 0, 1);
     if (!rc) rc = launch_volume(c, 0, nz - 1, nz);
     if (!rc && side) rc = join_side(c);
@@ -1375,7 +1487,8 @@ extern "C" int b200fdtd_reset_current_copy(b200fdtd_ctx* c)
 {
     if (!c) return fail("NULL ctx");
     c->vcur = c->ccur = 0;                       // the caller has copied the state back into the bound arrays
-    return 0;
+    CK(cudaSetDevice(c->device));
+    return normalize_flux(c);                    // ... and the library does the same for the PML flux copy it owns
 }
 
 extern "C" int b200fdtd_update_only(b200fdtd_ctx* c, int which)
@@ -1391,7 +1504,11 @@ extern "C" int b200fdtd_update_only(b200fdtd_ctx* c, int which)
         if (!he_ready(c, 2)) return fail("fused H->E launch not available for this set-up");
         return launch_he(c, c->stream);
     }
-    if (which < 2) return launch_volume(c, which, 0, c->nz);
+    if (which < 2) {
+        if (launch_volume(c, which, 0, c->nz)) return 1;
+        if (which == 1 && c->flux_pp) c->fcur ^= 1;
+        return 0;
+    }
     // 2/3: only the plain (non-PML) launch of the E/H update — the kernel the roofline is quoted on
     if (!c->volt || !c->vv) return fail("fields/coefficients not bound");
     if (!c->plan.valid) if (build_plan(c)) return 1;
@@ -1418,10 +1535,13 @@ extern "C" int b200fdtd_plan_info(b200fdtd_ctx* c, int64_t* plain_cells, int64_t
 extern "C" int b200fdtd_set_he_tuning(b200fdtd_ctx* c, int rows, int planes)
 {
     if (!c) return fail("NULL ctx");
-    if (!(rows == 0 || rows == 3 || rows == 5 || rows == 7 || rows == 9 || rows == 15)) return fail("rows must be 0, 3, 5, 7, 9 or 15");
+    if (!(rows == 0 || rows == 3 || rows == 7 || rows == 15)) return fail("rows must be 0, 3, 7 or 15");
     if (planes < 0) return fail("planes must be >= 0");
+    const int de = (planes >> 24) & 3; planes &= 0xffffff;     // bits 24-25 of `planes`: E planes landing ahead (1 | 2; 0 = automatic)
+    if (de == 3) return fail("the E lookahead must be 0 (automatic), 1 or 2");
     if (rows) c->he_ty = rows;
     if (planes) c->he_kz = planes;
+    c->he_de = de;
     drop_graph(c);
     return 0;
 }

@@ -20,6 +20,7 @@ struct HeParams {
     const float* __restrict__ xv_h; const unsigned char* __restrict__ meta_h;
     int ny, px; long long sz, cs;
     int X0, X1, XT0;                // owned columns [X0,X1) and [XT0,px), multiples of 4 (the gap is a narrow PML x-slab)
+    int X0s;                        // column where the first x-segment starts (X0; 0 when whole-row PML slabs are swept too)
     int Y0, Y1, Z0, Z1;             // owned rows and planes
     int kz;
     int pf;                         // planes of L2 prefetch distance (0 = off)
@@ -138,13 +139,7 @@ __global__ void __launch_bounds__(32 * (TY + 1), 16 / (TY + 1)) update_he_kernel
 }
 
 
-// ---- the same sweep with the planes staged through shared memory by cp.async (LDGSTS) ----
-// The register version above is bound by DRAM latency: 16 warps per SM, each waiting on the loads of its own plane.
-// Here every thread copies the float4s it will need one plane ahead straight into shared memory (no registers held while
-// the copy is in flight), so a CTA always has a whole plane of loads outstanding while it computes the previous one, and
-// the y-neighbour rows come from shared memory instead of a second global load.
-//   E ring: HE_DIST+2 planes (k and k+1 in use, the rest landing)   [3 comps][TY+2 rows][33 float4]   (row TY+1 / column 32 = +1 halo)
-//   H ring: HE_DIST+1 planes (k in use, the rest landing)           [3 comps][TY+1 rows][32 float4]
+// ---- helpers of the staged kernel ----
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid)
 {
     const unsigned dst = (unsigned)__cvta_generic_to_shared(smem);
@@ -154,135 +149,7 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool va
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
-#define HE_DIST 2           // planes in flight ahead of the one being computed
-template <int TY>
-struct HeSmem {
-    float4 e[HE_DIST + 2][3][TY + 2][33];
-    float4 h[HE_DIST + 1][3][TY + 1][32];
-    float4 xb[2][TY + 1][2][32];
-};
 
-template <int TY, bool CMP>
-__global__ void __launch_bounds__(32 * (TY + 1), 16 / (TY + 1)) update_he_staged_kernel(const HeParams p)
-{
-    extern __shared__ __align__(16) unsigned char he_smem_raw[];
-    HeSmem<TY>& S = *reinterpret_cast<HeSmem<TY>*>(he_smem_raw);
-    const int lane = threadIdx.x, r = threadIdx.y;
-    const int i0 = p.X0 - 4 + HE_SEG * (int)blockIdx.x + 4 * lane;
-    const int j = p.Y0 - 1 + TY * (int)blockIdx.y + r;
-    const int kbeg = p.Z0 + (int)blockIdx.z * p.kz;
-    const int kend = min(kbeg + p.kz, p.Z1);
-    const bool col_ok = i0 >= 0 && i0 < p.px;
-    const bool in_grid = col_ok && j >= 0 && j < p.Y1;      // rows >= Y1 are needed only as the +1 neighbour row
-    const bool reg_x = (i0 >= p.X0 && i0 < p.X1) || i0 >= p.XT0;
-    const bool ext = in_grid && (!reg_x || j < p.Y0);       // H_new was written by a slab launch: read it
-    const bool calc = in_grid && !ext;
-    const bool own = calc && lane >= 1 && r >= 1;
-    // what this thread stages: its own float4 of E (any row of the grid up to Y1, which is the +1 row of the last owned
-    // row), the +1 row for the top warp, the +1 column for lane 31, and its own float4 of H_old where H_new is computed
-    const bool e_ok = col_ok && j >= 0 && j < p.ny && j <= p.Y1;
-    const bool top = r == TY;
-    const bool e_top_ok = top && col_ok && j + 1 < p.ny && j + 1 <= p.Y1;
-    const bool e_col_ok = lane == 31 && i0 + 4 < p.px && j >= 0 && j < p.Y1;
-    const long long cs = p.cs, sz = p.sz;
-    const float* __restrict__ ein = p.ein; const float* __restrict__ hin = p.hin;
-    float* __restrict__ eout = p.eout; float* hout = p.hout;
-    const long long rowoff = (long long)j * p.px + i0;       // may be "negative" for halo threads: only used when valid
-
-    auto stage_e = [&](int k) {                              // E_old(k) -> ring slot k % (HE_DIST+2)
-        const int s = k % (HE_DIST + 2);
-        const long long b = (long long)(k + 1) * sz + rowoff;
-        const float* src = e_ok ? ein + b : ein;
-        cp_async16(&S.e[s][0][r][lane], src, e_ok);
-        cp_async16(&S.e[s][1][r][lane], src + (e_ok ? cs : 0), e_ok);
-        cp_async16(&S.e[s][2][r][lane], src + (e_ok ? 2 * cs : 0), e_ok);
-        if (top) {                                           // row TY+1: (ex, ez) of row j+1
-            const float* st = e_top_ok ? ein + b + p.px : ein;
-            cp_async16(&S.e[s][0][TY + 1][lane], st, e_top_ok);
-            cp_async16(&S.e[s][2][TY + 1][lane], st + (e_top_ok ? 2 * cs : 0), e_top_ok);
-        }
-        if (lane == 31) {                                    // column 32: (ey, ez) of the float4 right of the segment
-            const float* sc = e_col_ok ? ein + b + 4 : ein;
-            cp_async16(&S.e[s][1][r][32], sc + (e_col_ok ? cs : 0), e_col_ok);
-            cp_async16(&S.e[s][2][r][32], sc + (e_col_ok ? 2 * cs : 0), e_col_ok);
-        }
-    };
-    auto stage_h = [&](int k) {                              // H_old(k) -> ring slot k % (HE_DIST+1)
-        const int s = k % (HE_DIST + 1);
-        const float* src = calc ? hin + (long long)(k + 1) * sz + rowoff : hin;
-        cp_async16(&S.h[s][0][r][lane], src, calc);
-        cp_async16(&S.h[s][1][r][lane], src + (calc ? cs : 0), calc);
-        cp_async16(&S.h[s][2][r][lane], src + (calc ? 2 * cs : 0), calc);
-    };
-
-    const int kfirst = kbeg > p.Z0 ? kbeg - 1 : kbeg;        // one plane below the chunk: H_new(kbeg-1) is recomputed
-    // one commit group per plane of the march: group d holds what iteration kfirst+d needs on top of the groups before it
-    stage_e(kfirst); stage_e(kfirst + 1); stage_h(kfirst);
-    cp_async_commit();
-#pragma unroll
-    for (int d = 1; d < HE_DIST; ++d) {
-        if (kfirst + d < kend) { stage_e(kfirst + d + 1); stage_h(kfirst + d); }
-        cp_async_commit();
-    }
-    long long base = (long long)(kfirst + 1) * sz + rowoff;  // plane kfirst (ghost offset +1)
-    float4 hx_km = zero4(), hy_km = zero4();                 // H_new(k-1)
-    if (kfirst == kbeg && own) { hx_km = ld4(hout + base - sz); hy_km = ld4(hout + cs + base - sz); }
-    cp_async_wait<HE_DIST - 1>();
-    __syncthreads();
-
-    for (int k = kfirst; k < kend; ++k, base += sz) {
-        const bool pro = k < kbeg;                           // prologue plane: H_new only, nothing stored
-        if (k + HE_DIST < kend) { stage_e(k + HE_DIST + 1); stage_h(k + HE_DIST); }
-        cp_async_commit();
-        const int se = k % (HE_DIST + 2), se1 = (k + 1) % (HE_DIST + 2), sh = k % (HE_DIST + 1);
-        float4 hx = zero4(), hy = zero4(), hz = zero4();
-        float4 ax, ay, az, bx, by, bz;
-        const float4 ex = S.e[se][0][r][lane], ey = S.e[se][1][r][lane], ez = S.e[se][2][r][lane];
-        if (calc) {
-            load_coefs6<CMP>(p.ii, p.iv, p.xv_h, p.meta_h, base, cs, (long long)(k + 1) * p.ny + j, p.ny, i0, p.px, ax, ay, az, bx, by, bz);
-            hx = S.h[sh][0][r][lane]; hy = S.h[sh][1][r][lane]; hz = S.h[sh][2][r][lane];
-        } else if (ext) {
-            hx = ld4(hout + base); hy = ld4(hout + cs + base); hz = ld4(hout + 2 * cs + base);
-        }
-        float ez_r = __shfl_down_sync(0xffffffffu, ez.x, 1);
-        float ey_r = __shfl_down_sync(0xffffffffu, ey.x, 1);
-        if (lane == 31) { ez_r = S.e[se][2][r][32].x; ey_r = S.e[se][1][r][32].x; }
-        if (calc) {
-            const float4 ex1 = S.e[se1][0][r][lane], ey1 = S.e[se1][1][r][lane];
-            const float4 ex_jp = S.e[se][0][r + 1][lane], ez_jp = S.e[se][2][r + 1][lane];
-            const float4 ez_ip = make_float4(ez.y, ez.z, ez.w, ez_r);
-            const float4 ey_ip = make_float4(ey.y, ey.z, ey.w, ey_r);
-            hx = upd4(ax, hx, bx, ez, ez_jp, ey, ey1);
-            hy = upd4(ay, hy, by, ex, ex1, ez, ez_ip);
-            hz = upd4(az, hz, bz, ey, ey_ip, ex, ex_jp);
-        }
-        // hx, hy, hz now hold H_new(k) (zero outside the grid)
-        if (own && !pro) { st4(hout + base, hx); st4(hout + cs + base, hy); st4(hout + 2 * cs + base, hz); }
-        S.xb[k & 1][r][0][lane] = hz; S.xb[k & 1][r][1][lane] = hx;
-        cp_async_wait<HE_DIST - 1>();                        // the next plane has landed (this thread's copies) ...
-        __syncthreads();                                     // ... and everybody's, together with this plane's H_new rows
-        const float hz_l = __shfl_up_sync(0xffffffffu, hz.w, 1);
-        const float hy_l = __shfl_up_sync(0xffffffffu, hy.w, 1);
-        if (own && !pro) {
-            const float4 hz_jm = S.xb[k & 1][r - 1][0][lane], hx_jm = S.xb[k & 1][r - 1][1][lane];
-            const float4 hz_im = make_float4(hz_l, hz.x, hz.y, hz.z);
-            const float4 hy_im = make_float4(hy_l, hy.x, hy.y, hy.z);
-            load_coefs6<CMP>(p.vv, p.vi, p.xv_e, p.meta_e, base, cs, (long long)(k + 1) * p.ny + j, p.ny, i0, p.px, ax, ay, az, bx, by, bz);
-            const float4 exn = upd4(ax, ex, bx, hz, hz_jm, hy, hy_km);
-            const float4 eyn = upd4(ay, ey, by, hx, hx_km, hz, hz_im);
-            const float4 ezn = upd4(az, ez, bz, hy, hy_im, hx, hx_jm);
-            st4(eout + base, exn); st4(eout + cs + base, eyn); st4(eout + 2 * cs + base, ezn);
-        }
-        hx_km = hx; hy_km = hy;
-    }
-}
-
-
-// ---- the register version again, with the address arithmetic written out ----
-// update_he_kernel spends ~60 % of its instructions on 64-bit index arithmetic and on the "row streamed in full"
-// alternative of every coefficient; with 16 warps per SM that, not DRAM, bounds it.  Here every array has one per-thread
-// byte pointer that advances by a plane per iteration, all other offsets are launch constants, the x-vector of a
-// compressed row is one mad.wide away, and rows with a slot streamed in full take a (warp-uniform) side path.
 __device__ __forceinline__ float4 ldb4(const char* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ float4 ldb4_cs(const char* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float4 ldb4_nc(const char* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
@@ -317,450 +184,6 @@ __device__ __forceinline__ void row_coefs(const float4 m0, const float4 m1, cons
     }
 }
 
-template <int TY>
-__global__ void __launch_bounds__(32 * (TY + 1)) __maxnreg__(TY == 5 ? 112 : (TY == 9 ? 96 : 128)) update_he2_kernel(const HeParams p)
-{
-    __shared__ float4 xb[2][TY + 1][2][32];
-    // row records of the H and E pass, staged one plane ahead by the warp that uses them (lanes 0-3, cp.async): the
-    // records steer dependent loads, so they must not cost a cache miss on the critical path of the march
-    __shared__ float4 ms[2][TY + 1][4];
-    // the CTA's 128-column slice of every x-vector ([nv_h + nv_e][32] float4, loaded once): a coefficient of a compressed
-    // row is one LDS and one multiply
-    extern __shared__ float4 xs_all[];
-    const int lane = threadIdx.x, r = threadIdx.y;
-    const int i0 = p.X0 - 4 + HE_SEG * (int)blockIdx.x + 4 * lane;
-    {
-        const bool col_ok = i0 >= 0 && i0 < p.px;
-        for (int v = r; v < p.nv_h + p.nv_e; v += TY + 1) {
-            const float* src = v < p.nv_h ? p.xv_h + (size_t)v * p.px : p.xv_e + (size_t)(v - p.nv_h) * p.px;
-            xs_all[v * 32 + lane] = col_ok ? __ldg(reinterpret_cast<const float4*>(src + i0)) : zero4();
-        }
-    }
-    const float4* xsh = xs_all + lane;
-    const float4* xse = xs_all + p.nv_h * 32 + lane;
-    const int j = p.Y0 - 1 + TY * (int)blockIdx.y + r;
-    const int kbeg = p.Z0 + (int)blockIdx.z * p.kz;
-    const int kend = min(kbeg + p.kz, p.Z1);
-    const bool in_grid = i0 >= 0 && i0 < p.px && j >= 0 && j < p.Y1;
-    const bool reg_x = (i0 >= p.X0 && i0 < p.X1) || i0 >= p.XT0;
-    const bool ext = in_grid && (!reg_x || j < p.Y0);
-    const bool calc = in_grid && !ext;
-    const bool own = calc && lane >= 1 && r >= 1;
-    const bool has_jp = in_grid && j + 1 < p.ny;
-    const bool edge_load = in_grid && lane == 31 && i0 + 4 < p.px;
-    const bool row_ok = j >= 0 && j < p.Y1;                  // the row has records (warp-uniform)
-    const int kfirst = kbeg > p.Z0 ? kbeg - 1 : kbeg;
-    const long long base0 = (long long)(kfirst + 1) * p.sz + (long long)j * p.px + i0;
-    const long long mrow0 = ((long long)(kfirst + 1) * p.ny + j) * 32;
-    // per-thread plane pointers (never dereferenced where the thread is outside the grid)
-    const char* pe = reinterpret_cast<const char*>(p.ein + base0);
-    const char* ph = reinterpret_cast<const char*>(p.hin + base0);
-    char* qe = reinterpret_cast<char*>(p.eout + base0);
-    char* qh = reinterpret_cast<char*>(p.hout + base0);
-    // lanes 0,1 stage the H record, lanes 2,3 the E record of this warp's row
-    const char* mrec = (lane < 2 ? reinterpret_cast<const char*>(p.meta_h) : reinterpret_cast<const char*>(p.meta_e)) + mrow0 + (lane & 1) * 16;
-
-    float4 ex = zero4(), ey = zero4(), ez = zero4();         // E_old(k)
-    float4 hx_km = zero4(), hy_km = zero4();                 // H_new(k-1)
-    if (lane < 4) cp_async16(&ms[kfirst & 1][r][lane], row_ok ? mrec : reinterpret_cast<const char*>(p.meta_h), row_ok);
-    cp_async_commit();
-    if (in_grid) { ex = ldb4(pe); ey = ldb4(pe + p.b_cs); ez = ldb4(pe + p.b_2cs); }
-    if (kfirst == kbeg && own) { hx_km = ldb4(qh - p.b_sz); hy_km = ldb4(qh - p.b_sz + p.b_cs); }
-    cp_async_wait<0>();
-    __syncthreads();                                         // x-vector slices and the first records are in place
-
-    for (int k = kfirst; k < kend; ++k, pe += p.b_sz, ph += p.b_sz, qe += p.b_sz, qh += p.b_sz, mrec += p.meta_step) {
-        const bool pro = k < kbeg;
-        float4 ex1 = zero4(), ey1 = zero4(), ez1 = zero4(), ez_jp = zero4(), ex_jp = zero4();
-        float4 hx = zero4(), hy = zero4(), hz = zero4();
-        float4 ax = zero4(), ay = zero4(), az = zero4(), bx = zero4(), by = zero4(), bz = zero4();
-        float ez_e = 0.f, ey_e = 0.f;
-        // next plane's records (ghost planes have records too)
-        if (lane < 4) cp_async16(&ms[(k + 1) & 1][r][lane], row_ok ? mrec + p.meta_step : reinterpret_cast<const char*>(p.meta_h), row_ok);
-        cp_async_commit();
-        if (in_grid) {
-            if (p.pf > 0 && k + 1 < kend) {
-                if (p.pf == 2) {
-                    prefetch_l1(pe + p.b_pfe[0]); prefetch_l1(pe + p.b_pfe[1]); prefetch_l1(pe + p.b_pfe[2]);
-                    if (calc) { prefetch_l1(ph + p.b_pfh[0]); prefetch_l1(ph + p.b_pfh[1]); prefetch_l1(ph + p.b_pfh[2]); }
-                } else {
-                    prefetch_l2(pe + p.b_pfe[0]); prefetch_l2(pe + p.b_pfe[1]); prefetch_l2(pe + p.b_pfe[2]);
-                    if (calc) { prefetch_l2(ph + p.b_pfh[0]); prefetch_l2(ph + p.b_pfh[1]); prefetch_l2(ph + p.b_pfh[2]); }
-                }
-            }
-            ex1 = ldb4(pe + p.b_sz); ey1 = ldb4(pe + p.b_sz_cs); ez1 = ldb4(pe + p.b_sz_2cs);
-            if (has_jp) { ex_jp = ldb4(pe + p.b_row); ez_jp = ldb4(pe + p.b_row_2cs); }
-        }
-        if (calc) {
-            hx = ldb4_cs(ph); hy = ldb4_cs(ph + p.b_cs); hz = ldb4_cs(ph + p.b_2cs);
-            row_coefs(ms[k & 1][r][0], ms[k & 1][r][1], xsh, p.ii, p.iv, p.xv_h,
-                      (long long)((ph - reinterpret_cast<const char*>(p.hin)) >> 2), p.cs, i0, p.px, ax, ay, az, bx, by, bz);
-        } else if (ext) {
-            hx = ldb4(qh); hy = ldb4(qh + p.b_cs); hz = ldb4(qh + p.b_2cs);
-        }
-        if (edge_load) { ey_e = *reinterpret_cast<const float*>(pe + p.b_cs + 16); ez_e = *reinterpret_cast<const float*>(pe + p.b_2cs + 16); }
-        float ez_r = __shfl_down_sync(0xffffffffu, ez.x, 1);
-        float ey_r = __shfl_down_sync(0xffffffffu, ey.x, 1);
-        if (lane == 31) { ez_r = ez_e; ey_r = ey_e; }
-        if (calc) {
-            const float4 ez_ip = make_float4(ez.y, ez.z, ez.w, ez_r);
-            const float4 ey_ip = make_float4(ey.y, ey.z, ey.w, ey_r);
-            hx = upd4(ax, hx, bx, ez, ez_jp, ey, ey1);
-            hy = upd4(ay, hy, by, ex, ex1, ez, ez_ip);
-            hz = upd4(az, hz, bz, ey, ey_ip, ex, ex_jp);
-        }
-        if (own && !pro) {
-            stb4(qh, hx); stb4(qh + p.b_cs, hy); stb4(qh + p.b_2cs, hz);
-            // the E coefficients do not depend on H_new: fetch them before the barrier, into the registers the H pass freed
-            row_coefs(ms[k & 1][r][2], ms[k & 1][r][3], xse, p.vv, p.vi, p.xv_e,
-                      (long long)((pe - reinterpret_cast<const char*>(p.ein)) >> 2), p.cs, i0, p.px, ax, ay, az, bx, by, bz);
-        }
-        xb[k & 1][r][0][lane] = hz; xb[k & 1][r][1][lane] = hx;
-        cp_async_wait<0>();                                  // next plane's records (this warp's own copies)
-        __syncthreads();
-        const float hz_l = __shfl_up_sync(0xffffffffu, hz.w, 1);
-        const float hy_l = __shfl_up_sync(0xffffffffu, hy.w, 1);
-        if (own && !pro) {
-            const float4 hz_jm = xb[k & 1][r - 1][0][lane], hx_jm = xb[k & 1][r - 1][1][lane];
-            const float4 hz_im = make_float4(hz_l, hz.x, hz.y, hz.z);
-            const float4 hy_im = make_float4(hy_l, hy.x, hy.y, hy.z);
-            ex = upd4(ax, ex, bx, hz, hz_jm, hy, hy_km);
-            ey = upd4(ay, ey, by, hx, hx_km, hz, hz_im);
-            ez = upd4(az, ez, bz, hy, hy_im, hx, hx_jm);
-            stb4(qe, ex); stb4(qe + p.b_cs, ey); stb4(qe + p.b_2cs, ez);
-        }
-        hx_km = hx; hy_km = hy;
-        ex = ex1; ey = ey1; ez = ez1;
-    }
-}
-
-
-// ---- update_he2_kernel with the field planes staged one plane ahead by cp.async ----
-// ncu on update_he2_kernel: a third of all stall samples sit on the first use of the plane's global loads (L2 latency
-// under load, 16 warps per SM to hide it) and a fifth on the barrier.  Here every thread copies the float4s it needs for
-// the NEXT plane straight into shared memory at the top of the iteration (LDGSTS: no registers held, a whole plane of the
-// CTA in flight while the current one is computed); the plane being computed is read from shared memory, including the
-// +1 row (y-neighbour) and the +1 column of lane 31, so no second global load and no carried E registers.  With the
-// x-vector slices already in shared memory the smaller L1 no longer matters (it did for update_he_staged_kernel).
-//   es: E ring, 3 planes (k, k+1 in use, k+2 landing)  [3][3 comps][TY+2 rows][33 float4]
-//   hs: H ring, 2 planes (k in use, k+1 landing)       [2][3 comps][TY+1 rows][32 float4]
-template <int TY>
-struct He3Smem {
-    float4 es[3][3][TY + 2][33];
-    float4 hs[2][3][TY + 1][32];
-    float4 xb[2][TY + 1][2][32];
-    float4 ms[2][TY + 1][4];
-    float4 xs[1];                                            // [nv_h + nv_e][32], sized at launch
-};
-
-template <int TY>
-__global__ void __launch_bounds__(32 * (TY + 1), 16 / (TY + 1)) update_he3_kernel(const HeParams p)
-{
-    extern __shared__ __align__(16) unsigned char he3_raw[];
-    He3Smem<TY>& S = *reinterpret_cast<He3Smem<TY>*>(he3_raw);
-    const int lane = threadIdx.x, r = threadIdx.y;
-    const int i0 = p.X0 - 4 + HE_SEG * (int)blockIdx.x + 4 * lane;
-    const int j = p.Y0 - 1 + TY * (int)blockIdx.y + r;
-    const int kbeg = p.Z0 + (int)blockIdx.z * p.kz;
-    const int kend = min(kbeg + p.kz, p.Z1);
-    const bool col_ok = i0 >= 0 && i0 < p.px;
-    {
-        for (int v = r; v < p.nv_h + p.nv_e; v += TY + 1) {
-            const float* src = v < p.nv_h ? p.xv_h + (size_t)v * p.px : p.xv_e + (size_t)(v - p.nv_h) * p.px;
-            S.xs[v * 32 + lane] = col_ok ? __ldg(reinterpret_cast<const float4*>(src + i0)) : zero4();
-        }
-    }
-    const float4* xsh = S.xs + lane;
-    const float4* xse = S.xs + p.nv_h * 32 + lane;
-    const bool in_grid = col_ok && j >= 0 && j < p.Y1;
-    const bool reg_x = (i0 >= p.X0 && i0 < p.X1) || i0 >= p.XT0;
-    const bool ext = in_grid && (!reg_x || j < p.Y0);
-    const bool calc = in_grid && !ext;
-    const bool own = calc && lane >= 1 && r >= 1;
-    const bool row_ok = j >= 0 && j < p.Y1;
-    // what this thread stages per plane: its own float4 of E (rows up to Y1, the +1 row of the last owned row), the +1 row
-    // for the top warp, the +1 column for lane 31, its own float4 of H_old where H_new is computed, 16 bytes of a record
-    const bool e_ok = col_ok && j >= 0 && j < p.ny && j <= p.Y1;
-    const bool top = r == TY;
-    const bool e_top_ok = top && col_ok && j + 1 >= 0 && j + 1 < p.ny && j + 1 <= p.Y1;
-    const bool e_col_ok = lane == 31 && i0 + 4 < p.px && j >= 0 && j < p.Y1;
-    const int kfirst = kbeg > p.Z0 ? kbeg - 1 : kbeg;
-    const long long base0 = (long long)(kfirst + 1) * p.sz + (long long)j * p.px + i0;
-    const long long mrow0 = ((long long)(kfirst + 1) * p.ny + j) * 32;
-    const char* pe = reinterpret_cast<const char*>(p.ein + base0);          // plane k of E_old / H_old / outputs
-    const char* ph = reinterpret_cast<const char*>(p.hin + base0);
-    char* qe = reinterpret_cast<char*>(p.eout + base0);
-    char* qh = reinterpret_cast<char*>(p.hout + base0);
-    const char* mrec = (lane < 2 ? reinterpret_cast<const char*>(p.meta_h) : reinterpret_cast<const char*>(p.meta_e)) + mrow0 + (lane & 1) * 16;
-    const char* safe = reinterpret_cast<const char*>(p.ein);               // any valid address for the zero-fill copies
-
-    // stage E_old of the plane d planes above the current one into ring slot se
-    auto stage_e = [&](int se, long long d) {
-        const char* b = pe + d;
-        cp_async16(&S.es[se][0][r][lane], e_ok ? b : safe, e_ok);
-        cp_async16(&S.es[se][1][r][lane], e_ok ? b + p.b_cs : safe, e_ok);
-        cp_async16(&S.es[se][2][r][lane], e_ok ? b + p.b_2cs : safe, e_ok);
-        if (top) {
-            cp_async16(&S.es[se][0][TY + 1][lane], e_top_ok ? b + p.b_row : safe, e_top_ok);
-            cp_async16(&S.es[se][2][TY + 1][lane], e_top_ok ? b + p.b_row_2cs : safe, e_top_ok);
-        }
-        if (lane == 31) {
-            cp_async16(&S.es[se][1][r][32], e_col_ok ? b + p.b_cs + 16 : safe, e_col_ok);
-            cp_async16(&S.es[se][2][r][32], e_col_ok ? b + p.b_2cs + 16 : safe, e_col_ok);
-        }
-    };
-    auto stage_h = [&](int sh, long long d) {
-        const char* b = ph + d;
-        cp_async16(&S.hs[sh][0][r][lane], calc ? b : safe, calc);
-        cp_async16(&S.hs[sh][1][r][lane], calc ? b + p.b_cs : safe, calc);
-        cp_async16(&S.hs[sh][2][r][lane], calc ? b + p.b_2cs : safe, calc);
-    };
-
-    int se = 0, sh = 0;                                      // ring slots of plane k
-    stage_e(0, 0); stage_e(1, p.b_sz); stage_h(0, 0);
-    if (lane < 4) cp_async16(&S.ms[0][r][lane], row_ok ? mrec : safe, row_ok);
-    cp_async_commit();
-    float4 hx_km = zero4(), hy_km = zero4();                 // H_new(k-1)
-    if (kfirst == kbeg && own) { hx_km = ldb4(qh - p.b_sz); hy_km = ldb4(qh - p.b_sz + p.b_cs); }
-    cp_async_wait<0>();
-    __syncthreads();
-
-    for (int k = kfirst; k < kend; ++k, pe += p.b_sz, ph += p.b_sz, qe += p.b_sz, qh += p.b_sz, mrec += p.meta_step) {
-        const bool pro = k < kbeg;
-        const int se1 = se == 2 ? 0 : se + 1, se2 = se1 == 2 ? 0 : se1 + 1, mb = (k - kfirst) & 1;
-        if (k + 1 < kend) {                                  // next iteration's new data: E(k+2), H_old(k+1), records of k+1
-            stage_e(se2, 2 * p.b_sz); stage_h(sh ^ 1, p.b_sz);
-            if (lane < 4) cp_async16(&S.ms[mb ^ 1][r][lane], row_ok ? mrec + p.meta_step : safe, row_ok);
-        }
-        cp_async_commit();
-        float4 hx = zero4(), hy = zero4(), hz = zero4();
-        float4 ax = zero4(), ay = zero4(), az = zero4(), bx = zero4(), by = zero4(), bz = zero4();
-        const float4 ex = S.es[se][0][r][lane], ey = S.es[se][1][r][lane], ez = S.es[se][2][r][lane];
-        if (calc) {
-            hx = S.hs[sh][0][r][lane]; hy = S.hs[sh][1][r][lane]; hz = S.hs[sh][2][r][lane];
-            row_coefs(S.ms[mb][r][0], S.ms[mb][r][1], xsh, p.ii, p.iv, p.xv_h,
-                      (long long)((ph - reinterpret_cast<const char*>(p.hin)) >> 2), p.cs, i0, p.px, ax, ay, az, bx, by, bz);
-        } else if (ext) {
-            hx = ldb4(qh); hy = ldb4(qh + p.b_cs); hz = ldb4(qh + p.b_2cs);
-        }
-        float ez_r = __shfl_down_sync(0xffffffffu, ez.x, 1);
-        float ey_r = __shfl_down_sync(0xffffffffu, ey.x, 1);
-        if (lane == 31) { ez_r = S.es[se][2][r][32].x; ey_r = S.es[se][1][r][32].x; }
-        if (calc) {
-            const float4 ex1 = S.es[se1][0][r][lane], ey1 = S.es[se1][1][r][lane];
-            const float4 ex_jp = S.es[se][0][r + 1][lane], ez_jp = S.es[se][2][r + 1][lane];
-            const float4 ez_ip = make_float4(ez.y, ez.z, ez.w, ez_r);
-            const float4 ey_ip = make_float4(ey.y, ey.z, ey.w, ey_r);
-            hx = upd4(ax, hx, bx, ez, ez_jp, ey, ey1);
-            hy = upd4(ay, hy, by, ex, ex1, ez, ez_ip);
-            hz = upd4(az, hz, bz, ey, ey_ip, ex, ex_jp);
-        }
-        if (own && !pro) {
-            stb4(qh, hx); stb4(qh + p.b_cs, hy); stb4(qh + p.b_2cs, hz);
-            row_coefs(S.ms[mb][r][2], S.ms[mb][r][3], xse, p.vv, p.vi, p.xv_e,
-                      (long long)((pe - reinterpret_cast<const char*>(p.ein)) >> 2), p.cs, i0, p.px, ax, ay, az, bx, by, bz);
-        }
-        S.xb[mb][r][0][lane] = hz; S.xb[mb][r][1][lane] = hx;
-        cp_async_wait<0>();                                  // next plane has landed (this thread's copies) ...
-        __syncthreads();                                     // ... and everybody's, together with this plane's H_new rows
-        const float hz_l = __shfl_up_sync(0xffffffffu, hz.w, 1);
-        const float hy_l = __shfl_up_sync(0xffffffffu, hy.w, 1);
-        if (own && !pro) {
-            const float4 hz_jm = S.xb[mb][r - 1][0][lane], hx_jm = S.xb[mb][r - 1][1][lane];
-            const float4 hz_im = make_float4(hz_l, hz.x, hz.y, hz.z);
-            const float4 hy_im = make_float4(hy_l, hy.x, hy.y, hy.z);
-            const float4 exn = upd4(ax, ex, bx, hz, hz_jm, hy, hy_km);
-            const float4 eyn = upd4(ay, ey, by, hx, hx_km, hz, hz_im);
-            const float4 ezn = upd4(az, ez, bz, hy, hy_im, hx, hx_jm);
-            stb4(qe, exn); stb4(qe + p.b_cs, eyn); stb4(qe + p.b_2cs, ezn);
-        }
-        hx_km = hx; hy_km = hy;
-        se = se1; sh ^= 1;
-    }
-}
-
-
-// ---- update_he3_kernel without the CTA barrier ----
-// ncu on update_he3_kernel: 30 % of the stall samples sit on the per-plane __syncthreads (8 warps in lock step, the
-// slowest warp's memory latency is everybody's).  A warp only needs its two neighbours: the H_new row of the warp below,
-// the staged +1 row of the warp above.  Three monotonic per-warp counters in shared memory replace the barrier:
-//   prod[w] = planes whose H_new row warp w has published (xb is 2 deep: w waits for rd[w+1] >= t-1 before reuse)
-//   stg[w]  = planes whose staged copies of warp w have landed (+1: plane t+1 is in place when stg[w] >= t+2)
-//   rd[w]   = planes for which warp w is done reading other warps' data (w+1 may then reuse the E ring slot)
-// Every wait is for a warp at an earlier or equal plane, so the slowest warp can always proceed (no cycle).
-__device__ __forceinline__ void spin_ge(const volatile int* f, int v)
-{
-    while (*f < v) { }
-    __threadfence_block();
-}
-__device__ __forceinline__ void publish1(volatile int* f, int v)
-{
-    __syncwarp();
-    __threadfence_block();
-    if (threadIdx.x == 0) *f = v;
-}
-__device__ __forceinline__ void publish2(volatile int* f, int v, volatile int* g, int w)
-{
-    __syncwarp();
-    __threadfence_block();
-    if (threadIdx.x == 0) { *f = v; *g = w; }
-}
-template <int TY>
-struct He4Smem {
-    float4 es[3][3][TY + 2][33];
-    float4 hs[2][3][TY + 1][32];
-    float4 xb[2][TY + 1][2][32];
-    float4 ms[2][TY + 1][4];
-    int prod[TY + 2], rd[TY + 2], stg[TY + 2];               // per-warp progress counters (see update_he4_kernel)
-    int pad_[(4 - (3 * (TY + 2)) % 4) % 4];
-    float4 xs[1];                                            // [nv_h + nv_e][32], sized at launch
-};
-
-template <int TY>
-__global__ void __launch_bounds__(32 * (TY + 1), 16 / (TY + 1)) update_he4_kernel(const HeParams p)
-{
-    extern __shared__ __align__(16) unsigned char he4_raw[];
-    He4Smem<TY>& S = *reinterpret_cast<He4Smem<TY>*>(he4_raw);
-    const int lane = threadIdx.x, r = threadIdx.y;
-    const int i0 = p.X0 - 4 + HE_SEG * (int)blockIdx.x + 4 * lane;
-    const int j = p.Y0 - 1 + TY * (int)blockIdx.y + r;
-    const int kbeg = p.Z0 + (int)blockIdx.z * p.kz;
-    const int kend = min(kbeg + p.kz, p.Z1);
-    const bool col_ok = i0 >= 0 && i0 < p.px;
-    {
-        for (int v = r; v < p.nv_h + p.nv_e; v += TY + 1) {
-            const float* src = v < p.nv_h ? p.xv_h + (size_t)v * p.px : p.xv_e + (size_t)(v - p.nv_h) * p.px;
-            S.xs[v * 32 + lane] = col_ok ? __ldg(reinterpret_cast<const float4*>(src + i0)) : zero4();
-        }
-    }
-    const float4* xsh = S.xs + lane;
-    const float4* xse = S.xs + p.nv_h * 32 + lane;
-    const bool in_grid = col_ok && j >= 0 && j < p.Y1;
-    const bool reg_x = (i0 >= p.X0 && i0 < p.X1) || i0 >= p.XT0;
-    const bool ext = in_grid && (!reg_x || j < p.Y0);
-    const bool calc = in_grid && !ext;
-    const bool own = calc && lane >= 1 && r >= 1;
-    const bool row_ok = j >= 0 && j < p.Y1;
-    // what this thread stages per plane: its own float4 of E (rows up to Y1, the +1 row of the last owned row), the +1 row
-    // for the top warp, the +1 column for lane 31, its own float4 of H_old where H_new is computed, 16 bytes of a record
-    const bool e_ok = col_ok && j >= 0 && j < p.ny && j <= p.Y1;
-    const bool top = r == TY;
-    const bool e_top_ok = top && col_ok && j + 1 >= 0 && j + 1 < p.ny && j + 1 <= p.Y1;
-    const bool e_col_ok = lane == 31 && i0 + 4 < p.px && j >= 0 && j < p.Y1;
-    const int kfirst = kbeg > p.Z0 ? kbeg - 1 : kbeg;
-    const long long base0 = (long long)(kfirst + 1) * p.sz + (long long)j * p.px + i0;
-    const long long mrow0 = ((long long)(kfirst + 1) * p.ny + j) * 32;
-    const char* pe = reinterpret_cast<const char*>(p.ein + base0);          // plane k of E_old / H_old / outputs
-    const char* ph = reinterpret_cast<const char*>(p.hin + base0);
-    char* qe = reinterpret_cast<char*>(p.eout + base0);
-    char* qh = reinterpret_cast<char*>(p.hout + base0);
-    const char* mrec = (lane < 2 ? reinterpret_cast<const char*>(p.meta_h) : reinterpret_cast<const char*>(p.meta_e)) + mrow0 + (lane & 1) * 16;
-    const char* safe = reinterpret_cast<const char*>(p.ein);               // any valid address for the zero-fill copies
-
-    // stage E_old of the plane d planes above the current one into ring slot se
-    auto stage_e = [&](int se, long long d) {
-        const char* b = pe + d;
-        cp_async16(&S.es[se][0][r][lane], e_ok ? b : safe, e_ok);
-        cp_async16(&S.es[se][1][r][lane], e_ok ? b + p.b_cs : safe, e_ok);
-        cp_async16(&S.es[se][2][r][lane], e_ok ? b + p.b_2cs : safe, e_ok);
-        if (top) {
-            cp_async16(&S.es[se][0][TY + 1][lane], e_top_ok ? b + p.b_row : safe, e_top_ok);
-            cp_async16(&S.es[se][2][TY + 1][lane], e_top_ok ? b + p.b_row_2cs : safe, e_top_ok);
-        }
-        if (lane == 31) {
-            cp_async16(&S.es[se][1][r][32], e_col_ok ? b + p.b_cs + 16 : safe, e_col_ok);
-            cp_async16(&S.es[se][2][r][32], e_col_ok ? b + p.b_2cs + 16 : safe, e_col_ok);
-        }
-    };
-    auto stage_h = [&](int sh, long long d) {
-        const char* b = ph + d;
-        cp_async16(&S.hs[sh][0][r][lane], calc ? b : safe, calc);
-        cp_async16(&S.hs[sh][1][r][lane], calc ? b + p.b_cs : safe, calc);
-        cp_async16(&S.hs[sh][2][r][lane], calc ? b + p.b_2cs : safe, calc);
-    };
-
-    int se = 0, sh = 0;                                      // ring slots of plane k
-    stage_e(0, 0); stage_e(1, p.b_sz); stage_h(0, 0);
-    if (lane < 4) cp_async16(&S.ms[0][r][lane], row_ok ? mrec : safe, row_ok);
-    cp_async_commit();
-    float4 hx_km = zero4(), hy_km = zero4();                 // H_new(k-1)
-    if (kfirst == kbeg && own) { hx_km = ldb4(qh - p.b_sz); hy_km = ldb4(qh - p.b_sz + p.b_cs); }
-    if (lane == 0) { S.prod[r] = 0; S.rd[r] = 0; S.stg[r] = 1; }
-    cp_async_wait<0>();
-    __syncthreads();
-    volatile int* const prod = S.prod; volatile int* const rd = S.rd; volatile int* const stg = S.stg;
-
-    for (int k = kfirst; k < kend; ++k, pe += p.b_sz, ph += p.b_sz, qe += p.b_sz, qh += p.b_sz, mrec += p.meta_step) {
-        const bool pro = k < kbeg;
-        const int t = k - kfirst;
-        const int se1 = se == 2 ? 0 : se + 1, se2 = se1 == 2 ? 0 : se1 + 1, mb = t & 1;
-        // ring slot se2 held plane k-1, whose row r the warp below read during its iteration t-1
-        if (r >= 1 && t >= 1) spin_ge(&rd[r - 1], t);
-        if (k + 1 < kend) {                                  // next iteration's new data: E(k+2), H_old(k+1), records of k+1
-            stage_e(se2, 2 * p.b_sz); stage_h(sh ^ 1, p.b_sz);
-            if (lane < 4) cp_async16(&S.ms[mb ^ 1][r][lane], row_ok ? mrec + p.meta_step : safe, row_ok);
-        }
-        cp_async_commit();
-        float4 hx = zero4(), hy = zero4(), hz = zero4();
-        float4 ax = zero4(), ay = zero4(), az = zero4(), bx = zero4(), by = zero4(), bz = zero4();
-        if (r < TY) spin_ge(&stg[r + 1], t + 1);             // row r+1 of plane k is staged by the warp above
-        const float4 ex = S.es[se][0][r][lane], ey = S.es[se][1][r][lane], ez = S.es[se][2][r][lane];
-        if (calc) {
-            hx = S.hs[sh][0][r][lane]; hy = S.hs[sh][1][r][lane]; hz = S.hs[sh][2][r][lane];
-            row_coefs(S.ms[mb][r][0], S.ms[mb][r][1], xsh, p.ii, p.iv, p.xv_h,
-                      (long long)((ph - reinterpret_cast<const char*>(p.hin)) >> 2), p.cs, i0, p.px, ax, ay, az, bx, by, bz);
-        } else if (ext) {
-            hx = ldb4(qh); hy = ldb4(qh + p.b_cs); hz = ldb4(qh + p.b_2cs);
-        }
-        float ez_r = __shfl_down_sync(0xffffffffu, ez.x, 1);
-        float ey_r = __shfl_down_sync(0xffffffffu, ey.x, 1);
-        if (lane == 31) { ez_r = S.es[se][2][r][32].x; ey_r = S.es[se][1][r][32].x; }
-        if (calc) {
-            const float4 ex1 = S.es[se1][0][r][lane], ey1 = S.es[se1][1][r][lane];
-            const float4 ex_jp = S.es[se][0][r + 1][lane], ez_jp = S.es[se][2][r + 1][lane];
-            const float4 ez_ip = make_float4(ez.y, ez.z, ez.w, ez_r);
-            const float4 ey_ip = make_float4(ey.y, ey.z, ey.w, ey_r);
-            hx = upd4(ax, hx, bx, ez, ez_jp, ey, ey1);
-            hy = upd4(ay, hy, by, ex, ex1, ez, ez_ip);
-            hz = upd4(az, hz, bz, ey, ey_ip, ex, ex_jp);
-        }
-        if (own && !pro) {
-            stb4(qh, hx); stb4(qh + p.b_cs, hy); stb4(qh + p.b_2cs, hz);
-            row_coefs(S.ms[mb][r][2], S.ms[mb][r][3], xse, p.vv, p.vi, p.xv_e,
-                      (long long)((pe - reinterpret_cast<const char*>(p.ein)) >> 2), p.cs, i0, p.px, ax, ay, az, bx, by, bz);
-        }
-        // publish this plane's H_new row for the warp above (it must have consumed the row of two planes ago) ...
-        if (r < TY && t >= 2) spin_ge(&rd[r + 1], t - 1);
-        S.xb[mb][r][0][lane] = hz; S.xb[mb][r][1][lane] = hx;
-        cp_async_wait<0>();                                  // ... and the staged data of the next plane (this warp's copies)
-        publish2(&prod[r], t + 1, &stg[r], t + 2);
-        if (r >= 1) spin_ge(&prod[r - 1], t + 1);            // the row below has published H_new(k)
-        const float hz_l = __shfl_up_sync(0xffffffffu, hz.w, 1);
-        const float hy_l = __shfl_up_sync(0xffffffffu, hy.w, 1);
-        float4 hz_jm = zero4(), hx_jm = zero4();
-        if (r >= 1) { hz_jm = S.xb[mb][r - 1][0][lane]; hx_jm = S.xb[mb][r - 1][1][lane]; }
-        publish1(&rd[r], t + 1);                             // done with every other warp's data of this plane
-        if (own && !pro) {
-            const float4 hz_im = make_float4(hz_l, hz.x, hz.y, hz.z);
-            const float4 hy_im = make_float4(hy_l, hy.x, hy.y, hy.z);
-            const float4 exn = upd4(ax, ex, bx, hz, hz_jm, hy, hy_km);
-            const float4 eyn = upd4(ay, ey, by, hx, hx_km, hz, hz_im);
-            const float4 ezn = upd4(az, ez, bz, hy, hy_im, hx, hx_jm);
-            stb4(qe, exn); stb4(qe + p.b_cs, eyn); stb4(qe + p.b_2cs, ezn);
-        }
-        hx_km = hx; hy_km = hy;
-        se = se1; sh ^= 1;
-    }
-}
-
-
-
-// ---- update_he3_kernel with the planes staged by the TMA engine (cp.async.bulk + mbarrier) ----
-// The row segments a CTA stages are contiguous in global memory (33 float4 of E, 32 of H per row and component), so one
-// elected lane per warp hands them to the TMA engine as 1-D bulk copies that complete on an mbarrier; the 256 threads no
-// longer spend ~25 instructions each per plane on LDGSTS and their addresses.  Out-of-grid parts of the ring are zeroed
-// once at the start and never written again (a bulk copy only covers the in-grid part of its row).
-// full[b]: completion of the copies issued during iteration t (consumed in iteration t+1), b = (t+1) & 1.
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
 {
@@ -787,23 +210,73 @@ __device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, unsigned 
                  :: "r"(smem_u32(smem)), "l"(gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-template <int TY>
-struct He5Smem {
-    float4 es[3][3][TY + 2][33];
+
+// ------------------------------------------------------------------------------------
+// update_he6_kernel: the fused H->E launch of the production path
+// ------------------------------------------------------------------------------------
+// One CTA = (TY+1) warps = TY owned rows + the halo row below, 124 owned columns + the halo float4 on the left, marching
+// up in z.  The row segments a CTA needs are contiguous in global memory (33 float4 of E, 32 of H per row and component):
+// one elected lane per warp hands them to the TMA engine as 1-D bulk copies (cp.async.bulk, SASS UBLKCP) that complete on
+// one mbarrier per ring slot.  E ring: planes k and k+1 in use + DE planes landing; H ring: plane k in use + one landing.
+// A slot is refilled as soon as the CTA barrier in the middle of the iteration has passed (every read of plane k is
+// before it), not at the top of the next iteration, so 1.5 / (DE + 0.5) planes are in flight per CTA: the launch is bound
+// by bytes in flight per SM, not by the barrier (every tile shape of the previous generation ran at the same speed because
+// they all kept one plane in flight per ring).  Out-of-grid parts of the rings are zeroed once and never written again.
+//
+// PML rows.  Rows inside a whole-row PML slab (z-slabs: all rows of some planes; y-slabs: some rows of the other planes)
+// are updated by the same warps with the split-flux pre -> update -> post sequence of update_h/e_kernel MODE 1 on the
+// registers they already hold (identical arithmetic per cell).  The halo recompute needs the OLD current flux of cells whose
+// owner may already have written the new one, so the current flux is double buffered like the fields (gin -> gout); the
+// voltage flux is touched by the owner of a cell only and stays in place.
+struct HePmlBox {
+    int y0, by, z0, bz;
+    const float* gin; float* gout;          // current (H) flux [3][bz][by][px]: read copy / written copy
+    float* fv;                              // voltage (E) flux, in place
+    const float *ah, *foh, *fnh;            // ii, iifo, iifn
+    const float *ae, *foe, *fne;            // vv, vvfo, vvfn
+    const float *xvh, *xve; const unsigned char *mh, *me;     // row compression of the slab coefficients (or NULL)
+};
+struct HePml {
+    int zlo, zhi, ym0, ym1;                 // plain planes [zlo,zhi), plain rows [ym0,ym1) of those planes
+    int b_zlo, b_zhi, b_ylo, b_yhi;         // box index of each slab (-1: none)
+    HePmlBox b[4];
+};
+
+// a, fo, fn of component c of a slab row; rec = the row's 48-byte record (9 scales, 9 ids, pad[0] = a slot is streamed in
+// full) or NULL: stream the full arrays.  The record is read where it is used (a warp-uniform L1 hit), not kept in registers.
+__device__ __forceinline__ void pml_coefs(const unsigned char* rec, int c, const float* A, const float* FO, const float* FN,
+        const float* __restrict__ xv, long long lofs, int i0, int px, float4& a, float4& fo, float4& fn)
+{
+    if (rec == nullptr) { a = ld4_nc(A + lofs); fo = ld4_nc(FO + lofs); fn = ld4_nc(FN + lofs); return; }
+    const float* sc = reinterpret_cast<const float*>(rec);
+    const float s0 = __ldg(sc + c), s1 = __ldg(sc + 3 + c), s2 = __ldg(sc + 6 + c);
+    const unsigned i0_ = __ldg(rec + 36 + c), i1_ = __ldg(rec + 39 + c), i2_ = __ldg(rec + 42 + c), full = __ldg(rec + 45);
+    if (full == 0) {
+        const char* pl = reinterpret_cast<const char*>(xv + i0); const unsigned pp = 4u * (unsigned)px;
+        a = xvg4(pl, i0_, pp, s0); fo = xvg4(pl, i1_, pp, s1); fn = xvg4(pl, i2_, pp, s2);
+    } else {
+        a = pcoef4(i0_, s0, A + lofs, xv, i0, px); fo = pcoef4(i1_, s1, FO + lofs, xv, i0, px); fn = pcoef4(i2_, s2, FN + lofs, xv, i0, px);
+    }
+}
+
+template <int TY, int DE>
+struct He6Smem {
+    float4 es[2 + DE][3][TY + 2][33];
     float4 hs[2][3][TY + 1][32];
-    float4 xb[2][TY + 1][2][32];
+    float4 xb[2][TY][2][32];                                 // H_new (hz, hx) of rows 0..TY-1, for the row above
     float4 ms[2][TY + 1][4];
-    unsigned long long full[2];
+    unsigned long long ebar[2 + DE], hbar[2];
     float4 xs[1];                                            // [nv_h + nv_e][32], sized at launch
 };
 
-template <int TY>
-__global__ void __launch_bounds__(32 * (TY + 1), 16 / (TY + 1)) update_he5_kernel(const HeParams p)
+template <int TY, int DE, bool PML>
+__global__ void __launch_bounds__(32 * (TY + 1), 16 / (TY + 1)) update_he6_kernel(const HeParams p, const __grid_constant__ HePml Q)
 {
-    extern __shared__ __align__(16) unsigned char he5_raw[];
-    He5Smem<TY>& S = *reinterpret_cast<He5Smem<TY>*>(he5_raw);
+    constexpr int NS = 2 + DE;
+    extern __shared__ __align__(16) unsigned char he6_raw[];
+    He6Smem<TY, DE>& S = *reinterpret_cast<He6Smem<TY, DE>*>(he6_raw);
     const int lane = threadIdx.x, r = threadIdx.y;
-    const int i_seg = p.X0 - 4 + HE_SEG * (int)blockIdx.x;  // column of lane 0
+    const int i_seg = p.X0s - 4 + HE_SEG * (int)blockIdx.x;  // column of lane 0
     const int i0 = i_seg + 4 * lane;
     const int j = p.Y0 - 1 + TY * (int)blockIdx.y + r;
     const int kbeg = p.Z0 + (int)blockIdx.z * p.kz;
@@ -817,7 +290,10 @@ __global__ void __launch_bounds__(32 * (TY + 1), 16 / (TY + 1)) update_he5_kerne
         float4* z = &S.es[0][0][0][0];
         const int nz4 = (int)((sizeof(S.es) + sizeof(S.hs)) / sizeof(float4));
         for (int q = r * 32 + lane; q < nz4; q += 32 * (TY + 1)) z[q] = zero4();
-        if (r == 0 && lane == 0) { mbar_init(&S.full[0], TY + 1); mbar_init(&S.full[1], TY + 1); }
+        if (r == 0 && lane == 0) {
+            for (int q = 0; q < NS; ++q) mbar_init(&S.ebar[q], TY + 1);
+            mbar_init(&S.hbar[0], TY + 1); mbar_init(&S.hbar[1], TY + 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the zeros are ordered before the TMA writes
     }
@@ -825,10 +301,7 @@ __global__ void __launch_bounds__(32 * (TY + 1), 16 / (TY + 1)) update_he5_kerne
     const float4* xsh = S.xs + lane;
     const float4* xse = S.xs + p.nv_h * 32 + lane;
     const bool in_grid = col_ok && j >= 0 && j < p.Y1;
-    const bool reg_x = (i0 >= p.X0 && i0 < p.X1) || i0 >= p.XT0;
-    const bool ext = in_grid && (!reg_x || j < p.Y0);
-    const bool calc = in_grid && !ext;
-    const bool own = calc && lane >= 1 && r >= 1;
+    const bool reg_x = (i0 >= p.X0 && i0 < p.X1) || i0 >= p.XT0;     // plain rows: columns of the launch region
     const bool row_ok = j >= 0 && j < p.Y1;
     // warp-uniform staging plan: in-grid float4 range [c_lo, c_hi) of the 33-wide E row segment (32-wide for H)
     const int c_lo = i_seg < 0 ? (-i_seg + 3) / 4 : 0;
@@ -837,110 +310,182 @@ __global__ void __launch_bounds__(32 * (TY + 1), 16 / (TY + 1)) update_he5_kerne
     const bool e_top = r == TY && j + 1 >= 0 && j + 1 < p.ny && j + 1 <= p.Y1 && c_hi_e > c_lo;   // +1 row (top warp)
     const bool h_row = j >= p.Y0 && j < p.Y1 && c_hi_h > c_lo;                    // H_old where H_new is computed (j >= Y0 >= 0)
     const unsigned nb_e = (unsigned)(c_hi_e - c_lo) * 16u, nb_h = (unsigned)(c_hi_h - c_lo) * 16u;
+    const unsigned bytes_e = (e_row ? 3u * nb_e : 0u) + (e_top ? 2u * nb_e : 0u), bytes_h = h_row ? 3u * nb_h : 0u;
     const int kfirst = kbeg > p.Z0 ? kbeg - 1 : kbeg;
-    const long long base0 = (long long)(kfirst + 1) * p.sz + (long long)j * p.px + i0;
-    const long long mrow0 = ((long long)(kfirst + 1) * p.ny + j) * 32;
-    const char* pe = reinterpret_cast<const char*>(p.ein + base0);
-    const char* ph = reinterpret_cast<const char*>(p.hin + base0);
-    char* qe = reinterpret_cast<char*>(p.eout + base0);
-    char* qh = reinterpret_cast<char*>(p.hout + base0);
-    // lane 0's view: start of the in-grid part of this warp's row segment in plane k
-    const long long seg0 = (long long)(kfirst + 1) * p.sz + (long long)j * p.px + i_seg + 4 * c_lo;
-    const char* ge = reinterpret_cast<const char*>(p.ein + seg0);
-    const char* gh = reinterpret_cast<const char*>(p.hin + seg0);
-    const char* mrec = (lane < 2 ? reinterpret_cast<const char*>(p.meta_h) : reinterpret_cast<const char*>(p.meta_e)) + mrow0 + (lane & 1) * 16;
+    // one byte offset per thread, advancing by a plane per iteration; every address is a launch-constant base plus it
+    long long boff = 4 * ((long long)(kfirst + 1) * p.sz + (long long)j * p.px + i0);
+    const long long soff = 16LL * (c_lo - lane);             // lane 0: from its own cell to the start of the in-grid part of the row segment
+    const char* const ein_b = reinterpret_cast<const char*>(p.ein); const char* const hin_b = reinterpret_cast<const char*>(p.hin);
+    char* const eout_b = reinterpret_cast<char*>(p.eout); char* const hout_b = reinterpret_cast<char*>(p.hout);
+    const char* mrec = (lane < 2 ? reinterpret_cast<const char*>(p.meta_h) : reinterpret_cast<const char*>(p.meta_e))
+                       + ((long long)(kfirst + 1) * p.ny + j) * 32 + (lane & 1) * 16;
     const char* safe = reinterpret_cast<const char*>(p.ein);
 
-    // lane 0 of every warp: hand the warp's rows of E_old(plane k + de) and H_old(plane k + dh) to the TMA engine
-    auto stage = [&](unsigned long long* bar, int se, bool with_e, long long de, int se_b, bool with_e2, long long de2,
-                     int shs, bool with_h, long long dh) {
+    int tcur = 0;                                            // iteration boff belongs to
+    // lane 0 of every warp: hand this warp's rows of E_old(plane kfirst + d) to the TMA engine, into ring slot `slot`
+    auto stage_e = [&](int slot, int d) {
         if (lane != 0) return;
-        unsigned bytes = 0;
-        if (with_e) bytes += (e_row ? 3u * nb_e : 0u) + (e_top ? 2u * nb_e : 0u);
-        if (with_e2) bytes += (e_row ? 3u * nb_e : 0u) + (e_top ? 2u * nb_e : 0u);
-        if (with_h && h_row) bytes += 3u * nb_h;
-        mbar_arrive_expect(bar, bytes);
-        auto rows_e = [&](int slot, long long d) {
-            if (e_row) {
-                bulk_g2s(&S.es[slot][0][r][c_lo], ge + d, nb_e, bar);
-                bulk_g2s(&S.es[slot][1][r][c_lo], ge + d + p.b_cs, nb_e, bar);
-                bulk_g2s(&S.es[slot][2][r][c_lo], ge + d + p.b_2cs, nb_e, bar);
-            }
-            if (e_top) {
-                bulk_g2s(&S.es[slot][0][TY + 1][c_lo], ge + d + p.b_row, nb_e, bar);
-                bulk_g2s(&S.es[slot][2][TY + 1][c_lo], ge + d + p.b_row_2cs, nb_e, bar);
-            }
-        };
-        if (with_e) rows_e(se, de);
-        if (with_e2) rows_e(se_b, de2);
-        if (with_h && h_row) {
-            bulk_g2s(&S.hs[shs][0][r][c_lo], gh + dh, nb_h, bar);
-            bulk_g2s(&S.hs[shs][1][r][c_lo], gh + dh + p.b_cs, nb_h, bar);
-            bulk_g2s(&S.hs[shs][2][r][c_lo], gh + dh + p.b_2cs, nb_h, bar);
+        unsigned long long* bar = &S.ebar[slot];
+        mbar_arrive_expect(bar, bytes_e);
+        const char* g = ein_b + (boff + soff) + (long long)(d - tcur) * p.b_sz;
+        if (e_row) {
+            bulk_g2s(&S.es[slot][0][r][c_lo], g, nb_e, bar);
+            bulk_g2s(&S.es[slot][1][r][c_lo], g + p.b_cs, nb_e, bar);
+            bulk_g2s(&S.es[slot][2][r][c_lo], g + p.b_2cs, nb_e, bar);
+        }
+        if (e_top) {
+            bulk_g2s(&S.es[slot][0][TY + 1][c_lo], g + p.b_row, nb_e, bar);
+            bulk_g2s(&S.es[slot][2][TY + 1][c_lo], g + p.b_row_2cs, nb_e, bar);
         }
     };
+    auto stage_h = [&](int slot, int d) {
+        if (lane != 0) return;
+        unsigned long long* bar = &S.hbar[slot];
+        mbar_arrive_expect(bar, bytes_h);
+        if (h_row) {
+            const char* g = hin_b + (boff + soff) + (long long)(d - tcur) * p.b_sz;
+            bulk_g2s(&S.hs[slot][0][r][c_lo], g, nb_h, bar);
+            bulk_g2s(&S.hs[slot][1][r][c_lo], g + p.b_cs, nb_h, bar);
+            bulk_g2s(&S.hs[slot][2][r][c_lo], g + p.b_2cs, nb_h, bar);
+        }
+    };
+    // which whole-row PML slab row (j, k) lies in (-1: a plain row); warp-uniform
+    auto pml_box = [&](int k) -> int {
+        if (!PML) return -1;
+        if (k < Q.zlo) return Q.b_zlo;
+        if (k >= Q.zhi) return Q.b_zhi;
+        if (j < Q.ym0) return Q.b_ylo;
+        if (j >= Q.ym1) return Q.b_yhi;
+        return -1;
+    };
 
-    int se = 0, sh = 0;
-    stage(&S.full[0], 0, true, 0, 1, true, p.b_sz, 0, true, 0);              // planes kfirst, kfirst+1 of E, kfirst of H
+    const int nplanes = kend - kfirst;                       // iterations; E planes kfirst .. kend are needed (nplanes + 1)
+#pragma unroll
+    for (int q = 0; q < NS; ++q) if (q <= nplanes) stage_e(q, q);
+    stage_h(0, 0);
+    if (nplanes > 1) stage_h(1, 1);
     if (lane < 4) cp_async16(&S.ms[0][r][lane], row_ok ? mrec : safe, row_ok);
     cp_async_commit();
     float4 hx_km = zero4(), hy_km = zero4();
-    if (kfirst == kbeg && own) { hx_km = ldb4(qh - p.b_sz); hy_km = ldb4(qh - p.b_sz + p.b_cs); }
+    if (kfirst == kbeg && in_grid && lane >= 1 && r >= 1) { hx_km = ldb4(hout_b + boff - p.b_sz); hy_km = ldb4(hout_b + boff - p.b_sz + p.b_cs); }
     cp_async_wait<0>();
     __syncwarp();
+    mbar_wait(&S.ebar[0], 0u);
 
-    for (int k = kfirst; k < kend; ++k, pe += p.b_sz, ph += p.b_sz, qe += p.b_sz, qh += p.b_sz, ge += p.b_sz, gh += p.b_sz, mrec += p.meta_step) {
+    int se = 0;                                              // ring slot of plane k
+    for (int t = 0; t < nplanes; ++t, boff += p.b_sz, mrec += p.meta_step) {
+        const int k = kfirst + t;
+        tcur = t;
+        char* const qh = hout_b + boff;
         const bool pro = k < kbeg;
-        const int t = k - kfirst;
-        const int se1 = se == 2 ? 0 : se + 1, se2 = se1 == 2 ? 0 : se1 + 1, mb = t & 1;
-        // next iteration's new data: E(k+2) -> slot se2, H_old(k+1) -> slot sh^1 (every warp arrives, with or without bytes)
-        stage(&S.full[(t + 1) & 1], se2, k + 1 < kend, 2 * p.b_sz, 0, false, 0, sh ^ 1, k + 1 < kend, p.b_sz);
-        if (k + 1 < kend && lane < 4) cp_async16(&S.ms[mb ^ 1][r][lane], row_ok ? mrec + p.meta_step : safe, row_ok);
+        const int se1 = se + 1 == NS ? 0 : se + 1, sh = t & 1, mb = t & 1;
+        // row type of this iteration (warp-uniform) and what each lane does with its cells
+        const int pb = pml_box(k);
+        const bool regc = PML && pb >= 0 ? true : reg_x;
+        const bool ext = in_grid && (!regc || j < p.Y0);     // H_new was written by a slab launch: read it
+        const bool calc = in_grid && !ext;                   // H_new is computed here (owned cells and halo cells)
+        const bool own = calc && lane >= 1 && r >= 1;        // ... and stored, together with E_new
+        if (t + 1 < nplanes && lane < 4) cp_async16(&S.ms[mb ^ 1][r][lane], row_ok ? mrec + p.meta_step : safe, row_ok);
         cp_async_commit();
-        mbar_wait(&S.full[t & 1], (unsigned)(t >> 1) & 1u);  // this plane's staged rows have landed (all warps' copies)
+        // PML row: slab-local offsets, old flux, row records (issued before the wait on the staged planes)
+        long long lofs = 0, lcs = 0;
+        float4 g0 = zero4(), g1 = zero4(), g2 = zero4();
+        const unsigned char *rech = nullptr, *rece = nullptr;
+        const HePmlBox* B = nullptr;
+        if (PML && pb >= 0) {
+            B = &Q.b[pb];
+            const long long lrow = (long long)(k - B->z0) * B->by + (j - B->y0);
+            lofs = lrow * p.px + i0; lcs = (long long)B->bz * B->by * p.px;
+            if (B->mh) rech = B->mh + lrow * 48;
+            if (B->me) rece = B->me + lrow * 48;
+            if (calc) { g0 = __ldcs(reinterpret_cast<const float4*>(B->gin + lofs)); g1 = __ldcs(reinterpret_cast<const float4*>(B->gin + lcs + lofs));
+                        g2 = __ldcs(reinterpret_cast<const float4*>(B->gin + 2 * lcs + lofs)); }
+        }
+        if (PML) {                                           // pull the slab rows of plane k+2 into L2
+            const int pb2 = k + 2 < kend ? pml_box(k + 2) : -1;
+            if (pb2 >= 0 && in_grid) {
+                const HePmlBox& B2 = Q.b[pb2];
+                const long long l2 = ((long long)(k + 2 - B2.z0) * B2.by + (j - B2.y0)) * p.px + i0, c2 = (long long)B2.bz * B2.by * p.px;
+                prefetch_l2(B2.gin + l2); prefetch_l2(B2.gin + c2 + l2); prefetch_l2(B2.gin + 2 * c2 + l2);
+                prefetch_l2(B2.fv + l2); prefetch_l2(B2.fv + c2 + l2); prefetch_l2(B2.fv + 2 * c2 + l2);
+            }
+        }
         float4 hx = zero4(), hy = zero4(), hz = zero4();
+        if (ext) { hx = ldb4(qh); hy = ldb4(qh + p.b_cs); hz = ldb4(qh + p.b_2cs); }
+        mbar_wait(&S.ebar[se1], (unsigned)((t + 1) / NS) & 1u);  // plane k+1 has landed (plane k was waited for one iteration ago)
+        mbar_wait(&S.hbar[sh], (unsigned)(t >> 1) & 1u);
         float4 ax = zero4(), ay = zero4(), az = zero4(), bx = zero4(), by = zero4(), bz = zero4();
         const float4 ex = S.es[se][0][r][lane], ey = S.es[se][1][r][lane], ez = S.es[se][2][r][lane];
-        if (calc) {
-            hx = S.hs[sh][0][r][lane]; hy = S.hs[sh][1][r][lane]; hz = S.hs[sh][2][r][lane];
-            row_coefs(S.ms[mb][r][0], S.ms[mb][r][1], xsh, p.ii, p.iv, p.xv_h,
-                      (long long)((ph - reinterpret_cast<const char*>(p.hin)) >> 2), p.cs, i0, p.px, ax, ay, az, bx, by, bz);
-        } else if (ext) {
-            hx = ldb4(qh); hy = ldb4(qh + p.b_cs); hz = ldb4(qh + p.b_2cs);
-        }
         float ez_r = __shfl_down_sync(0xffffffffu, ez.x, 1);
         float ey_r = __shfl_down_sync(0xffffffffu, ey.x, 1);
         if (lane == 31) { ez_r = S.es[se][2][r][32].x; ey_r = S.es[se][1][r][32].x; }
         if (calc) {
+            hx = S.hs[sh][0][r][lane]; hy = S.hs[sh][1][r][lane]; hz = S.hs[sh][2][r][lane];
+            row_coefs(S.ms[mb][r][0], S.ms[mb][r][1], xsh, p.ii, p.iv, p.xv_h,
+                      boff >> 2, p.cs, i0, p.px, ax, ay, az, bx, by, bz);
             const float4 ex1 = S.es[se1][0][r][lane], ey1 = S.es[se1][1][r][lane];
             const float4 ex_jp = S.es[se][0][r + 1][lane], ez_jp = S.es[se][2][r + 1][lane];
             const float4 ez_ip = make_float4(ez.y, ez.z, ez.w, ez_r);
             const float4 ey_ip = make_float4(ey.y, ey.z, ey.w, ey_r);
-            hx = upd4(ax, hx, bx, ez, ez_jp, ey, ey1);
-            hy = upd4(ay, hy, by, ex, ex1, ez, ez_ip);
-            hz = upd4(az, hz, bz, ey, ey_ip, ex, ex_jp);
+            if (PML && pb >= 0) {
+                float4 a_, fo_, fn_, h_;
+                pml_coefs(rech, 0, B->ah, B->foh, B->fnh, B->xvh, lofs, i0, p.px, a_, fo_, fn_);
+                h_ = pml_pre4(a_, fo_, g0, hx); g0 = upd4(ax, g0, bx, ez, ez_jp, ey, ey1); hx = pml_post4(fn_, g0, h_);
+                pml_coefs(rech, 1, B->ah, B->foh, B->fnh, B->xvh, lcs + lofs, i0, p.px, a_, fo_, fn_);
+                h_ = pml_pre4(a_, fo_, g1, hy); g1 = upd4(ay, g1, by, ex, ex1, ez, ez_ip); hy = pml_post4(fn_, g1, h_);
+                pml_coefs(rech, 2, B->ah, B->foh, B->fnh, B->xvh, 2 * lcs + lofs, i0, p.px, a_, fo_, fn_);
+                h_ = pml_pre4(a_, fo_, g2, hz); g2 = upd4(az, g2, bz, ey, ey_ip, ex, ex_jp); hz = pml_post4(fn_, g2, h_);
+            } else {
+                hx = upd4(ax, hx, bx, ez, ez_jp, ey, ey1);
+                hy = upd4(ay, hy, by, ex, ex1, ez, ez_ip);
+                hz = upd4(az, hz, bz, ey, ey_ip, ex, ex_jp);
+            }
         }
         if (own && !pro) {
             stb4(qh, hx); stb4(qh + p.b_cs, hy); stb4(qh + p.b_2cs, hz);
-            row_coefs(S.ms[mb][r][2], S.ms[mb][r][3], xse, p.vv, p.vi, p.xv_e,
-                      (long long)((pe - reinterpret_cast<const char*>(p.ein)) >> 2), p.cs, i0, p.px, ax, ay, az, bx, by, bz);
+            if (PML && pb >= 0) {
+                float* go = B->gout + lofs;
+                __stcs(reinterpret_cast<float4*>(go), g0); __stcs(reinterpret_cast<float4*>(go + lcs), g1); __stcs(reinterpret_cast<float4*>(go + 2 * lcs), g2);
+            }
+            if (!PML) row_coefs(S.ms[mb][r][2], S.ms[mb][r][3], xse, p.vv, p.vi, p.xv_e,
+                                boff >> 2, p.cs, i0, p.px, ax, ay, az, bx, by, bz);
         }
-        S.xb[mb][r][0][lane] = hz; S.xb[mb][r][1][lane] = hx;
+        if (r < TY) { S.xb[mb][r][0][lane] = hz; S.xb[mb][r][1][lane] = hx; }
         cp_async_wait<0>();                                  // next plane's records (this warp's own copies)
-        __syncthreads();                                     // H_new rows visible; everybody is done with slots se2 / sh^1's old planes
+        __syncthreads();                                     // H_new rows visible; every read of plane k (E and H rings) is done
+        // refill the slots of plane k: E_old(k + NS), H_old(k + 2)
+        if (t + NS <= nplanes) stage_e(se, t + NS);
+        if (t + 2 < nplanes) stage_h(sh, t + 2);
         const float hz_l = __shfl_up_sync(0xffffffffu, hz.w, 1);
         const float hy_l = __shfl_up_sync(0xffffffffu, hy.w, 1);
         if (own && !pro) {
+            if (PML) row_coefs(S.ms[mb][r][2], S.ms[mb][r][3], xse, p.vv, p.vi, p.xv_e,
+                               boff >> 2, p.cs, i0, p.px, ax, ay, az, bx, by, bz);     // (after the barrier: fewer values live across it)
             const float4 hz_jm = S.xb[mb][r - 1][0][lane], hx_jm = S.xb[mb][r - 1][1][lane];
             const float4 hz_im = make_float4(hz_l, hz.x, hz.y, hz.z);
             const float4 hy_im = make_float4(hy_l, hy.x, hy.y, hy.z);
-            const float4 exn = upd4(ax, ex, bx, hz, hz_jm, hy, hy_km);
-            const float4 eyn = upd4(ay, ey, by, hx, hx_km, hz, hz_im);
-            const float4 ezn = upd4(az, ez, bz, hy, hy_im, hx, hx_jm);
+            float4 exn, eyn, ezn;
+            if (PML && pb >= 0) {
+                float4 a_, fo_, fn_, h_;
+                float* fp = B->fv + lofs;                    // the voltage flux of a cell is touched by its owner only: in place
+                float4 f0 = __ldcs(reinterpret_cast<const float4*>(fp)), f1 = __ldcs(reinterpret_cast<const float4*>(fp + lcs)),
+                       f2 = __ldcs(reinterpret_cast<const float4*>(fp + 2 * lcs));
+                pml_coefs(rece, 0, B->ae, B->foe, B->fne, B->xve, lofs, i0, p.px, a_, fo_, fn_);
+                h_ = pml_pre4(a_, fo_, f0, ex); f0 = upd4(ax, f0, bx, hz, hz_jm, hy, hy_km); exn = pml_post4(fn_, f0, h_);
+                pml_coefs(rece, 1, B->ae, B->foe, B->fne, B->xve, lcs + lofs, i0, p.px, a_, fo_, fn_);
+                h_ = pml_pre4(a_, fo_, f1, ey); f1 = upd4(ay, f1, by, hx, hx_km, hz, hz_im); eyn = pml_post4(fn_, f1, h_);
+                pml_coefs(rece, 2, B->ae, B->foe, B->fne, B->xve, 2 * lcs + lofs, i0, p.px, a_, fo_, fn_);
+                h_ = pml_pre4(a_, fo_, f2, ez); f2 = upd4(az, f2, bz, hy, hy_im, hx, hx_jm); ezn = pml_post4(fn_, f2, h_);
+                __stcs(reinterpret_cast<float4*>(fp), f0); __stcs(reinterpret_cast<float4*>(fp + lcs), f1); __stcs(reinterpret_cast<float4*>(fp + 2 * lcs), f2);
+            } else {
+                exn = upd4(ax, ex, bx, hz, hz_jm, hy, hy_km);
+                eyn = upd4(ay, ey, by, hx, hx_km, hz, hz_im);
+                ezn = upd4(az, ez, bz, hy, hy_im, hx, hx_jm);
+            }
+            char* const qe = eout_b + boff;
             stb4(qe, exn); stb4(qe + p.b_cs, eyn); stb4(qe + p.b_2cs, ezn);
         }
         hx_km = hx; hy_km = hy;
-        se = se1; sh ^= 1;
+        se = se1;
     }
 }
-

@@ -99,7 +99,8 @@ __device__ __forceinline__ float4 upd4(float4 ca, float4 f, float4 cb, float4 a,
 struct RowParams {
     int j0, j1;                     // rows handled by this launch
     int sj0a, sj1a, sj0b, sj1b;     // rows that belong to fused y-slabs (skipped by the plain launch; empty ranges if none)
-    float* flux;                    // fused slab arrays [3][bz][by][px] (PML launches only)
+    const float* flux;              // fused slab arrays [3][bz][by][px] (PML launches only): old flux is read here
+    float* flux_out;                // ... and the new flux written here (== flux, or the other copy when the current flux ping-pongs)
     const float* a; const float* fo; const float* fn;
     const float* pxv; const unsigned char* pmeta;   // row compression of a/fo/fn (48-byte records per slab row) or NULL
     int y0, z0, by, bz;
@@ -294,7 +295,7 @@ __global__ void __launch_bounds__(32 * TY, MODE ? (16 / TY > 0 ? 16 / TY : 1) : 
             PML_COMP(0, ex, fl0, ax, bx, hz, hz_jm, hy, hy_km, lb);
             PML_COMP(1, ey, fl1, ay, by, hx, hx_km, hz, hz_im, lcs + lb);
             PML_COMP(2, ez, fl2, az, bz, hy, hy_im, hx, hx_jm, 2 * lcs + lb);
-            if (act) { st4(r.flux + lb, fl0); st4(r.flux + lcs + lb, fl1); st4(r.flux + 2 * lcs + lb, fl2); }
+            if (act) { st4(r.flux_out + lb, fl0); st4(r.flux_out + lcs + lb, fl1); st4(r.flux_out + 2 * lcs + lb, fl2); }
         } else if (MODE == 2) {
             PML_COMP_X(0, ex, fl0, ax, bx, hz, hz_jm, hy, hy_km, lb);
             PML_COMP_X(1, ey, fl1, ay, by, hx, hx_km, hz, hz_im, lcs + lb);
@@ -416,7 +417,7 @@ __global__ void __launch_bounds__(32 * TY, MODE ? (16 / TY > 0 ? 16 / TY : 1) : 
             PML_COMP(0, hx, fl0, ax, bx, ez, ez_jp, ey, ey_kp, lb);
             PML_COMP(1, hy, fl1, ay, by, ex, ex_kp, ez, ez_ip, lcs + lb);
             PML_COMP(2, hz, fl2, az, bz, ey, ey_ip, ex, ex_jp, 2 * lcs + lb);
-            if (act) { st4(r.flux + lb, fl0); st4(r.flux + lcs + lb, fl1); st4(r.flux + 2 * lcs + lb, fl2); }
+            if (act) { st4(r.flux_out + lb, fl0); st4(r.flux_out + lcs + lb, fl1); st4(r.flux_out + 2 * lcs + lb, fl2); }
         } else if (MODE == 2) {
             PML_COMP_X(0, hx, fl0, ax, bx, ez, ez_jp, ey, ey_kp, lb);
             PML_COMP_X(1, hy, fl1, ay, by, ex, ex_kp, ez, ez_ip, lcs + lb);

@@ -71,11 +71,10 @@ int b200fdtd_expand_rows(b200fdtd_ctx* ctx, int which, int nvec, const float* xv
  * variant bits: 1 = PML slabs by the separate pre/post kernel instead of fused rows, 2 = no side stream,
  * 4 = ignore the row compression, 8 = narrow x-slabs by the separate kernel, 16 = ignore the PML slab compression,
  * 32 = slab side stream at highest priority, 64 = one side stream for all slab launches, 128 = no fused H->E launches,
- * bits 8-12 = rows per CTA of the slab launches (0 = ty), bits 16-17 = prefetch distance of the register-march fused
- * kernels (0 = default 1, 3 = off), 256 / 512 / bit 18 = older generations of the fused H->E kernel (experiments:
- * cp.async ring v1 / plain fusion / register march v2 instead of the staged v3), bit 19 = barrier-free v4, bit 21 = per-thread cp.async staging (v3)
- * instead of TMA bulk copies (v5, default),
- * bit 20 = high-end H / low-end E slab launches beside the fused launch instead of before / after it */
+ * bits 8-12 = rows per CTA of the slab launches (0 = ty), bits 16-17 = L2 prefetch distance of the plain fusion
+ * (0 = default 1, 3 = off), 512 = plain fusion (update_he_kernel) instead of the TMA-staged update_he6_kernel,
+ * bit 20 = high-end H / low-end E slab launches beside the fused launch instead of before / after it,
+ * bit 22 = whole-row PML slabs by their own launches instead of inside the fused H->E launch */
 int b200fdtd_set_tuning(b200fdtd_ctx* ctx, int kz, int ty, int variant);
 
 /* ---- excitation (openEMS Engine_Ext_Excitation::Apply2Voltages; AddLumpedPort's
@@ -198,7 +197,8 @@ int b200fdtd_plan_info(b200fdtd_ctx* ctx, int64_t* plain_cells, int64_t* fused_c
  * are done in one sweep that writes a second copy of the fields (allocated by the library, 24 B/cell; the run falls
  * back to the separate E and H launches if that allocation fails, if a PML box is not slab-shaped, or with
  * variant bit 128).  Results are identical either way.  rows in {3,7,15} = rows per CTA, planes >= 1 = planes marched
- * per CTA; 0 keeps the current value. */
+ * per CTA (0 keeps the current value); bits 24-25 of `planes` = E planes landing ahead of the two in use (1 | 2; 0 = as many
+ * as shared memory allows without costing a resident CTA). */
 int b200fdtd_set_he_tuning(b200fdtd_ctx* ctx, int rows, int planes);
 /* *active = 1 if the last b200fdtd_run used fused H->E launches */
 int b200fdtd_he_info(b200fdtd_ctx* ctx, int* active);

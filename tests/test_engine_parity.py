@@ -189,24 +189,27 @@ def test_fused_h_to_e_launches_bit_exact(shape, layout, interval, tile):
 
 @pytest.mark.parametrize("shape", [(37, 29, 23, 40), (261, 21, 14, 288), (130, 12, 9, 160)])
 @pytest.mark.parametrize("layout", ["slabs", "mur"])
-@pytest.mark.parametrize("interval,tile,variant", [(4, (7, 32), 0), (3, (3, 2), 0), (5, (15, 5), 0), (2, (5, 1), 0),
-                                                   (4, (7, 32), 1 << 18), (3, (7, 4), 1 << 19), (4, (7, 3), 1 << 21),
-                                                   (3, (7, 32), 256), (4, (7, 32), 512), (5, (7, 32), 1 << 20)])
-def test_fused_h_to_e_with_row_compression(shape, layout, interval, tile, variant):
-    """the compressed-operator generations of the fused launch (default: planes staged by TMA bulk copies; bit 21 by
-    per-thread cp.async, bit 18 register march, bit 19 barrier-free, 256/512 the first two versions, bit 20 the overlapped
-    slab schedule) on
-    one and several x-segments, with rows whose compression claims are false (demoted on the device)"""
+@pytest.mark.parametrize("interval,tile,variant,de", [(4, (7, 32), 0, 0), (3, (3, 2), 0, 0), (5, (15, 5), 0, 0), (2, (3, 1), 0, 0),
+                                                      (4, (7, 32), 0, 1), (3, (7, 4), 0, 2), (5, (7, 3), 1 << 22, 0), (3, (15, 2), 1 << 22, 1),
+                                                      (4, (7, 32), 512, 0), (5, (7, 32), 1 << 20, 0), (7, (7, 1), 0, 2)])
+def test_fused_h_to_e_with_row_compression(shape, layout, interval, tile, variant, de):
+    """the fused launch on a row-compressed operator (update_he6_kernel: planes staged by TMA bulk copies, whole-row PML slabs
+    swept inside the launch with a double-buffered current flux; de = E planes landing ahead, 0 = automatic; bit 22 keeps the
+    slabs as separate launches, 512 = the plain fusion update_he_kernel, bit 20 the overlapped slab schedule) on one and
+    several x-segments, with rows whose compression claims are false (demoted on the device), even and odd numbers of H
+    passes per chunk (the flux copies swap every pass)"""
     nx, ny, nz, px = shape
     P = synth.make_problem(nx, ny, nz, px, seed=9 + nx, with_pml=layout == "slabs", fused_pml=layout == "slabs",
                            compress=True, interval=interval, with_nf2ff=False)
     R, G = _engines(P)
     G.set_tuning(variant=variant)
-    G.set_he_tuning(*tile)
+    G.set_he_tuning(*tile, de=de)
     n = 2 * interval + 1
     R.run(n); G.run(n, use_graph=True)
     assert G.he_active
     _assert_fields_equal(R, G, f"fused H->E with row compression, variant {variant}")
+    R.run(3); G.run(3, use_graph=False)          # eager spans continue from the same flux state
+    _assert_fields_equal(R, G, "eager steps after the graph chunks")
 
 
 @pytest.mark.parametrize("layout", ["slabs", "mur"])
