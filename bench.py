@@ -453,11 +453,18 @@ def run_b200(args):
     t_run = time.perf_counter() - t_e0
     if port is not None:
         port.CalcPort(R.path, fgrid)
+    t_port = time.perf_counter() - t_e0 - t_run
+    t_nf = []
     if nf is not None:
         for ph in phis:
+            t1 = time.perf_counter()
             nf.CalcNF2FF(R.path, 2.45e9, theta, np.array([ph]), center=[0.0, 0.0, 0.8e-3])
+            t_nf.append(time.perf_counter() - t1)
     R.barrier()
     e2e_s = time.perf_counter() - t_e0
+    breakdown = {"run_s": round(t_run, 4), "restart_s": round(getattr(sim, "restart_s", 0.0), 4), "stepping_s": round(sim.wall_s, 4),
+                 "collect_s": round(getattr(sim, "collect_s", 0.0), 4), "calcport_s": round(t_port, 4),
+                 "calcnf2ff_first_s": round(t_nf[0], 4) if t_nf else None, "calcnf2ff_rest_s": round(sum(t_nf[1:]), 4) if t_nf else None}
     e2e_ok = None
     if before is not None:
         if local_cells > 300e6:
@@ -500,7 +507,7 @@ def run_b200(args):
                     "what": "public API on the prepared scene: FDTD.Run(sim_path) [compressed operator from pinned host memory -> device, "
                             "expanded + verified on the device, K steps with energy check, probe series/DFT + NF2FF spectra -> host], "
                             "port.CalcPort(201 f), nf2ff.CalcNF2FF per phi (19 theta x 8 phi)",
-                    "operator_restored_mismatches": e2e_ok, "seconds": round(e2e_s, 4), "run_seconds": round(t_run, 4)},
+                    "operator_restored_mismatches": e2e_ok, "seconds": round(e2e_s, 4), "breakdown": breakdown},
             "gpu_launches": int(launches),
             "clocks": clk,
         }

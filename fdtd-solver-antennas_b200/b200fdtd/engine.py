@@ -326,6 +326,15 @@ class FarfieldSources:
         self.pos = torch.as_tensor(np.ascontiguousarray(pos, np.float32), device=self.dev)
         self.J = torch.as_tensor(np.ascontiguousarray(np.stack([np.real(J), np.imag(J)], -1), np.float32), device=self.dev)
         self.M = torch.as_tensor(np.ascontiguousarray(np.stack([np.real(M), np.imag(M)], -1), np.float32), device=self.dev)
+        self.world, self.group = 1, None
+
+    @classmethod
+    def from_device(cls, pos, J, M):
+        """pos [3][n], J/M [3][n][2] float32 CUDA tensors formed on the device (postproc.device_sources)"""
+        o = cls.__new__(cls)
+        o.dev, o.pos, o.J, o.M = pos.device, pos, J, M
+        o.world, o.group = 1, None
+        return o
 
 
 def farfield(pos, J, M, k, theta, phi, device=0, sources=None):
@@ -338,8 +347,13 @@ def farfield(pos, J, M, k, theta, phi, device=0, sources=None):
     th, ph = _np(theta, np.float64), _np(phi, np.float64)
     out = torch.zeros((len(th), 4, 2), dtype=torch.float32, device=dev)
     s = torch.cuda.current_stream(dev)
-    check(L.b200fdtd_farfield(dev.index, C.c_void_p(s.cuda_stream), n, pos_t.data_ptr(), Jt.data_ptr(), Mt.data_ptr(),
-                              float(k), len(th), _ptr(th, c_d), _ptr(ph, c_d), out.data_ptr()))
+    if n > 0:                                      # a z-slab rank may hold no part of the box
+        check(L.b200fdtd_farfield(dev.index, C.c_void_p(s.cuda_stream), n, pos_t.data_ptr(), Jt.data_ptr(), Mt.data_ptr(),
+                                  float(k), len(th), _ptr(th, c_d), _ptr(ph, c_d), out.data_ptr()))
+    if getattr(src, "world", 1) > 1:               # the radiation integral is linear in the sources: add the ranks' sums
+        o64 = out.to(torch.float64)
+        torch.distributed.all_reduce(o64, group=src.group)
+        out = o64
     o = out.cpu().numpy().astype(np.float64)
     oc = o[..., 0] + 1j * o[..., 1]
     return oc[:, 0], oc[:, 1], oc[:, 2], oc[:, 3]

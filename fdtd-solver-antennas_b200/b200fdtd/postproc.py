@@ -89,6 +89,55 @@ def surface_currents(nf, freq, center):
     return pos, J, M, float(prad)
 
 
+def device_sources(nf, freq, center):
+    """equivalent currents formed ON THE DEVICE from this rank's device-resident face spectra (CUDA engine): the
+    accumulators never travel to the host.  Same formulas as surface_currents.  Returns (FarfieldSources, Prad); on a
+    z-slab run Prad is already summed over the ranks (collective)."""
+    import torch
+    from .engine import FarfieldSources
+    D = nf["device"]
+    dev = D["dev"]
+    freqs = np.asarray(nf["freqs"], np.float64)
+    hit = np.where(np.isclose(freqs, freq, rtol=1e-9, atol=0.0))[0]
+    faces = D["faces"]
+    if len(hit):
+        accs = [F["acc"][:, int(hit[0])] for F in faces]             # [4][nb][na][2] float32 views
+    else:
+        if D.get("td_dft") is None:
+            raise ValueError(f"NF2FF frequency {freq:g} Hz was not registered for the running DFT (available: {freqs.tolist()}) "
+                             "and the time-domain face samples were not kept (memory budget B200FDTD_NF2FF_TD_GB); "
+                             "pass frequency=[...] to CreateNF2FFBox")
+        accs = [a[:, 0] for a in D["td_dft"](float(freq))] if faces else []
+    scale = float(D["scale"])
+    c = np.asarray(center, np.float64).reshape(3)
+    f32 = dict(dtype=torch.float32, device=dev)
+    pos, Jl, Ml = [torch.zeros((3, 0), **f32)], [torch.zeros((3, 0, 2), **f32)], [torch.zeros((3, 0, 2), **f32)]
+    prad = torch.zeros(1, dtype=torch.float64, device=dev)
+    for F, acc in zip(faces, accs):
+        n = F["normal"]; a, b = (n + 1) % 3, (n + 2) % 3
+        s = 1.0 if F["side"] == 1 else -1.0
+        dA = (torch.as_tensor(F["wb"], dtype=torch.float64, device=dev)[:, None] * torch.as_tensor(F["wa"], dtype=torch.float64, device=dev)[None, :])
+        w32 = (dA * scale).to(torch.float32).unsqueeze(-1)            # dA and the DFT scale in one factor
+        Ea, Eb, Ha, Hb = (acc[q] for q in range(4))                   # [nb][na][2]
+        nb_, na_ = dA.shape
+        P = torch.empty((3, nb_, na_), **f32)
+        P[n] = float(F["coord"] - c[n])
+        P[a] = torch.as_tensor(np.asarray(F["xa"]) - c[a], **f32)[None, :]
+        P[b] = torch.as_tensor(np.asarray(F["xb"]) - c[b], **f32)[:, None]
+        J = torch.zeros((3, nb_, na_, 2), **f32); M = torch.zeros_like(J)
+        J[a] = -s * Hb * w32; J[b] = s * Ha * w32                     # J = n x H
+        M[a] = s * Eb * w32; M[b] = -s * Ea * w32                     # M = -n x E
+        ea, eb, ha, hb = (t.to(torch.float64) for t in (Ea, Eb, Ha, Hb))
+        re = (ea[..., 0] * hb[..., 0] + ea[..., 1] * hb[..., 1]) - (eb[..., 0] * ha[..., 0] + eb[..., 1] * ha[..., 1])
+        prad = prad + 0.5 * s * scale * scale * torch.sum(re * dA)
+        pos.append(P.reshape(3, -1)); Jl.append(J.reshape(3, -1, 2)); Ml.append(M.reshape(3, -1, 2))
+    if D.get("world", 1) > 1:
+        torch.distributed.all_reduce(prad, group=D.get("group"))
+    src = FarfieldSources.from_device(torch.cat(pos, 1).contiguous(), torch.cat(Jl, 1).contiguous(), torch.cat(Ml, 1).contiguous())
+    src.world, src.group = D.get("world", 1), D.get("group")
+    return src, float(prad.item())
+
+
 def far_field(nf, freq, theta_deg, phi_deg, center=(0, 0, 0), radius=1.0, farfield_fn=None, device=0):
     """E_theta/E_phi on the theta x phi grid (degrees) for one frequency of the box spectra."""
     # the reference calls CalcNF2FF once per phi with the same frequency and centre (73 calls): the equivalent currents are
@@ -98,7 +147,11 @@ def far_field(nf, freq, theta_deg, phi_deg, center=(0, 0, 0), radius=1.0, farfie
     if key not in cache:
         if len(cache) >= 8:
             cache.clear()
-        cache[key] = dict(cur=surface_currents(nf, float(freq), center), dev=None)
+        if farfield_fn is None and nf.get("device") is not None:
+            src, prad = device_sources(nf, float(freq), center)
+            cache[key] = dict(cur=(None, None, None, prad), dev=src)
+        else:
+            cache[key] = dict(cur=surface_currents(nf, float(freq), center), dev=None)
     ent = cache[key]
     pos, J, M, prad = ent["cur"]
     th = np.deg2rad(np.atleast_1d(np.asarray(theta_deg, np.float64)))

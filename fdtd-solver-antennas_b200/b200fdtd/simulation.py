@@ -23,6 +23,31 @@ def _np(t):
     return t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
 
 
+class LazyResults(dict):
+    """dict whose expensive entries are produced on first access (e.g. the host copy of the NF2FF face spectra: the far
+    field on the CUDA path is formed from the device-resident accumulators and never needs it)"""
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self._thunks = {}
+
+    def lazy(self, key, fn):
+        self._thunks[key] = fn
+
+    def __missing__(self, key):
+        if key in self._thunks:
+            v = self._thunks.pop(key)()
+            self[key] = v
+            return v
+        raise KeyError(key)
+
+    def __contains__(self, key):
+        return dict.__contains__(self, key) or key in self._thunks
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+
 def _round_up(n, m):
     return (n + m - 1) // m * m
 
@@ -249,6 +274,12 @@ class Simulation:
         scale = 2.0 * self.interval * self.dt          # single-sided pulse spectrum, like DFT_time2freq (App. A5/A6)
         return [f * scale for f in full]
 
+    def _device_faces_ok(self):
+        E = self.engine
+        return (isinstance(getattr(E, "device", None), torch.device) and E.device.type == "cuda"
+                and not getattr(self.builder, "nf2ff_mirrors", [])
+                and (self.world == 1 or torch.distributed.get_backend(self.group) == "nccl"))
+
     def nf2ff_spectra(self, freqs):
         """face spectra at arbitrary frequencies from the stored time-domain samples (collective on z-slab runs)"""
         if not getattr(self, "td_store", False):
@@ -327,10 +358,12 @@ class Simulation:
     def restart(self):
         """a new run of the prepared scene: operator host -> device (if a host copy is kept), all state back to zero"""
         E = self.engine
+        t0 = time.time()
         self.reloaded = None
         if getattr(self, "host_op", None) is not None:
             self.reloaded = self.load_operator(self.host_op)
         E.reset_state()
+        self.restart_s = time.time() - t0
         if getattr(self, "_tv", None) is not None:
             self._vcur = self._ccur = 0
         self.results = None
@@ -513,7 +546,9 @@ class Simulation:
         self.wall_s = time.time() - t0
         self.stop_reason = stop_reason
         self.timesteps = E.ts
+        t1 = time.time()
         self.collect()
+        self.collect_s = time.time() - t1
         return self
 
     # ------------------------------------------------------------------ results
@@ -538,10 +573,33 @@ class Simulation:
                                            dft=(dft[p, :, 0] + 1j * dft[p, :, 1]) if len(self.probe_freqs) else None)
             res["probe_freqs"] = self.probe_freqs
         if self.faces:
-            full = self._assemble_faces(E.face_acc, len(self.nf2ff_freqs))
-            res["nf2ff"] = dict(faces=self.faces, acc=full, freqs=self.nf2ff_freqs, mirrors=list(getattr(self.builder, "nf2ff_mirrors", [])),
-                                weights=[self.builder.face_weights(F) for F in self.faces],
-                                spectra_fn=self.nf2ff_spectra if getattr(self, "td_store", False) else None, extra={}, sources={})
+            nf = LazyResults(faces=self.faces, freqs=self.nf2ff_freqs, mirrors=list(getattr(self.builder, "nf2ff_mirrors", [])),
+                             weights=[self.builder.face_weights(F) for F in self.faces],
+                             spectra_fn=self.nf2ff_spectra if getattr(self, "td_store", False) else None, extra={}, sources={})
+            dev_ok = self._device_faces_ok()
+            if self.world > 1 and not dev_ok:
+                nf["acc"] = self._assemble_faces(E.face_acc, len(self.nf2ff_freqs))      # collective: every rank takes part now
+            else:
+                # host copy of the spectra only if somebody asks for it (z-slab runs: a collective, every rank must ask)
+                nf.lazy("acc", lambda: self._assemble_faces(E.face_acc, len(self.nf2ff_freqs)))
+            if dev_ok:
+                # CUDA engine, no image walls: the equivalent currents are formed on the device from this rank's part of
+                # the faces (postproc.device_sources); z-slab ranks add their far-field sums (a few numbers per direction)
+                loc = []
+                for q, L in enumerate(self.local_faces):
+                    F = self.faces[L["face"]]
+                    xa, xb, wa, wb = nf["weights"][L["face"]]
+                    n = F["normal"]; a = (n + 1) % 3
+                    if n != 2:
+                        o = L["z_off"]
+                        if a == 2:
+                            m = L["a1"] - L["a0"] + 1; xa, wa = xa[o:o + m], wa[o:o + m]
+                        else:
+                            m = L["b1"] - L["b0"] + 1; xb, wb = xb[o:o + m], wb[o:o + m]
+                    loc.append(dict(normal=n, side=F["side"], coord=F["coord"], xa=xa, xb=xb, wa=wa, wb=wb, acc=E.face_acc[q]))
+                nf["device"] = dict(faces=loc, scale=2.0 * self.interval * self.dt, dev=E.device, world=self.world, group=self.group,
+                                    td_dft=(lambda f: self.engine.nf2ff_td_dft([f], self.results["n_samples"])) if getattr(self, "td_store", False) else None)
+            res["nf2ff"] = nf
         self.results = res
         return res
 

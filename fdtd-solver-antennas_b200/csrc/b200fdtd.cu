@@ -415,7 +415,12 @@ static HeChoice he_choice(const b200fdtd_ctx* c)
     const int r1 = ctas1 < reg_ctas ? ctas1 : reg_ctas, r2 = ctas2 < reg_ctas ? ctas2 : reg_ctas;
     h.de = c->he_de ? c->he_de : ((r2 >= r1 && r2 > 0) ? 2 : 1);
     if (h.de == 2 && ctas2 == 0) h.de = 1;
-    h.pml = c->plan.nfused > 0 && (c->variant & (1 << 22)) == 0;
+    // Whole-row PML slabs inside the fused launch: one launch instead of 2 x (1 + slabs) per step.  That is what counts on
+    // small grids (a step of a 0.3 M-cell scene is a dozen under-filled launches otherwise); on large grids the slab rows
+    // run slower inside the fused launch than in their own launches, so those keep them (bit 22: never inside, bit 23: always)
+    static const long long pml_max_cells = [] { const char* e = getenv("B200FDTD_HE_PML_MAX_CELLS"); return e ? atoll(e) : 6000000LL; }();
+    const long long cells = (long long)c->nx * c->ny * c->nz;
+    h.pml = c->plan.nfused > 0 && (c->variant & (1 << 22)) == 0 && ((c->variant & (1 << 23)) != 0 || cells <= pml_max_cells);
     return h;
 }
 
@@ -494,6 +499,11 @@ static int launch_he(b200fdtd_ctx* c, cudaStream_t stream, int zc0 = -1, int zc1
     if (p.Y1 <= p.Y0 || p.Z1 <= p.Z0 || (!pml && p.X1 <= p.X0)) return fail("fused H->E launch over an empty region");
     const int ty = c->he_ty;
     int kz = c->he_kz; if (kz > p.Z1 - p.Z0) kz = p.Z1 - p.Z0;
+    {   // small grids: the z-march is a serial chain of planes per CTA, so the launch gets its parallelism from more, shorter
+        // chunks (each pays one extra plane of halo recompute) until the machine is filled a few times over
+        const long long per_chunk = (long long)((c->px - p.X0s + HE_SEG - 1) / HE_SEG) * ((p.Y1 - p.Y0 + ty - 1) / ty);
+        while (kz > 4 && per_chunk * ((p.Z1 - p.Z0 + kz - 1) / kz) < 148LL * 4) kz = (kz + 1) / 2;
+    }
     { const int n = (p.Z1 - p.Z0 + kz - 1) / kz; kz = (p.Z1 - p.Z0 + n - 1) / n; }      // chunks of equal length
     p.kz = kz;
     p.pf = (c->variant >> 16) & 3;                   // L2 prefetch distance in planes (plain fusion only): 0 = default (1), 3 = off
@@ -1602,18 +1612,26 @@ extern "C" int b200fdtd_farfield(int device, void* stream, int64_t npts, const f
     if (npts <= 0 || ndir <= 0 || !pos || !J || !M || !theta || !phi || !out) return fail("bad far-field arguments");
     CK(cudaSetDevice(device));
     cudaStream_t s = (cudaStream_t)stream;
-    // direction buffer of the calling thread, grown on demand and kept (the reference calls CalcNF2FF once per phi: 73 calls)
+    // direction + partial-sum buffer of the calling thread, grown on demand and kept (the reference calls CalcNF2FF once per phi: 73 calls)
     static thread_local double* d_dir = nullptr; static thread_local int d_cap = 0, d_dev = -1;
+    const int target = 148 * 4;
+    int nsplit = (target + ndir - 1) / ndir;
+    if ((long long)nsplit * 2048 > npts) nsplit = (int)((npts + 2047) / 2048);       // at least ~2 k points per block
+    if (nsplit < 1) nsplit = 1;
+    if (nsplit > 64) nsplit = 64;
     if (d_dev != device || d_cap < ndir) {
         if (d_dir && d_dev >= 0) { cudaSetDevice(d_dev); cudaFree(d_dir); cudaSetDevice(device); }
         d_dir = nullptr; d_cap = 0; d_dev = device;
         const int cap = ndir < 8192 ? 8192 : ndir;
-        CK(cudaMalloc((void**)&d_dir, sizeof(double) * 2 * cap));
+        CK(cudaMalloc((void**)&d_dir, sizeof(double) * (2 * (size_t)cap + 12ULL * 64 * cap)));
         d_cap = cap;
     }
+    double* d_part = d_dir + 2 * (size_t)d_cap;
     CK(cudaMemcpyAsync(d_dir, theta, sizeof(double) * ndir, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(d_dir + d_cap, phi, sizeof(double) * ndir, cudaMemcpyHostToDevice, s));
-    farfield_kernel<<<ndir, 256, 0, s>>>(npts, pos, J, M, k, ndir, d_dir, d_dir + d_cap, out);
+    farfield_kernel<<<dim3(ndir, nsplit), 256, 0, s>>>(npts, pos, J, M, k, ndir, d_dir, d_dir + d_cap, d_part);
+    CKL();
+    farfield_final_kernel<<<(ndir + 127) / 128, 128, 0, s>>>(ndir, nsplit, d_part, d_dir, d_dir + d_cap, out);
     CKL();
     CK(cudaStreamSynchronize(s));                 // theta/phi are pageable host arrays of the caller
     return 0;

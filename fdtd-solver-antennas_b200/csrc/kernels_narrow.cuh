@@ -244,9 +244,12 @@ __global__ void energy_final_kernel(const double* __restrict__ partials, int n, 
 }
 
 // K11 far field: N = sum J e^{jk r^.r'}, L = sum M e^{jk r^.r'} projected on theta^/phi^ (App. A6)
+// grid (ndir, nsplit): block (d, s) sums its share of the surface points for direction d in fp64 and writes 12 partial sums;
+// farfield_final_kernel adds the shares in a fixed order (deterministic) and projects.  The reference asks for one phi at a
+// time (91 directions per call): without the split a call would occupy 91 of 148 SMs with one block each.
 __global__ void __launch_bounds__(256) farfield_kernel(long long npts, const float* __restrict__ pos,
         const float* __restrict__ J, const float* __restrict__ M, double k, int ndir,
-        const double* __restrict__ theta, const double* __restrict__ phi, float* __restrict__ out)
+        const double* __restrict__ theta, const double* __restrict__ phi, double* __restrict__ partial)
 {
     const int d = blockIdx.x;
     if (d >= ndir) return;
@@ -257,16 +260,17 @@ __global__ void __launch_bounds__(256) farfield_kernel(long long npts, const flo
     double a[12];
 #pragma unroll
     for (int i = 0; i < 12; ++i) a[i] = 0.0;
-    for (long long q = threadIdx.x; q < npts; q += blockDim.x) {
+    const long long per = (npts + gridDim.y - 1) / gridDim.y;
+    const long long q0 = per * blockIdx.y, q1 = min(npts, q0 + per);
+    for (long long q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
         double tn = ux * (double)pos[q] + uy * (double)pos[npts + q] + uz * (double)pos[2 * npts + q];
         tn -= rint(tn);
         float sn, cn; sincospif(2.0f * (float)tn, &sn, &cn);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            const float jr = J[(c * npts + q) * 2], ji = J[(c * npts + q) * 2 + 1];
-            const float mr = M[(c * npts + q) * 2], mi = M[(c * npts + q) * 2 + 1];
-            a[2 * c] += (double)(jr * cn - ji * sn); a[2 * c + 1] += (double)(jr * sn + ji * cn);
-            a[6 + 2 * c] += (double)(mr * cn - mi * sn); a[6 + 2 * c + 1] += (double)(mr * sn + mi * cn);
+            const float2 jv = reinterpret_cast<const float2*>(J)[c * npts + q], mv = reinterpret_cast<const float2*>(M)[c * npts + q];
+            a[2 * c] += (double)(jv.x * cn - jv.y * sn); a[2 * c + 1] += (double)(jv.x * sn + jv.y * cn);
+            a[6 + 2 * c] += (double)(mv.x * cn - mv.y * sn); a[6 + 2 * c + 1] += (double)(mv.x * sn + mv.y * cn);
         }
     }
     __shared__ double red[8][12];
@@ -277,18 +281,28 @@ __global__ void __launch_bounds__(256) farfield_kernel(long long npts, const flo
         if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][i] = v;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        double s[12];
-        for (int i = 0; i < 12; ++i) { s[i] = 0; for (int wv = 0; wv < 8; ++wv) s[i] += red[wv][i]; }
-        // theta^ = (ct cp, ct sp, -st), phi^ = (-sp, cp, 0)
-        for (int part = 0; part < 2; ++part) {         // 0: N from J, 1: L from M
-            const double* v = s + 6 * part;
-            for (int ri = 0; ri < 2; ++ri) {
-                const double vx = v[ri], vy = v[2 + ri], vz = v[4 + ri];
-                out[((long long)d * 4 + 2 * part) * 2 + ri] = (float)(vx * ct * cp + vy * ct * sp - vz * st);
-                out[((long long)d * 4 + 2 * part + 1) * 2 + ri] = (float)(-vx * sp + vy * cp);
-            }
+    if (threadIdx.x < 12) {
+        double s = 0;
+        for (int wv = 0; wv < 8; ++wv) s += red[wv][threadIdx.x];
+        partial[((long long)d * gridDim.y + blockIdx.y) * 12 + threadIdx.x] = s;
+    }
+}
+__global__ void farfield_final_kernel(int ndir, int nsplit, const double* __restrict__ partial,
+        const double* __restrict__ theta, const double* __restrict__ phi, float* __restrict__ out)
+{
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= ndir) return;
+    double s[12];
+    for (int i = 0; i < 12; ++i) { s[i] = 0; for (int q = 0; q < nsplit; ++q) s[i] += partial[((long long)d * nsplit + q) * 12 + i]; }
+    double st, ct, sp, cp;
+    sincos(theta[d], &st, &ct); sincos(phi[d], &sp, &cp);
+    // theta^ = (ct cp, ct sp, -st), phi^ = (-sp, cp, 0)
+    for (int part = 0; part < 2; ++part) {             // 0: N from J, 1: L from M
+        const double* v = s + 6 * part;
+        for (int ri = 0; ri < 2; ++ri) {
+            const double vx = v[ri], vy = v[2 + ri], vz = v[4 + ri];
+            out[((long long)d * 4 + 2 * part) * 2 + ri] = (float)(vx * ct * cp + vy * ct * sp - vz * st);
+            out[((long long)d * 4 + 2 * part + 1) * 2 + ri] = (float)(-vx * sp + vy * cp);
         }
     }
 }
-

@@ -190,7 +190,7 @@ def test_fused_h_to_e_launches_bit_exact(shape, layout, interval, tile):
 @pytest.mark.parametrize("shape", [(37, 29, 23, 40), (261, 21, 14, 288), (130, 12, 9, 160)])
 @pytest.mark.parametrize("layout", ["slabs", "mur"])
 @pytest.mark.parametrize("interval,tile,variant,de", [(4, (7, 32), 0, 0), (3, (3, 2), 0, 0), (5, (15, 5), 0, 0), (2, (3, 1), 0, 0),
-                                                      (4, (7, 32), 0, 1), (3, (7, 4), 0, 2), (5, (7, 3), 1 << 22, 0), (3, (15, 2), 1 << 22, 1),
+                                                      (4, (7, 32), 1 << 23, 1), (3, (7, 4), 1 << 23, 2), (5, (7, 3), 1 << 22, 0), (3, (15, 2), 1 << 22, 1),
                                                       (4, (7, 32), 512, 0), (5, (7, 32), 1 << 20, 0), (7, (7, 1), 0, 2)])
 def test_fused_h_to_e_with_row_compression(shape, layout, interval, tile, variant, de):
     """the fused launch on a row-compressed operator (update_he6_kernel: planes staged by TMA bulk copies, whole-row PML slabs

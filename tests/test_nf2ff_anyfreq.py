@@ -41,7 +41,9 @@ def _check_td_equals_running(engine):
     # the per-phi loop of the reference reuses the cached sources (one entry per (frequency, centre))
     for ph in (0.0, 45.0, 90.0):
         nfb.CalcNF2FF(pb, f_other, THETA, np.array([ph]), center=[0, 0, 0])
-    assert len(Fb.results["nf2ff"]["sources"]) == 1 and len(Fb.results["nf2ff"]["extra"]) == 1
+    assert len(Fb.results["nf2ff"]["sources"]) == 1
+    if engine == "oracle":          # host path: the transformed spectra are cached too (the CUDA path keeps them on the device)
+        assert len(Fb.results["nf2ff"]["extra"]) == 1
     return rb
 
 

@@ -23,7 +23,7 @@ ap.add_argument("--workload", default="patch100m")
 ap.add_argument("--cube-n", type=int, default=768)
 ap.add_argument("--out", default="variants.json")
 ap.add_argument("--reps", type=int, default=3)
-ap.add_argument("--he", default="0:0", help="fused H->E tiles rows:planes[,rows:planes...] (0 = keep)")
+ap.add_argument("--he", default="0:0", help="fused H->E tiles rows:planes[:lookahead][,rows:planes...] (0 = keep / automatic)")
 args = ap.parse_args()
 
 if args.workload == "cube":
@@ -37,7 +37,8 @@ sim.prepare()
 E = sim.engine
 res = []
 for he in args.he.split(","):
-  E.set_he_tuning(*[int(v) for v in he.split(":")])
+  hv = [int(v) for v in he.split(":")] + [0]
+  E.set_he_tuning(hv[0], hv[1], de=hv[2])
   for variant in [int(v) for v in args.variants.split(",")]:
     for ty in [int(v) for v in args.ty.split(",")]:
         for kz in [int(v) for v in args.kz.split(",")]:
@@ -54,7 +55,16 @@ for he in args.he.split(","):
                 torch.cuda.synchronize()
                 best = min(best, a.elapsed_time(b) / args.steps)
             ms = best
-            r = dict(he=he, fused=E.he_active, variant=variant, ty=ty, kz=kz, ms_per_step=round(ms, 5), mcells=round(sim.cells / ms / 1e3, 1))
+            kms = None
+            if E.he_active:                      # the fused launch alone
+                E.update_only(4, join=False)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize(); a.record(E.stream)
+                for _ in range(10):
+                    E.update_only(4, join=False)
+                b.record(E.stream); torch.cuda.synchronize()
+                kms = round(a.elapsed_time(b) / 10, 4)
+            r = dict(he=he, fused=E.he_active, variant=variant, ty=ty, kz=kz, ms_per_step=round(ms, 5), mcells=round(sim.cells / ms / 1e3, 1), he_kernel_ms=kms)
             res.append(r)
             print(r, flush=True)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
