@@ -443,9 +443,19 @@ def run_b200(args):
             before = [t.clone() for t in (E.vv, E.vi, E.ii, E.iv)]
         for t in (E.vv, E.vi, E.ii, E.iv):
             t.zero_()
-    F.SetNumberOfTimeSteps(K)
     theta, phis = np.arange(0.0, 181.0, 10.0), np.arange(0.0, 360.0, 45.0)
     fgrid = np.linspace(1e9, 4e9, 201)
+    # untimed warm-up of the same call sequence (3 steps): first launches of the reload / far-field kernels load their modules
+    F.SetNumberOfTimeSteps(3)
+    F.Run(R.path)
+    if port is not None:
+        port.CalcPort(R.path, fgrid)
+    if nf is not None:
+        nf.CalcNF2FF(R.path, 2.45e9, theta, phis[:1], center=[0.0, 0.0, 0.8e-3])
+    if before is not None:
+        for t in (E.vv, E.vi, E.ii, E.iv):
+            t.zero_()
+    F.SetNumberOfTimeSteps(K)
     R.barrier()
     t_e0 = time.perf_counter()
     F.Run(R.path)

@@ -119,6 +119,7 @@ struct b200fdtd_ctx {
     float* exc_sig = nullptr; int exc_siglen = 0;
     // mur
     int64_t n_mur = 0; int64_t *mur_dst = nullptr, *mur_src = nullptr; float *mur_coeff = nullptr, *mur_tmp = nullptr;
+    struct MurSeg* mur_segs = nullptr; int n_mur_segs = 0;   // the same lists as arithmetic runs (used when the runs are long)
     // pml: all boxes as given, the boxes left to the separate pre/post passes, and the fused launch plan
     int64_t pml_rows_compressed = 0, pml_rows_demoted = 0;
     PmlTable pml_all{};
@@ -415,12 +416,11 @@ static HeChoice he_choice(const b200fdtd_ctx* c)
     const int r1 = ctas1 < reg_ctas ? ctas1 : reg_ctas, r2 = ctas2 < reg_ctas ? ctas2 : reg_ctas;
     h.de = c->he_de ? c->he_de : ((r2 >= r1 && r2 > 0) ? 2 : 1);
     if (h.de == 2 && ctas2 == 0) h.de = 1;
-    // Whole-row PML slabs inside the fused launch: one launch instead of 2 x (1 + slabs) per step.  That is what counts on
-    // small grids (a step of a 0.3 M-cell scene is a dozen under-filled launches otherwise); on large grids the slab rows
-    // run slower inside the fused launch than in their own launches, so those keep them (bit 22: never inside, bit 23: always)
-    static const long long pml_max_cells = [] { const char* e = getenv("B200FDTD_HE_PML_MAX_CELLS"); return e ? atoll(e) : 6000000LL; }();
-    const long long cells = (long long)c->nx * c->ny * c->nz;
-    h.pml = c->plan.nfused > 0 && (c->variant & (1 << 22)) == 0 && ((c->variant & (1 << 23)) != 0 || cells <= pml_max_cells);
+    // Whole-row PML slabs inside the fused launch (variant bit 23): one launch instead of 2 x (1 + slabs) per step and 96
+    // instead of 120 B per PML cell, bit-exact like the separate launches.  Measured on B200 it loses on every grid size:
+    // a slab row costs 3-4 x a plain row inside the fused launch (0.32 M cells: 58 vs 31 us per step; 106 M cells: 1.73 vs
+    // 1.40 ms), and a CTA advances at the pace of its slowest row, so the default keeps the slabs in their own launches.
+    h.pml = c->plan.nfused > 0 && (c->variant & (1 << 22)) == 0 && (c->variant & (1 << 23)) != 0;
     return h;
 }
 
@@ -664,7 +664,7 @@ extern "C" int b200fdtd_destroy(b200fdtd_ctx* c)
     if (c->alt_owned) { cudaFree(c->alt_volt); cudaFree(c->alt_curr); }
     for (int q = 0; q < 4; ++q) cudaFree(c->flux_alt[q]);
     cudaFree(c->exc_idx); cudaFree(c->exc_amp); cudaFree(c->exc_delay); cudaFree(c->exc_sig);
-    cudaFree(c->mur_dst); cudaFree(c->mur_src); cudaFree(c->mur_coeff); cudaFree(c->mur_tmp);
+    cudaFree(c->mur_dst); cudaFree(c->mur_src); cudaFree(c->mur_coeff); cudaFree(c->mur_tmp); cudaFree(c->mur_segs);
     cudaFree(c->pr_kind); cudaFree(c->pr_off); cudaFree(c->pr_idx); cudaFree(c->pr_w); cudaFree(c->pr_freqs);
     cudaFree(c->nf_freqs);
     for (int a = 0; a < 3; ++a) { cudaFree(c->inv_len[a]); cudaFree(c->inv_dual[a]); }
@@ -858,6 +858,27 @@ extern "C" int b200fdtd_set_mur(b200fdtd_ctx* c, int64_t n, const int64_t* dst, 
     if (upload(&c->mur_coeff, coeff, n, c->stream)) return 1;
     if (c->mur_tmp) { cudaFree(c->mur_tmp); c->mur_tmp = nullptr; }
     if (n > 0) { CK(cudaMalloc((void**)&c->mur_tmp, sizeof(float) * n)); CK(cudaMemsetAsync(c->mur_tmp, 0, sizeof(float) * n, c->stream)); }
+    // arithmetic runs of (dst, src): rows / columns of the boundary faces
+    std::vector<MurSeg> segs;
+    for (int64_t e = 0; e < n;) {
+        MurSeg S; S.dst0 = dst[e]; S.src0 = src[e]; S.e0 = e; S.pad = 0; S.sd = 0; S.ss = 0; S.count = 1;
+        if (e + 1 < n) {
+            const long long sd = dst[e + 1] - dst[e], ss = src[e + 1] - src[e];
+            if (sd > -(1LL << 30) && sd < (1LL << 30) && ss > -(1LL << 30) && ss < (1LL << 30)) {
+                S.sd = (int)sd; S.ss = (int)ss;
+                while (e + S.count < n && S.count < (1 << 20) && dst[e + S.count] - dst[e + S.count - 1] == sd &&
+                       src[e + S.count] - src[e + S.count - 1] == ss) S.count++;
+            }
+        }
+        segs.push_back(S);
+        e += S.count;
+    }
+    if (c->mur_segs) { cudaFree(c->mur_segs); c->mur_segs = nullptr; }
+    c->n_mur_segs = 0;
+    if (n > 0 && (int64_t)segs.size() * 16 <= n && segs.size() < (1u << 30) && (c->variant & (1 << 24)) == 0) {   // long runs: drop the index lists
+        if (upload(&c->mur_segs, segs.data(), (int64_t)segs.size(), c->stream)) return 1;
+        c->n_mur_segs = (int)segs.size();
+    }
     return 0;
 }
 
@@ -1102,6 +1123,12 @@ static int launch_pml(b200fdtd_ctx* c, int which, int post)
 static int launch_mur(b200fdtd_ctx* c, int phase)
 {
     if (c->n_mur == 0) return 0;
+    if (c->n_mur_segs > 0) {
+        mur_seg_kernel<<<(unsigned)(((long long)c->n_mur_segs * 32 + 127) / 128), 128, 0, c->stream>>>(cur_volt(c), c->mur_segs, c->n_mur_segs,
+                                                                                                       c->mur_coeff, c->mur_tmp, phase);
+        CKL();
+        return 0;
+    }
     const int threads = 256;
     mur_kernel<<<(unsigned)((c->n_mur + threads - 1) / threads), threads, 0, c->stream>>>(cur_volt(c), c->mur_dst, c->mur_src,
                                                                                        c->mur_coeff, c->mur_tmp, c->n_mur, phase);

@@ -243,14 +243,14 @@ struct HePml {
 };
 
 // a, fo, fn of component c of a slab row; rec = the row's 48-byte record (9 scales, 9 ids, pad[0] = a slot is streamed in
-// full) or NULL: stream the full arrays.  The record is read where it is used (a warp-uniform L1 hit), not kept in registers.
+// full; staged in shared memory one plane ahead) or NULL: stream the full arrays.
 __device__ __forceinline__ void pml_coefs(const unsigned char* rec, int c, const float* A, const float* FO, const float* FN,
         const float* __restrict__ xv, long long lofs, int i0, int px, float4& a, float4& fo, float4& fn)
 {
     if (rec == nullptr) { a = ld4_nc(A + lofs); fo = ld4_nc(FO + lofs); fn = ld4_nc(FN + lofs); return; }
-    const float* sc = reinterpret_cast<const float*>(rec);
-    const float s0 = __ldg(sc + c), s1 = __ldg(sc + 3 + c), s2 = __ldg(sc + 6 + c);
-    const unsigned i0_ = __ldg(rec + 36 + c), i1_ = __ldg(rec + 39 + c), i2_ = __ldg(rec + 42 + c), full = __ldg(rec + 45);
+    const float* sc = reinterpret_cast<const float*>(rec);   // staged in shared memory one plane ahead
+    const float s0 = sc[c], s1 = sc[3 + c], s2 = sc[6 + c];
+    const unsigned i0_ = rec[36 + c], i1_ = rec[39 + c], i2_ = rec[42 + c], full = rec[45];
     if (full == 0) {
         const char* pl = reinterpret_cast<const char*>(xv + i0); const unsigned pp = 4u * (unsigned)px;
         a = xvg4(pl, i0_, pp, s0); fo = xvg4(pl, i1_, pp, s1); fn = xvg4(pl, i2_, pp, s2);
@@ -265,6 +265,7 @@ struct He6Smem {
     float4 hs[2][3][TY + 1][32];
     float4 xb[2][TY][2][32];                                 // H_new (hz, hx) of rows 0..TY-1, for the row above
     float4 ms[2][TY + 1][4];
+    float4 pms[2][TY + 1][6];                                // 48-byte records of a PML slab row: H pass, E pass
     unsigned long long ebar[2 + DE], hbar[2];
     float4 xs[1];                                            // [nv_h + nv_e][32], sized at launch
 };
@@ -359,12 +360,24 @@ __global__ void __launch_bounds__(32 * (TY + 1), 16 / (TY + 1)) update_he6_kerne
         return -1;
     };
 
+    // lanes 4..9: the two 48-byte slab row records of plane k (if (j, k) is a PML row) into pms[buf]
+    auto stage_pml_rec = [&](int buf, int k) {
+        if (!PML) return;
+        const int pbk = pml_box(k);
+        if (pbk < 0 || !row_ok || lane < 4 || lane >= 10) return;
+        const HePmlBox& Bk = Q.b[pbk];
+        const unsigned char* m = lane < 7 ? Bk.mh : Bk.me;
+        if (m == nullptr) return;
+        const long long lrow = (long long)(k - Bk.z0) * Bk.by + (j - Bk.y0);
+        cp_async16(&S.pms[buf][r][lane - 4], m + lrow * 48 + ((lane - 4) % 3) * 16, true);
+    };
     const int nplanes = kend - kfirst;                       // iterations; E planes kfirst .. kend are needed (nplanes + 1)
 #pragma unroll
     for (int q = 0; q < NS; ++q) if (q <= nplanes) stage_e(q, q);
     stage_h(0, 0);
     if (nplanes > 1) stage_h(1, 1);
     if (lane < 4) cp_async16(&S.ms[0][r][lane], row_ok ? mrec : safe, row_ok);
+    stage_pml_rec(0, kfirst);
     cp_async_commit();
     float4 hx_km = zero4(), hy_km = zero4();
     if (kfirst == kbeg && in_grid && lane >= 1 && r >= 1) { hx_km = ldb4(hout_b + boff - p.b_sz); hy_km = ldb4(hout_b + boff - p.b_sz + p.b_cs); }
@@ -386,6 +399,7 @@ __global__ void __launch_bounds__(32 * (TY + 1), 16 / (TY + 1)) update_he6_kerne
         const bool calc = in_grid && !ext;                   // H_new is computed here (owned cells and halo cells)
         const bool own = calc && lane >= 1 && r >= 1;        // ... and stored, together with E_new
         if (t + 1 < nplanes && lane < 4) cp_async16(&S.ms[mb ^ 1][r][lane], row_ok ? mrec + p.meta_step : safe, row_ok);
+        if (t + 1 < nplanes) stage_pml_rec(mb ^ 1, k + 1);
         cp_async_commit();
         // PML row: slab-local offsets, old flux, row records (issued before the wait on the staged planes)
         long long lofs = 0, lcs = 0;
@@ -396,8 +410,8 @@ __global__ void __launch_bounds__(32 * (TY + 1), 16 / (TY + 1)) update_he6_kerne
             B = &Q.b[pb];
             const long long lrow = (long long)(k - B->z0) * B->by + (j - B->y0);
             lofs = lrow * p.px + i0; lcs = (long long)B->bz * B->by * p.px;
-            if (B->mh) rech = B->mh + lrow * 48;
-            if (B->me) rece = B->me + lrow * 48;
+            if (B->mh) rech = reinterpret_cast<const unsigned char*>(&S.pms[mb][r][0]);
+            if (B->me) rece = reinterpret_cast<const unsigned char*>(&S.pms[mb][r][3]);
             if (calc) { g0 = __ldcs(reinterpret_cast<const float4*>(B->gin + lofs)); g1 = __ldcs(reinterpret_cast<const float4*>(B->gin + lcs + lofs));
                         g2 = __ldcs(reinterpret_cast<const float4*>(B->gin + 2 * lcs + lofs)); }
         }
@@ -441,11 +455,15 @@ __global__ void __launch_bounds__(32 * (TY + 1), 16 / (TY + 1)) update_he6_kerne
                 hz = upd4(az, hz, bz, ey, ey_ip, ex, ex_jp);
             }
         }
+        float4 f0 = zero4(), f1 = zero4(), f2 = zero4();
         if (own && !pro) {
             stb4(qh, hx); stb4(qh + p.b_cs, hy); stb4(qh + p.b_2cs, hz);
             if (PML && pb >= 0) {
                 float* go = B->gout + lofs;
                 __stcs(reinterpret_cast<float4*>(go), g0); __stcs(reinterpret_cast<float4*>(go + lcs), g1); __stcs(reinterpret_cast<float4*>(go + 2 * lcs), g2);
+                const float* fp = B->fv + lofs;              // old voltage flux: in flight while the CTA barrier is crossed
+                f0 = __ldcs(reinterpret_cast<const float4*>(fp)); f1 = __ldcs(reinterpret_cast<const float4*>(fp + lcs));
+                f2 = __ldcs(reinterpret_cast<const float4*>(fp + 2 * lcs));
             }
             if (!PML) row_coefs(S.ms[mb][r][2], S.ms[mb][r][3], xse, p.vv, p.vi, p.xv_e,
                                 boff >> 2, p.cs, i0, p.px, ax, ay, az, bx, by, bz);
@@ -468,8 +486,6 @@ __global__ void __launch_bounds__(32 * (TY + 1), 16 / (TY + 1)) update_he6_kerne
             if (PML && pb >= 0) {
                 float4 a_, fo_, fn_, h_;
                 float* fp = B->fv + lofs;                    // the voltage flux of a cell is touched by its owner only: in place
-                float4 f0 = __ldcs(reinterpret_cast<const float4*>(fp)), f1 = __ldcs(reinterpret_cast<const float4*>(fp + lcs)),
-                       f2 = __ldcs(reinterpret_cast<const float4*>(fp + 2 * lcs));
                 pml_coefs(rece, 0, B->ae, B->foe, B->fne, B->xve, lofs, i0, p.px, a_, fo_, fn_);
                 h_ = pml_pre4(a_, fo_, f0, ex); f0 = upd4(ax, f0, bx, hz, hz_jm, hy, hy_km); exn = pml_post4(fn_, f0, h_);
                 pml_coefs(rece, 1, B->ae, B->foe, B->fne, B->xve, lcs + lofs, i0, p.px, a_, fo_, fn_);

@@ -35,6 +35,24 @@ __global__ void mur_kernel(float* __restrict__ volt, const int64_t* __restrict__
     }
 }
 
+// K3 with implicit indices.  The edges of a Mur face come in long arithmetic runs (a row of a z- or y-face: stride 1; a
+// column of an x-face: stride px), so the lists are stored as segments {first dst, first src, strides, count, first
+// entry}: 40 bytes per run instead of 16 bytes of int64 indices per edge.  One warp per segment; same arithmetic per edge.
+struct MurSeg { long long dst0, src0; int sd, ss; int count; int pad; long long e0; };
+__global__ void __launch_bounds__(128) mur_seg_kernel(float* __restrict__ volt, const MurSeg* __restrict__ segs, int nsegs,
+                                                      const float* __restrict__ coeff, float* __restrict__ tmp, int phase)
+{
+    const int w = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (w >= nsegs) return;
+    const MurSeg S = segs[w];
+    for (int q = lane; q < S.count; q += 32) {
+        const long long e = S.e0 + q, d = S.dst0 + (long long)q * S.sd, sidx = S.src0 + (long long)q * S.ss;
+        if (phase == 0) tmp[e] = __fmaf_rn(-coeff[e], volt[d], volt[sidx]);
+        else if (phase == 1) tmp[e] = __fmaf_rn(coeff[e], volt[sidx], tmp[e]);
+        else volt[d] = tmp[e];
+    }
+}
+
 // K4 PML_8 (App. A4): split-flux UPML, pre and post passes over one slab box (the boxes that are not fused
 // into the volume kernels: the narrow x-slabs).  blockIdx = (row chunk, z, component); threadIdx = (x, row).
 //   pre : h = a*f - fo*flux ; f = flux ; flux = h

@@ -74,8 +74,9 @@ int b200fdtd_expand_rows(b200fdtd_ctx* ctx, int which, int nvec, const float* xv
  * bits 8-12 = rows per CTA of the slab launches (0 = ty), bits 16-17 = L2 prefetch distance of the plain fusion
  * (0 = default 1, 3 = off), 512 = plain fusion (update_he_kernel) instead of the TMA-staged update_he6_kernel,
  * bit 20 = high-end H / low-end E slab launches beside the fused launch instead of before / after it,
- * bit 22 / bit 23 = whole-row PML slabs never / always inside the fused H->E launch (default: inside up to
- * B200FDTD_HE_PML_MAX_CELLS = 6 M cells per slab, where the step is launch-bound; their own launches above) */
+ * bit 23 = whole-row PML slabs inside the fused H->E launch (double-buffered current flux; bit-exact, measured slower than
+ * their own launches on B200, hence off by default), bit 22 = never (overrides bit 23),
+ * bit 24 = Mur edges by index lists even where they form long arithmetic runs */
 int b200fdtd_set_tuning(b200fdtd_ctx* ctx, int kz, int ty, int variant);
 
 /* ---- excitation (openEMS Engine_Ext_Excitation::Apply2Voltages; AddLumpedPort's
