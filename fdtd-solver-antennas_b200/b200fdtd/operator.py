@@ -637,16 +637,18 @@ class OperatorBuilder:
                     eps = np.transpose(eps, (2, 1, 0)).ravel()                         # ij-order like meshgrid
                     c = C0 / np.sqrt(np.maximum(eps, 1e-30))
                     coeff = (c * dt - delta) / (c * dt + delta)
-                    out.append((np.full(len(dst[0]), comp), dst, src, coeff))
+                    out.append((np.full(len(dst[0]), comp), dst, src, coeff, np.full(len(dst[0]), 2 * ax + side)))
         if not out:
             return None
         comp = np.concatenate([o[0] for o in out])
         dst = [np.concatenate([o[1][a] for o in out]) for a in range(3)]
         src = [np.concatenate([o[2][a] for o in out]) for a in range(3)]
         coeff = np.concatenate([o[3] for o in out])
+        self.mur_face = np.concatenate([o[4] for o in out])
         key = ((comp * nz + dst[2]) * ny + dst[1]) * nx + dst[0]
         _, first_rev = np.unique(key[::-1], return_index=True)
         keep = np.sort(len(key) - 1 - first_rev)
+        self.mur_face = self.mur_face[keep]                # which boundary face an entry belongs to (for ordering only)
         return comp[keep], [d[keep] for d in dst], [s[keep] for s in src], coeff[keep]
 
     def probe_lists(self):

@@ -150,10 +150,10 @@ class Simulation:
                 # the inward neighbour of a z-face edge lives in the same slab (checked by the builder)
                 d_lin = lin(comp[sel], dst[2][sel], dst[1][sel], dst[0][sel])
                 s_lin = lin(comp[sel], src[2][sel], src[1][sel], src[0][sel])
-                # memory order: rows of a z- or y-face become runs of stride 1, columns of an x-face runs of stride px
-                # (the engine stores such runs as segments instead of index lists); every edge appears once, so the
-                # order of the list does not change any result
-                o = np.argsort(d_lin, kind="stable")
+                # face by face in memory order: rows of a z- or y-face become runs of stride 1, columns of an x-face runs
+                # of stride px (the engine stores such runs as segments instead of index lists); every edge appears
+                # once, so the order of the list does not change any result
+                o = np.lexsort((d_lin, B.mur_face[sel]))
                 E.set_mur(d_lin[o], s_lin[o], coeff[sel][o])
         # PML
         boxes = []

@@ -858,7 +858,7 @@ extern "C" int b200fdtd_set_mur(b200fdtd_ctx* c, int64_t n, const int64_t* dst, 
     if (upload(&c->mur_coeff, coeff, n, c->stream)) return 1;
     if (c->mur_tmp) { cudaFree(c->mur_tmp); c->mur_tmp = nullptr; }
     if (n > 0) { CK(cudaMalloc((void**)&c->mur_tmp, sizeof(float) * n)); CK(cudaMemsetAsync(c->mur_tmp, 0, sizeof(float) * n, c->stream)); }
-    // arithmetic runs of (dst, src): rows / columns of the boundary faces
+    // arithmetic runs of (dst, src): rows / columns of the boundary faces (at most 1024 edges each: one warp sweeps a run)
     std::vector<MurSeg> segs;
     for (int64_t e = 0; e < n;) {
         MurSeg S; S.dst0 = dst[e]; S.src0 = src[e]; S.e0 = e; S.pad = 0; S.sd = 0; S.ss = 0; S.count = 1;
@@ -866,7 +866,7 @@ extern "C" int b200fdtd_set_mur(b200fdtd_ctx* c, int64_t n, const int64_t* dst, 
             const long long sd = dst[e + 1] - dst[e], ss = src[e + 1] - src[e];
             if (sd > -(1LL << 30) && sd < (1LL << 30) && ss > -(1LL << 30) && ss < (1LL << 30)) {
                 S.sd = (int)sd; S.ss = (int)ss;
-                while (e + S.count < n && S.count < (1 << 20) && dst[e + S.count] - dst[e + S.count - 1] == sd &&
+                while (e + S.count < n && S.count < 1024 && dst[e + S.count] - dst[e + S.count - 1] == sd &&
                        src[e + S.count] - src[e + S.count - 1] == ss) S.count++;
             }
         }
@@ -1641,11 +1641,11 @@ extern "C" int b200fdtd_farfield(int device, void* stream, int64_t npts, const f
     cudaStream_t s = (cudaStream_t)stream;
     // direction + partial-sum buffer of the calling thread, grown on demand and kept (the reference calls CalcNF2FF once per phi: 73 calls)
     static thread_local double* d_dir = nullptr; static thread_local int d_cap = 0, d_dev = -1;
-    const int target = 148 * 4;
-    int nsplit = (target + ndir - 1) / ndir;
+    const int target = 148 * 4, ngroups = (ndir + 7) / 8;                            // a block = 8 directions (one per warp)
+    int nsplit = (target + ngroups - 1) / ngroups;
     if ((long long)nsplit * 2048 > npts) nsplit = (int)((npts + 2047) / 2048);       // at least ~2 k points per block
     if (nsplit < 1) nsplit = 1;
-    if (nsplit > 64) nsplit = 64;
+    if (nsplit > 64) nsplit = 64;                                                    // (partial-sum buffer: 64 shares per direction)
     if (d_dev != device || d_cap < ndir) {
         if (d_dir && d_dev >= 0) { cudaSetDevice(d_dev); cudaFree(d_dir); cudaSetDevice(device); }
         d_dir = nullptr; d_cap = 0; d_dev = device;
@@ -1656,7 +1656,7 @@ extern "C" int b200fdtd_farfield(int device, void* stream, int64_t npts, const f
     double* d_part = d_dir + 2 * (size_t)d_cap;
     CK(cudaMemcpyAsync(d_dir, theta, sizeof(double) * ndir, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(d_dir + d_cap, phi, sizeof(double) * ndir, cudaMemcpyHostToDevice, s));
-    farfield_kernel<<<dim3(ndir, nsplit), 256, 0, s>>>(npts, pos, J, M, k, ndir, d_dir, d_dir + d_cap, d_part);
+    farfield_kernel<<<dim3(ngroups, nsplit), 256, 0, s>>>(npts, pos, J, M, k, ndir, d_dir, d_dir + d_cap, d_part);
     CKL();
     farfield_final_kernel<<<(ndir + 127) / 128, 128, 0, s>>>(ndir, nsplit, d_part, d_dir, d_dir + d_cap, out);
     CKL();

@@ -425,7 +425,14 @@ __global__ void __launch_bounds__(32 * (TY + 1), 16 / (TY + 1)) update_he6_kerne
             }
         }
         float4 hx = zero4(), hy = zero4(), hz = zero4();
-        if (ext) { hx = ldb4(qh); hy = ldb4(qh + p.b_cs); hz = ldb4(qh + p.b_2cs); }
+        // H_new of cells a slab launch owns, where an owned cell of this tile needs it (the lane left of an owned lane, the
+        // row below the first owned row).  Loaded into registers of their own and merged after the H phase: the loads (L2 or
+        // DRAM round trips) then overlap the whole H phase instead of blocking the first instruction that reuses a register.
+        const int own_right = __shfl_down_sync(0xffffffffu, own ? 1 : 0, 1);      // every lane takes part (no short-circuit around it)
+        // (with PML rows inside, the row or plane above may own columns this row does not: then every such value is needed)
+        const bool ext_need = ext && (PML || j < p.Y0 || own_right != 0);
+        float4 hxe = zero4(), hye = zero4(), hze = zero4();
+        if (ext_need) { hxe = ldb4(qh); hye = ldb4(qh + p.b_cs); hze = ldb4(qh + p.b_2cs); }
         mbar_wait(&S.ebar[se1], (unsigned)((t + 1) / NS) & 1u);  // plane k+1 has landed (plane k was waited for one iteration ago)
         mbar_wait(&S.hbar[sh], (unsigned)(t >> 1) & 1u);
         float4 ax = zero4(), ay = zero4(), az = zero4(), bx = zero4(), by = zero4(), bz = zero4();
@@ -455,6 +462,7 @@ __global__ void __launch_bounds__(32 * (TY + 1), 16 / (TY + 1)) update_he6_kerne
                 hz = upd4(az, hz, bz, ey, ey_ip, ex, ex_jp);
             }
         }
+        if (ext) { hx = hxe; hy = hye; hz = hze; }
         float4 f0 = zero4(), f1 = zero4(), f2 = zero4();
         if (own && !pro) {
             stb4(qh, hx); stb4(qh + p.b_cs, hy); stb4(qh + p.b_2cs, hz);

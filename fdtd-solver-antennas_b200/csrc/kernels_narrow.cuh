@@ -262,47 +262,65 @@ __global__ void energy_final_kernel(const double* __restrict__ partials, int n, 
 }
 
 // K11 far field: N = sum J e^{jk r^.r'}, L = sum M e^{jk r^.r'} projected on theta^/phi^ (App. A6)
-// grid (ndir, nsplit): block (d, s) sums its share of the surface points for direction d in fp64 and writes 12 partial sums;
-// farfield_final_kernel adds the shares in a fixed order (deterministic) and projects.  The reference asks for one phi at a
-// time (91 directions per call): without the split a call would occupy 91 of 148 SMs with one block each.
+// grid (ceil(ndir / 8), nsplit): a block sums its share of the surface points for 8 directions, one per warp.  The points
+// are staged through shared memory in chunks of 256, so every point is fetched once per 8 directions (the sources of a
+// 100 M-cell scene are 76 MB: per direction that read was the bound); fp64 phase and accumulation; farfield_final_kernel
+// adds the shares in a fixed order (deterministic) and projects.
+#define FF_CHUNK 256
 __global__ void __launch_bounds__(256) farfield_kernel(long long npts, const float* __restrict__ pos,
         const float* __restrict__ J, const float* __restrict__ M, double k, int ndir,
         const double* __restrict__ theta, const double* __restrict__ phi, double* __restrict__ partial)
 {
-    const int d = blockIdx.x;
-    if (d >= ndir) return;
-    double st, ct, sp, cp;
-    sincos(theta[d], &st, &ct); sincos(phi[d], &sp, &cp);
-    // phase in turns, formed and reduced in fp64 (k r can be hundreds of radians on a large box), then one fp32 sincospi
-    const double ux = k * st * cp * 0.15915494309189535, uy = k * st * sp * 0.15915494309189535, uz = k * ct * 0.15915494309189535;
+    __shared__ float sp_[3][FF_CHUNK];
+    __shared__ float2 sj_[3][FF_CHUNK], sm_[3][FF_CHUNK];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int d = blockIdx.x * 8 + warp;
+    const bool live = d < ndir;
+    double ux = 0, uy = 0, uz = 0;
+    if (live) {
+        double st, ct, sp, cp;
+        sincos(theta[d], &st, &ct); sincos(phi[d], &sp, &cp);
+        // phase in turns, formed and reduced in fp64 (k r can be hundreds of radians on a large box), then one fp32 sincospi
+        ux = k * st * cp * 0.15915494309189535; uy = k * st * sp * 0.15915494309189535; uz = k * ct * 0.15915494309189535;
+    }
     double a[12];
 #pragma unroll
     for (int i = 0; i < 12; ++i) a[i] = 0.0;
     const long long per = (npts + gridDim.y - 1) / gridDim.y;
     const long long q0 = per * blockIdx.y, q1 = min(npts, q0 + per);
-    for (long long q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
-        double tn = ux * (double)pos[q] + uy * (double)pos[npts + q] + uz * (double)pos[2 * npts + q];
-        tn -= rint(tn);
-        float sn, cn; sincospif(2.0f * (float)tn, &sn, &cn);
+    for (long long c0 = q0; c0 < q1; c0 += FF_CHUNK) {
+        const int m = (int)min((long long)FF_CHUNK, q1 - c0);
+        __syncthreads();
+        if ((int)threadIdx.x < m) {
+            const long long q = c0 + threadIdx.x;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float2 jv = reinterpret_cast<const float2*>(J)[c * npts + q], mv = reinterpret_cast<const float2*>(M)[c * npts + q];
-            a[2 * c] += (double)(jv.x * cn - jv.y * sn); a[2 * c + 1] += (double)(jv.x * sn + jv.y * cn);
-            a[6 + 2 * c] += (double)(mv.x * cn - mv.y * sn); a[6 + 2 * c + 1] += (double)(mv.x * sn + mv.y * cn);
+            for (int c = 0; c < 3; ++c) {
+                sp_[c][threadIdx.x] = pos[c * npts + q];
+                sj_[c][threadIdx.x] = reinterpret_cast<const float2*>(J)[c * npts + q];
+                sm_[c][threadIdx.x] = reinterpret_cast<const float2*>(M)[c * npts + q];
+            }
+        }
+        __syncthreads();
+        if (live) {
+            for (int t = lane; t < m; t += 32) {
+                double tn = ux * (double)sp_[0][t] + uy * (double)sp_[1][t] + uz * (double)sp_[2][t];
+                tn -= rint(tn);
+                float sn, cn; sincospif(2.0f * (float)tn, &sn, &cn);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float2 jv = sj_[c][t], mv = sm_[c][t];
+                    a[2 * c] += (double)(jv.x * cn - jv.y * sn); a[2 * c + 1] += (double)(jv.x * sn + jv.y * cn);
+                    a[6 + 2 * c] += (double)(mv.x * cn - mv.y * sn); a[6 + 2 * c + 1] += (double)(mv.x * sn + mv.y * cn);
+                }
+            }
         }
     }
-    __shared__ double red[8][12];
+    if (!live) return;
 #pragma unroll
     for (int i = 0; i < 12; ++i) {
         double v = a[i];
         for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][i] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x < 12) {
-        double s = 0;
-        for (int wv = 0; wv < 8; ++wv) s += red[wv][threadIdx.x];
-        partial[((long long)d * gridDim.y + blockIdx.y) * 12 + threadIdx.x] = s;
+        if (lane == 0) partial[((long long)d * gridDim.y + blockIdx.y) * 12 + i] = v;
     }
 }
 __global__ void farfield_final_kernel(int ndir, int nsplit, const double* __restrict__ partial,
