@@ -14,6 +14,7 @@
 //   curl = ((a - b) - c) + d          (three rounded fp32 adds, this order)
 //   f    = fmaf(ca, f, cb * curl)     (one rounded multiply, one fused multiply-add)
 #include <cuda_runtime.h>
+#include <cuda.h>               // CUtensorMap (the encoder itself comes from the driver through cudaGetDriverEntryPoint: no -lcuda)
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -157,17 +158,32 @@ static int sample_interval(const b200fdtd_ctx* c) {
 #include "kernels_volume.cuh"      // K1/K2 volume updates
 #include "kernels_fused.cuh"       // fused H->E launch (all generations)
 
-template <int MODE>
-static int launch_volume_one(b200fdtd_ctx* c, int which, int k0, int k1, const RowParams& r, cudaStream_t stream, int kz, int nchunks, int grid_y = 0)
+static void fill_vol_params(const b200fdtd_ctx* c, int which, VolParams& p)
 {
-    if (k1 <= k0 || r.j1 <= r.j0 || nchunks <= 0) return 0;
-    VolParams p;
     p.fin = which == 0 ? cur_volt(c) : cur_curr(c);
     p.f = c->flip ? (which == 0 ? oth_volt(c) : oth_curr(c)) : const_cast<float*>(p.fin);
     p.g = which == 0 ? cur_curr(c) : cur_volt(c);
     p.ca = which == 0 ? c->vv : c->ii;
     p.cb = which == 0 ? c->vi : c->iv;
     p.nx = c->nx; p.ny = c->ny; p.nz = c->nz; p.px = c->px; p.sz = c->sz; p.cs = c->cs;
+    p.kz = 1; p.k0 = 0; p.k1 = 0;
+    p.xv = c->cmp_xv[which]; p.meta = c->cmp_meta[which];
+}
+
+template <int MODE>
+static int launch_volume_one(b200fdtd_ctx* c, int which, int k0, int k1, const RowParams& r, cudaStream_t stream, int kz, int nchunks, int grid_y = 0,
+                             SlabSet* collect = nullptr)
+{
+    if (k1 <= k0 || r.j1 <= r.j0 || nchunks <= 0) return 0;
+    if (collect != nullptr && MODE != 0) {                  // merged slab launch: only note what this launch would have been
+        if (collect->n >= MAX_SLABS) return fail("too many PML slabs for one merged launch");
+        const int ty_s = ((c->variant >> 8) & 31) ? ((c->variant >> 8) & 31) : c->ty;
+        SlabEntry& E = collect->e[collect->n++];
+        E.r = r; E.mode = MODE; E.gx = nchunks; E.gy = grid_y > 0 ? grid_y : (r.j1 - r.j0 + ty_s - 1) / ty_s; E.gz = (k1 - k0 + kz - 1) / kz;
+        E.kz = kz; E.k0 = k0; E.k1 = k1; E.cta0 = 0;
+        return 0;
+    }
+    VolParams p; fill_vol_params(c, which, p);
     p.kz = kz; p.k0 = k0; p.k1 = k1;
     // slab launches may use their own CTA height (variant bits 8-12): a 2-row slab CTA has the register footprint of one
     // plain CTA, so it fits the slot a retiring plain CTA frees when both run concurrently
@@ -177,7 +193,6 @@ static int launch_volume_one(b200fdtd_ctx* c, int which, int k0, int k1, const R
     dim3 grid(nchunks, grid_y > 0 ? grid_y : (r.j1 - r.j0 + ty - 1) / ty, (k1 - k0 + kz - 1) / kz);
     if (grid.y > 65535 || grid.z > 65535) return fail("grid too large for launch (ny/ty=%u, nz/kz=%u)", grid.y, grid.z);
     const bool cmp = c->cmp_meta[which] != nullptr && (c->variant & 4) == 0;
-    p.xv = c->cmp_xv[which]; p.meta = c->cmp_meta[which];
 #define LAUNCH(TYV) do { \
         if (which == 0) { if (cmp) update_e_kernel<TYV, MODE, true><<<grid, block, 0, stream>>>(p, r); \
                           else update_e_kernel<TYV, MODE, false><<<grid, block, 0, stream>>>(p, r); } \
@@ -312,7 +327,7 @@ static int slab_kz(int kz, int planes, long long ctas_per_chunk)
 
 // narrow x-slab launches (MODE 2): PML pre/update/post on the slab columns of the plain rows
 // sel: 0 = both slabs, 1 = only the slab at the low end of x, 2 = only the one at the high end
-static int launch_volume_xslabs(b200fdtd_ctx* c, int which, int k0, int k1, cudaStream_t stream, int sel = 0)
+static int launch_volume_xslabs(b200fdtd_ctx* c, int which, int k0, int k1, cudaStream_t stream, int sel = 0, SlabSet* collect = nullptr)
 {
     VolumePlan P = c->plan;
     if (!P.xedge) return 0;
@@ -342,12 +357,12 @@ static int launch_volume_xslabs(b200fdtd_ctx* c, int which, int k0, int k1, cuda
     const int kz = slab_kz(c->kz, b - a, ((long long)gy * (P.has_lo + P.has_hi) + 3) / 4);
     // launch_volume_one derives grid.y from (j1-j0)/ty: pass an equivalent row count
     g.j0 = e.j0; 
-    return launch_volume_one<2>(c, which, a, b, g, stream, kz, P.has_lo + P.has_hi, gy);
+    return launch_volume_one<2>(c, which, a, b, g, stream, kz, P.has_lo + P.has_hi, gy, collect);
 }
 
 // volume launches over the fused PML slabs (pre -> update -> post in registers)
 // sel: 0 = all slabs, 1 = only the slabs at the low end of their axis (z0 = 0 / y0 = 0), 2 = only those at the high end
-static int launch_volume_fused(b200fdtd_ctx* c, int which, int k0, int k1, cudaStream_t stream, int sel = 0)
+static int launch_volume_fused(b200fdtd_ctx* c, int which, int k0, int k1, cudaStream_t stream, int sel = 0, SlabSet* collect = nullptr)
 {
     const VolumePlan& P = c->plan;
     for (int q = 0; q < P.nfused; ++q) {
@@ -371,8 +386,50 @@ static int launch_volume_fused(b200fdtd_ctx* c, int which, int k0, int k1, cudaS
         const int kz = slab_kz(c->kz, b - a, per_chunk);
         cudaStream_t st = stream;
         if (stream == c->side2 && q > 0 && q <= 3 && (c->variant & 1024) == 0) st = c->slab_s[q - 1];
-        if (launch_volume_one<1>(c, which, a, b, f, st, kz, (c->px + 127) / 128)) return 1;
+        if (launch_volume_one<1>(c, which, a, b, f, st, kz, (c->px + 127) / 128, 0, collect)) return 1;
     }
+    return 0;
+}
+
+// every PML slab of one half step (planes [k0,k1)) in one launch (update_slabs_kernel); variant bit 26: one launch per slab
+static bool slabs_merged(const b200fdtd_ctx* c) { return (c->variant & (1 << 26)) == 0; }
+static int launch_slabs_merged(b200fdtd_ctx* c, int which, int k0, int k1, cudaStream_t stream, bool with_whole_rows = true, int sel = 0)
+{
+    SlabSet T; memset(&T, 0, sizeof(T));
+    if (launch_volume_xslabs(c, which, k0, k1, stream, sel, &T)) return 1;
+    if (with_whole_rows) if (launch_volume_fused(c, which, k0, k1, stream, sel, &T)) return 1;
+    if (T.n == 0) return 0;
+    long long total = 0;
+    for (int q = 0; q < T.n; ++q) { T.e[q].cta0 = (int)total; total += (long long)T.e[q].gx * T.e[q].gy * T.e[q].gz; }
+    if (total > 0x7fffffffLL) return fail("merged slab launch too large");
+    VolParams p; fill_vol_params(c, which, p);
+    const bool cmp = c->cmp_meta[which] != nullptr && (c->variant & 4) == 0;
+    const int ty = slab_ty(c);
+    dim3 block(32, ty);
+#define LAUNCH_SLABS(TYV) do { \
+        if (which == 0) { if (cmp) update_slabs_kernel<0, TYV, true><<<(unsigned)total, block, 0, stream>>>(p, T); \
+                          else update_slabs_kernel<0, TYV, false><<<(unsigned)total, block, 0, stream>>>(p, T); } \
+        else { if (cmp) update_slabs_kernel<1, TYV, true><<<(unsigned)total, block, 0, stream>>>(p, T); \
+               else update_slabs_kernel<1, TYV, false><<<(unsigned)total, block, 0, stream>>>(p, T); } } while (0)
+    switch (ty) {
+        case 1: LAUNCH_SLABS(1); break;
+        case 2: LAUNCH_SLABS(2); break;
+        case 4: LAUNCH_SLABS(4); break;
+        case 8: LAUNCH_SLABS(8); break;
+        case 16: LAUNCH_SLABS(16); break;
+        default: return fail("unsupported slab ty=%d", ty);
+    }
+#undef LAUNCH_SLABS
+    CKL();
+    return 0;
+}
+// the slab launches of one half step on `stream` (merged) or on the side streams the caller has forked (one launch per slab)
+static int launch_slabs(b200fdtd_ctx* c, int which, int k0, int k1, cudaStream_t merged_stream, cudaStream_t x_stream, cudaStream_t row_stream,
+                        bool with_whole_rows = true, int sel = 0)
+{
+    if (slabs_merged(c)) return launch_slabs_merged(c, which, k0, k1, merged_stream, with_whole_rows, sel);
+    if (launch_volume_xslabs(c, which, k0, k1, x_stream, sel)) return 1;
+    if (with_whole_rows) return launch_volume_fused(c, which, k0, k1, row_stream, sel);
     return 0;
 }
 
@@ -382,8 +439,7 @@ static int launch_volume(b200fdtd_ctx* c, int which, int k0, int k1)
     if (!c->volt || !c->vv) return fail("fields/coefficients not bound");
     if (!c->plan.valid) if (build_plan(c)) return 1;
     if (launch_volume_plain(c, which, k0, k1, c->stream)) return 1;
-    if (launch_volume_xslabs(c, which, k0, k1, c->stream)) return 1;
-    return launch_volume_fused(c, which, k0, k1, c->stream);
+    return launch_slabs(c, which, k0, k1, c->stream, c->stream, c->stream);
 }
 
 
@@ -399,6 +455,32 @@ static size_t he6_smem(int ty, int de, size_t xs_bytes)
     }
     return (size_t)1 << 30;
 }
+// 4-D tensor map of one field array [3][nz+2][ny][px] with a box of [3][rows][cols] (one plane): the whole tile of a CTA
+// comes in with one cp.async.bulk.tensor instruction per field; elements outside the grid read as zero
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tensor_map_encoder()
+{
+    static EncodeTiledFn fn = [] {
+        void* f = nullptr; cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) { cudaGetLastError(); f = nullptr; }
+        return (EncodeTiledFn)f;
+    }();
+    return fn;
+}
+static bool encode_field_map(CUtensorMap* m, const b200fdtd_ctx* c, const float* field, int box_cols, int box_rows)
+{
+    EncodeTiledFn enc = tensor_map_encoder();
+    if (!enc) return false;
+    const cuuint64_t dims[4] = {(cuuint64_t)c->px, (cuuint64_t)c->ny, (cuuint64_t)(c->nz + 2), 3};
+    const cuuint64_t strides[3] = {(cuuint64_t)c->px * 4, (cuuint64_t)c->sz * 4, (cuuint64_t)c->cs * 4};
+    const cuuint32_t box[4] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1, 3};
+    const cuuint32_t es[4] = {1, 1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(field), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 struct HeChoice { bool he6; int de; bool pml; };
 static HeChoice he_choice(const b200fdtd_ctx* c)
 {
@@ -517,9 +599,16 @@ static int launch_he(b200fdtd_ctx* c, cudaStream_t stream, int zc0 = -1, int zc1
     p.xv_pitch = 4u * (unsigned)p.px; p.meta_step = 32 * p.ny;
     p.nv_e = c->cmp_nvec[0]; p.nv_h = c->cmp_nvec[1];
     const size_t xs_bytes = (size_t)(p.nv_e + p.nv_h) * 32 * sizeof(float4);
+    // whole-tile staging by tiled TMA copies (one instruction per field and plane instead of eight row copies per warp);
+    // variant bit 25 keeps the per-row 1-D bulk copies
+    CUtensorMap tmE, tmH; memset(&tmE, 0, sizeof(tmE)); memset(&tmH, 0, sizeof(tmH));
+    const bool tm = hc.he6 && (c->variant & (1 << 25)) == 0 && p.px * 4LL < (1LL << 32) &&
+                    encode_field_map(&tmE, c, p.ein, 132, ty + 2) && encode_field_map(&tmH, c, p.hin, 128, ty + 1);
 #define LAUNCH_HE6(TYV, DEV, PMLV) do { const size_t sm6 = sizeof(He6Smem<TYV, DEV>) + xs_bytes; \
-        CK(cudaFuncSetAttribute(update_he6_kernel<TYV, DEV, PMLV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm6)); \
-        update_he6_kernel<TYV, DEV, PMLV><<<grid, block, sm6, stream>>>(p, Q); } while (0)
+        if (tm) { CK(cudaFuncSetAttribute(update_he6_kernel<TYV, DEV, PMLV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm6)); \
+                  update_he6_kernel<TYV, DEV, PMLV, true><<<grid, block, sm6, stream>>>(p, Q, tmE, tmH); } \
+        else { CK(cudaFuncSetAttribute(update_he6_kernel<TYV, DEV, PMLV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm6)); \
+               update_he6_kernel<TYV, DEV, PMLV, false><<<grid, block, sm6, stream>>>(p, Q, tmE, tmH); } } while (0)
 #define LAUNCH_HE(TYV) do { \
         if (hc.he6) { if (hc.de == 2) { if (pml) LAUNCH_HE6(TYV, 2, true); else LAUNCH_HE6(TYV, 2, false); } \
                       else { if (pml) LAUNCH_HE6(TYV, 1, true); else LAUNCH_HE6(TYV, 1, false); } } \
@@ -1176,11 +1265,10 @@ static int e_half(b200fdtd_ctx* c, int off)
     if (!c->plan.valid) if (build_plan(c)) return 1;
     const bool side = (c->plan.nfused > 0 || c->plan.xedge) && (c->variant & 2) == 0;
     if (launch_mur(c, 0)) return 1;              // Mur sees the true field, before any PML pass swaps in the flux
-    if (side) { if (fork_side(c)) return 1; if (launch_volume_xslabs(c, 0, 0, c->nz, c->side)) return 1;
-                if (launch_volume_fused(c, 0, 0, c->nz, slab_stream(c))) return 1; }
+    if (side) { if (fork_side(c)) return 1; if (launch_slabs(c, 0, 0, c->nz, c->side, c->side, slab_stream(c))) return 1; }
     if (launch_pml(c, 0, 0)) return 1;
     if (launch_volume_plain(c, 0, 0, c->nz, c->stream)) return 1;
-    if (!side) { if (launch_volume_xslabs(c, 0, 0, c->nz, c->stream)) return 1; if (launch_volume_fused(c, 0, 0, c->nz, c->stream)) return 1; }
+    if (!side) { if (launch_slabs(c, 0, 0, c->nz, c->stream, c->stream, c->stream)) return 1; }
     if (launch_pml(c, 0, 1)) return 1;
     if (side) if (join_side(c)) return 1;
     if (c->flip) c->vcur ^= 1;                    // the new E lives in the other copy
@@ -1193,11 +1281,10 @@ static int h_half(b200fdtd_ctx* c)
 {
     if (!c->plan.valid) if (build_plan(c)) return 1;
     const bool side = (c->plan.nfused > 0 || c->plan.xedge) && (c->variant & 2) == 0;
-    if (side) { if (fork_side(c)) return 1; if (launch_volume_xslabs(c, 1, 0, c->nz, c->side)) return 1;
-                if (launch_volume_fused(c, 1, 0, c->nz, slab_stream(c))) return 1; }
+    if (side) { if (fork_side(c)) return 1; if (launch_slabs(c, 1, 0, c->nz, c->side, c->side, slab_stream(c))) return 1; }
     if (launch_pml(c, 1, 0)) return 1;
     if (launch_volume_plain(c, 1, 0, c->nz, c->stream)) return 1;
-    if (!side) { if (launch_volume_xslabs(c, 1, 0, c->nz, c->stream)) return 1; if (launch_volume_fused(c, 1, 0, c->nz, c->stream)) return 1; }
+    if (!side) { if (launch_slabs(c, 1, 0, c->nz, c->stream, c->stream, c->stream)) return 1; }
     if (launch_pml(c, 1, 1)) return 1;
     if (side) if (join_side(c)) return 1;
     if (c->flip) c->ccur ^= 1;
@@ -1241,12 +1328,13 @@ static int he_step(b200fdtd_ctx* c, int off)
             c->vcur ^= 1;
             break;
         }
-        if (inhe) {
-            // only the narrow x-slabs keep their own launches: H before the fused launch (it reads their H_new), E after it
-            if ((rc = launch_volume_xslabs(c, 1, 0, c->nz, c->stream))) break;
+        if (inhe || slabs_merged(c)) {
+            // H of the slabs the fused launch does not sweep (one merged launch), the fused launch (it reads their H_new on
+            // its halo), E of those slabs: three launches on one stream
+            if ((rc = launch_slabs(c, 1, 0, c->nz, c->stream, c->stream, c->stream, !inhe))) break;
             if ((rc = launch_he(c, c->stream))) break;
-            c->ccur ^= 1; c->fcur ^= 1;
-            if ((rc = launch_volume_xslabs(c, 0, 0, c->nz, c->stream))) break;
+            c->ccur ^= 1; if (c->flux_pp) c->fcur ^= 1;
+            if ((rc = launch_slabs(c, 0, 0, c->nz, c->stream, c->stream, c->stream, !inhe))) break;
             c->vcur ^= 1;
             break;
         }
@@ -1459,8 +1547,7 @@ extern "C" int b200fdtd_fused_step_part(b200fdtd_ctx* c, int part)
         if (launch_mur(c, 0)) return 1;
         c->flip = true;
         if (side) rc = fork_side(c);
-        if (!rc) rc = launch_volume_xslabs(c, 1, 1, nz - 1, side ? c->side : c->stream);
-        if (!rc && !inhe) rc = launch_volume_fused(c, 1, 1, nz - 1, side ? slab_stream(c) : c->stream);
+        if (!rc) rc = launch_slabs(c, 1, 1, nz - 1, side ? c->side : c->stream, side ? c->side : c->stream, side ? slab_stream(c) : c->stream, !inhe);
         if (!rc) rc = launch_volume(c, 1, 0, 1);
         if (!rc && side) rc = join_side(c);
         c->flip = false;
@@ -1487,8 +1574,7 @@ extern "C" int b200fdtd_fused_step_part(b200fdtd_ctx* c, int part)
     }
     c->flip = true;
     if (side) rc = fork_side(c);
-    if (!rc) rc = launch_volume_xslabs(c, 0, 1, nz - 1, side ? c->side : c->stream);
-    if (!rc && !inhe) rc = launch_volume_fused(c, 0, 1, nz - 1, side ? slab_stream(c) : c->stream);
+    if (!rc) rc = launch_slabs(c, 0, 1, nz - 1, side ? c->side : c->stream, side ? c->side : c->stream, side ? slab_stream(c) : c->stream, !inhe);
     if (!rc) rc = launch_volume(c, 0, 0, 1);
     if (!rc) rc = launch_volume(c, 0, nz - 1, nz);
     if (!rc && side) rc = join_side(c);

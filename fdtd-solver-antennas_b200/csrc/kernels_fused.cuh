@@ -259,10 +259,20 @@ __device__ __forceinline__ void pml_coefs(const unsigned char* rec, int c, const
     }
 }
 
+// one tiled TMA copy of a [3 components][rows][columns] box of a field into shared memory (4-D tensor map over
+// [component][plane][row][column]; out-of-grid elements are zero-filled by the TMA engine)
+__device__ __forceinline__ void tma_box4(void* smem, const void* tmap, int c0, int c1, int c2, int c3, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                 :: "r"(smem_u32(smem)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)) : "memory");
+}
+
 template <int TY, int DE>
 struct He6Smem {
-    float4 es[2 + DE][3][TY + 2][33];
-    float4 hs[2][3][TY + 1][32];
+    struct alignas(128) ESlot { float4 v[3][TY + 2][33]; };  // (a tiled TMA copy wants a 128-byte aligned destination)
+    struct alignas(128) HSlot { float4 v[3][TY + 1][32]; };
+    ESlot es_[2 + DE];
+    HSlot hs_[2];
     float4 xb[2][TY][2][32];                                 // H_new (hz, hx) of rows 0..TY-1, for the row above
     float4 ms[2][TY + 1][4];
     float4 pms[2][TY + 1][6];                                // 48-byte records of a PML slab row: H pass, E pass
@@ -270,11 +280,12 @@ struct He6Smem {
     float4 xs[1];                                            // [nv_h + nv_e][32], sized at launch
 };
 
-template <int TY, int DE, bool PML>
-__global__ void __launch_bounds__(32 * (TY + 1), 16 / (TY + 1)) update_he6_kernel(const HeParams p, const __grid_constant__ HePml Q)
+template <int TY, int DE, bool PML, bool TM>
+__global__ void __launch_bounds__(32 * (TY + 1), 16 / (TY + 1)) update_he6_kernel(const HeParams p, const __grid_constant__ HePml Q,
+        const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmH)
 {
     constexpr int NS = 2 + DE;
-    extern __shared__ __align__(16) unsigned char he6_raw[];
+    extern __shared__ __align__(1024) unsigned char he6_raw[];
     He6Smem<TY, DE>& S = *reinterpret_cast<He6Smem<TY, DE>*>(he6_raw);
     const int lane = threadIdx.x, r = threadIdx.y;
     const int i_seg = p.X0s - 4 + HE_SEG * (int)blockIdx.x;  // column of lane 0
@@ -288,12 +299,15 @@ __global__ void __launch_bounds__(32 * (TY + 1), 16 / (TY + 1)) update_he6_kerne
             const float* src = v < p.nv_h ? p.xv_h + (size_t)v * p.px : p.xv_e + (size_t)(v - p.nv_h) * p.px;
             S.xs[v * 32 + lane] = col_ok ? __ldg(reinterpret_cast<const float4*>(src + i0)) : zero4();
         }
-        float4* z = &S.es[0][0][0][0];
-        const int nz4 = (int)((sizeof(S.es) + sizeof(S.hs)) / sizeof(float4));
-        for (int q = r * 32 + lane; q < nz4; q += 32 * (TY + 1)) z[q] = zero4();
+        if (!TM) {                                           // (a tiled TMA copy zero-fills what lies outside the grid itself)
+            float4* z = &S.es_[0].v[0][0][0];
+            const int nz4 = (int)((sizeof(S.es_) + sizeof(S.hs_)) / sizeof(float4));
+            for (int q = r * 32 + lane; q < nz4; q += 32 * (TY + 1)) z[q] = zero4();
+        }
         if (r == 0 && lane == 0) {
-            for (int q = 0; q < NS; ++q) mbar_init(&S.ebar[q], TY + 1);
-            mbar_init(&S.hbar[0], TY + 1); mbar_init(&S.hbar[1], TY + 1);
+            const unsigned arrivals = TM ? 1u : (unsigned)(TY + 1);      // TM: one thread issues the copies of the whole CTA
+            for (int q = 0; q < NS; ++q) mbar_init(&S.ebar[q], arrivals);
+            mbar_init(&S.hbar[0], arrivals); mbar_init(&S.hbar[1], arrivals);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the zeros are ordered before the TMA writes
@@ -324,30 +338,45 @@ __global__ void __launch_bounds__(32 * (TY + 1), 16 / (TY + 1)) update_he6_kerne
 
     int tcur = 0;                                            // iteration boff belongs to
     // lane 0 of every warp: hand this warp's rows of E_old(plane kfirst + d) to the TMA engine, into ring slot `slot`
+    const int j_first = p.Y0 - 1 + TY * (int)blockIdx.y;     // row of warp 0
     auto stage_e = [&](int slot, int d) {
+        if (TM) {      // one tiled copy: [3][TY+2 rows][132 columns] of plane kfirst + d
+            if (r == 0 && lane == 0) {
+                mbar_arrive_expect(&S.ebar[slot], 3u * (TY + 2) * 132u * 4u);
+                tma_box4(&S.es_[slot], &tmE, i_seg, j_first, kfirst + 1 + d, 0, &S.ebar[slot]);
+            }
+            return;
+        }
         if (lane != 0) return;
         unsigned long long* bar = &S.ebar[slot];
         mbar_arrive_expect(bar, bytes_e);
         const char* g = ein_b + (boff + soff) + (long long)(d - tcur) * p.b_sz;
         if (e_row) {
-            bulk_g2s(&S.es[slot][0][r][c_lo], g, nb_e, bar);
-            bulk_g2s(&S.es[slot][1][r][c_lo], g + p.b_cs, nb_e, bar);
-            bulk_g2s(&S.es[slot][2][r][c_lo], g + p.b_2cs, nb_e, bar);
+            bulk_g2s(&S.es_[slot].v[0][r][c_lo], g, nb_e, bar);
+            bulk_g2s(&S.es_[slot].v[1][r][c_lo], g + p.b_cs, nb_e, bar);
+            bulk_g2s(&S.es_[slot].v[2][r][c_lo], g + p.b_2cs, nb_e, bar);
         }
         if (e_top) {
-            bulk_g2s(&S.es[slot][0][TY + 1][c_lo], g + p.b_row, nb_e, bar);
-            bulk_g2s(&S.es[slot][2][TY + 1][c_lo], g + p.b_row_2cs, nb_e, bar);
+            bulk_g2s(&S.es_[slot].v[0][TY + 1][c_lo], g + p.b_row, nb_e, bar);
+            bulk_g2s(&S.es_[slot].v[2][TY + 1][c_lo], g + p.b_row_2cs, nb_e, bar);
         }
     };
     auto stage_h = [&](int slot, int d) {
+        if (TM) {
+            if (r == 0 && lane == 0) {
+                mbar_arrive_expect(&S.hbar[slot], 3u * (TY + 1) * 128u * 4u);
+                tma_box4(&S.hs_[slot], &tmH, i_seg, j_first, kfirst + 1 + d, 0, &S.hbar[slot]);
+            }
+            return;
+        }
         if (lane != 0) return;
         unsigned long long* bar = &S.hbar[slot];
         mbar_arrive_expect(bar, bytes_h);
         if (h_row) {
             const char* g = hin_b + (boff + soff) + (long long)(d - tcur) * p.b_sz;
-            bulk_g2s(&S.hs[slot][0][r][c_lo], g, nb_h, bar);
-            bulk_g2s(&S.hs[slot][1][r][c_lo], g + p.b_cs, nb_h, bar);
-            bulk_g2s(&S.hs[slot][2][r][c_lo], g + p.b_2cs, nb_h, bar);
+            bulk_g2s(&S.hs_[slot].v[0][r][c_lo], g, nb_h, bar);
+            bulk_g2s(&S.hs_[slot].v[1][r][c_lo], g + p.b_cs, nb_h, bar);
+            bulk_g2s(&S.hs_[slot].v[2][r][c_lo], g + p.b_2cs, nb_h, bar);
         }
     };
     // which whole-row PML slab row (j, k) lies in (-1: a plain row); warp-uniform
@@ -436,16 +465,16 @@ __global__ void __launch_bounds__(32 * (TY + 1), 16 / (TY + 1)) update_he6_kerne
         mbar_wait(&S.ebar[se1], (unsigned)((t + 1) / NS) & 1u);  // plane k+1 has landed (plane k was waited for one iteration ago)
         mbar_wait(&S.hbar[sh], (unsigned)(t >> 1) & 1u);
         float4 ax = zero4(), ay = zero4(), az = zero4(), bx = zero4(), by = zero4(), bz = zero4();
-        const float4 ex = S.es[se][0][r][lane], ey = S.es[se][1][r][lane], ez = S.es[se][2][r][lane];
+        const float4 ex = S.es_[se].v[0][r][lane], ey = S.es_[se].v[1][r][lane], ez = S.es_[se].v[2][r][lane];
         float ez_r = __shfl_down_sync(0xffffffffu, ez.x, 1);
         float ey_r = __shfl_down_sync(0xffffffffu, ey.x, 1);
-        if (lane == 31) { ez_r = S.es[se][2][r][32].x; ey_r = S.es[se][1][r][32].x; }
+        if (lane == 31) { ez_r = S.es_[se].v[2][r][32].x; ey_r = S.es_[se].v[1][r][32].x; }
         if (calc) {
-            hx = S.hs[sh][0][r][lane]; hy = S.hs[sh][1][r][lane]; hz = S.hs[sh][2][r][lane];
+            hx = S.hs_[sh].v[0][r][lane]; hy = S.hs_[sh].v[1][r][lane]; hz = S.hs_[sh].v[2][r][lane];
             row_coefs(S.ms[mb][r][0], S.ms[mb][r][1], xsh, p.ii, p.iv, p.xv_h,
                       boff >> 2, p.cs, i0, p.px, ax, ay, az, bx, by, bz);
-            const float4 ex1 = S.es[se1][0][r][lane], ey1 = S.es[se1][1][r][lane];
-            const float4 ex_jp = S.es[se][0][r + 1][lane], ez_jp = S.es[se][2][r + 1][lane];
+            const float4 ex1 = S.es_[se1].v[0][r][lane], ey1 = S.es_[se1].v[1][r][lane];
+            const float4 ex_jp = S.es_[se].v[0][r + 1][lane], ez_jp = S.es_[se].v[2][r + 1][lane];
             const float4 ez_ip = make_float4(ez.y, ez.z, ez.w, ez_r);
             const float4 ey_ip = make_float4(ey.y, ey.z, ey.w, ey_r);
             if (PML && pb >= 0) {

@@ -105,7 +105,7 @@ struct RowParams {
     const float* pxv; const unsigned char* pmeta;   // row compression of a/fo/fn (48-byte records per slab row) or NULL
     int y0, z0, by, bz;
     // narrow x-slabs (columns [0,xw0) and [xx1,xx1+xw1), multiples of 4): the plain launch (MODE 0) does not store
-    // these columns; a narrow launch (MODE 2, blockIdx.x = slab) owns them: a warp covers xs float4 columns of 32/xs
+    // these columns; a narrow launch (MODE 2, bix = slab) owns them: a warp covers xs float4 columns of 32/xs
     // rows and does the PML pre/update/post like the fused row launch
     float* xflux0; const float* xa0; const float* xfo0; const float* xfn0; int xw0, xs0;
     float* xflux1; const float* xa1; const float* xfo1; const float* xfn1; int xx1, xw1, xs1;
@@ -196,7 +196,7 @@ __device__ __forceinline__ float4 pcoef4(unsigned id, float sc, const float* ful
 //   y: ((Hx - Hx[k-1]) - Hz) + Hz[i-1]
 //   z: ((Hy - Hy[i-1]) - Hx) + Hx[j-1]
 template <int TY, int MODE, bool CMP>      // MODE 0 plain rows, 1 fused PML rows, 2 plain rows whose x-edge lanes are PML
-__global__ void __launch_bounds__(32 * TY, MODE ? (16 / TY > 0 ? 16 / TY : 1) : (24 / TY > 0 ? 24 / TY : 1)) update_e_kernel(const VolParams p, const RowParams r)
+__device__ __forceinline__ void update_e_body(const VolParams& p, const RowParams& r, const unsigned bix, const unsigned biy, const unsigned biz)
 {
     constexpr bool PML = MODE == 1;
     constexpr int KSTEP = 1;                                // the E march goes up in z
@@ -204,18 +204,18 @@ __global__ void __launch_bounds__(32 * TY, MODE ? (16 / TY > 0 ? 16 / TY : 1) : 
     int i0, j;
     bool act;
     // narrow-slab launch state (MODE 2)
-    const bool hi_slab = MODE == 2 && (blockIdx.x == 1 || r.xw0 == 0);
+    const bool hi_slab = MODE == 2 && (bix == 1 || r.xw0 == 0);
     const int xw = hi_slab ? r.xw1 : r.xw0, xx0 = hi_slab ? r.xx1 : 0;
     if (MODE == 2) {
         const int xs = hi_slab ? r.xs1 : r.xs0;             // float4 slots per row, 32/xs rows per warp (12 columns: 10 rows, 2 idle lanes)
         const int c4 = lane % xs, rw = lane / xs;
-        j = r.j0 + (blockIdx.y * TY + threadIdx.y) * (32 / xs) + rw;
+        j = r.j0 + (biy * TY + threadIdx.y) * (32 / xs) + rw;
         i0 = xx0 + c4 * 4;
         if (rw >= 32 / xs || j >= r.j1 || c4 * 4 >= xw) return;   // per lane (no warp collectives in this mode)
         act = true;
     } else {
-        i0 = (blockIdx.x * 32 + lane) * 4;
-        j = r.j0 + blockIdx.y * TY + threadIdx.y;
+        i0 = (bix * 32 + lane) * 4;
+        j = r.j0 + biy * TY + threadIdx.y;
         if (j >= r.j1) return;                              // warp-uniform
         if (MODE == 0) {
             if ((j >= r.sj0a && j < r.sj1a) || (j >= r.sj0b && j < r.sj1b)) return;
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(32 * TY, MODE ? (16 / TY > 0 ? 16 / TY : 1) : 
     }
     // plain launch: columns owned by a narrow-slab launch are computed but not stored
     const bool own = MODE != 0 || !(i0 < r.xw0 || (i0 >= r.xx1 && i0 < r.xx1 + r.xw1));
-    const int kbeg = p.k0 + blockIdx.z * p.kz;
+    const int kbeg = p.k0 + biz * p.kz;
     const int kend = min(kbeg + p.kz, p.k1);
     const long long cs = p.cs, sz = p.sz;
     const float* __restrict__ g = p.g;
@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(32 * TY, MODE ? (16 / TY > 0 ? 16 / TY : 1) : 
 //   y: ((Ex - Ex[k+1]) - Ez) + Ez[i+1]
 //   z: ((Ey - Ey[i+1]) - Ex) + Ex[j+1]
 template <int TY, int MODE, bool CMP>
-__global__ void __launch_bounds__(32 * TY, MODE ? (16 / TY > 0 ? 16 / TY : 1) : (24 / TY > 0 ? 24 / TY : 1)) update_h_kernel(const VolParams p, const RowParams r)
+__device__ __forceinline__ void update_h_body(const VolParams& p, const RowParams& r, const unsigned bix, const unsigned biy, const unsigned biz)
 {
     constexpr bool PML = MODE == 1;
     constexpr int KSTEP = -1;                               // the H march goes down in z
@@ -326,18 +326,18 @@ __global__ void __launch_bounds__(32 * TY, MODE ? (16 / TY > 0 ? 16 / TY : 1) : 
     int i0, j;
     bool act;
     // narrow-slab launch state (MODE 2)
-    const bool hi_slab = MODE == 2 && (blockIdx.x == 1 || r.xw0 == 0);
+    const bool hi_slab = MODE == 2 && (bix == 1 || r.xw0 == 0);
     const int xw = hi_slab ? r.xw1 : r.xw0, xx0 = hi_slab ? r.xx1 : 0;
     if (MODE == 2) {
         const int xs = hi_slab ? r.xs1 : r.xs0;             // float4 slots per row, 32/xs rows per warp (12 columns: 10 rows, 2 idle lanes)
         const int c4 = lane % xs, rw = lane / xs;
-        j = r.j0 + (blockIdx.y * TY + threadIdx.y) * (32 / xs) + rw;
+        j = r.j0 + (biy * TY + threadIdx.y) * (32 / xs) + rw;
         i0 = xx0 + c4 * 4;
         if (rw >= 32 / xs || j >= r.j1 || c4 * 4 >= xw) return;   // per lane (no warp collectives in this mode)
         act = true;
     } else {
-        i0 = (blockIdx.x * 32 + lane) * 4;
-        j = r.j0 + blockIdx.y * TY + threadIdx.y;
+        i0 = (bix * 32 + lane) * 4;
+        j = r.j0 + biy * TY + threadIdx.y;
         if (j >= r.j1) return;                              // warp-uniform
         if (MODE == 0) {
             if ((j >= r.sj0a && j < r.sj1a) || (j >= r.sj0b && j < r.sj1b)) return;
@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(32 * TY, MODE ? (16 / TY > 0 ? 16 / TY : 1) : 
     }
     // plain launch: columns owned by a narrow-slab launch are computed but not stored
     const bool own = MODE != 0 || !(i0 < r.xw0 || (i0 >= r.xx1 && i0 < r.xx1 + r.xw1));
-    const int kbeg = p.k0 + blockIdx.z * p.kz;
+    const int kbeg = p.k0 + biz * p.kz;
     const int kend = min(kbeg + p.kz, p.k1);
     const long long cs = p.cs, sz = p.sz;
     const float* __restrict__ g = p.g;
@@ -435,4 +435,35 @@ __global__ void __launch_bounds__(32 * TY, MODE ? (16 / TY > 0 ? 16 / TY : 1) : 
     }
 }
 
+template <int TY, int MODE, bool CMP>
+__global__ void __launch_bounds__(32 * TY, MODE ? (16 / TY > 0 ? 16 / TY : 1) : (24 / TY > 0 ? 24 / TY : 1)) update_e_kernel(const VolParams p, const RowParams r)
+{
+    update_e_body<TY, MODE, CMP>(p, r, blockIdx.x, blockIdx.y, blockIdx.z);
+}
+template <int TY, int MODE, bool CMP>
+__global__ void __launch_bounds__(32 * TY, MODE ? (16 / TY > 0 ? 16 / TY : 1) : (24 / TY > 0 ? 24 / TY : 1)) update_h_kernel(const VolParams p, const RowParams r)
+{
+    update_h_body<TY, MODE, CMP>(p, r, blockIdx.x, blockIdx.y, blockIdx.z);
+}
 
+// All PML slab launches of one half step in ONE launch: the CTAs of up to six slabs (two z-slabs, two y-slabs, the narrow
+// x-slab pair) are numbered consecutively; a CTA finds its slab and runs that slab's update exactly as its own launch
+// would.  One grid that fills the machine instead of five small ones on five streams, and 2 instead of 10 slab launches
+// per step (what matters most on small grids, where a step is launch-bound).
+struct SlabEntry { RowParams r; int mode; int gx, gy, gz; int kz, k0, k1; int cta0; };
+#define MAX_SLABS 6
+struct SlabSet { int n; SlabEntry e[MAX_SLABS]; };
+template <int WHICH, int TY, bool CMP>
+__global__ void __launch_bounds__(32 * TY, (16 / TY > 0 ? 16 / TY : 1)) update_slabs_kernel(const VolParams p0, const __grid_constant__ SlabSet T)
+{
+    int q = 0;
+#pragma unroll
+    for (int u = 1; u < MAX_SLABS; ++u) if (u < T.n && (int)blockIdx.x >= T.e[u].cta0) q = u;
+    const SlabEntry& E = T.e[q];
+    const unsigned local = blockIdx.x - E.cta0;
+    const unsigned bix = local % E.gx, biy = (local / E.gx) % E.gy, biz = local / (E.gx * E.gy);
+    VolParams p = p0;
+    p.kz = E.kz; p.k0 = E.k0; p.k1 = E.k1;
+    if (E.mode == 1) { if (WHICH == 0) update_e_body<TY, 1, CMP>(p, E.r, bix, biy, biz); else update_h_body<TY, 1, CMP>(p, E.r, bix, biy, biz); }
+    else             { if (WHICH == 0) update_e_body<TY, 2, CMP>(p, E.r, bix, biy, biz); else update_h_body<TY, 2, CMP>(p, E.r, bix, biy, biz); }
+}
