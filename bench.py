@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-seeded", action="store_true", help="skip the seeded per-cell-coefficient record (N = 1)")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling record (1024^3 Mur cube)")
+    ap.add_argument("--no-latency", action="store_true", help="skip the small-scene end-to-end record (N = 1)")
     ap.add_argument("--no-config3", action="store_true", help="skip the 4x4 array record (N > 1)")
     ap.add_argument("--strong-n", type=int, default=1024, help="edge of the strong-scaling cube")
     ap.add_argument("--config3-cells", type=float, default=1.0e9, help="total cells of the 4x4 array mesh")
@@ -353,6 +354,47 @@ def seeded_record(R, K, W, peak, peak_src):
     return rec
 
 
+def latency_record(args, local):
+    """BASELINE.json configs[0] end to end through the public API: the reference's own single-patch scene (recorded call trace
+    of the unmodified prepare, GUI defaults: PML_8, mesh quality 3, NrTS 30000, EndCriteria 1e-4, ~0.3 M cells), FDTD.Run to
+    its end criterion + CalcPort + the reference's 73-call CalcNF2FF loop; timed on the second run of the process (the first
+    one pays CUDA context creation and module loading), next to the CPU engine on all host cores"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import replay
+    import scenes as tscenes
+    out = {"workload": "patch_q3", "scene": "reference single-patch scene, unmodified prepare (trace_single_pml8_q3): PML_8, NrTS 30000, EndCriteria 1e-4"}
+
+    def once(tag):
+        R = replay.replay("trace_single_pml8_q3")
+        F, nf = R["FDTD"], R["nf"]
+        F.device = local
+        path = os.path.join("/tmp", f"b200fdtd_lat_{tag}_{os.getpid()}")
+        t0 = time.perf_counter()
+        F.Run(path, cleanup=True, verbose=0)
+        t_run = time.perf_counter() - t0
+        f = np.linspace(max(1e9, 0.7 * F.exc[1]), 1.3 * F.exc[1], 201)
+        F.ports[0].CalcPort(path, f)
+        dbi, dmax = replay.reference_postprocess(nf, path, F.exc[1], R["theta"], R["phi"], R["nf_center"])
+        t_all = time.perf_counter() - t0
+        sim = F.sim
+        return dict(run_s=round(t_run, 4), total_s=round(t_all, 4), prepare_s=round(sim.prepare_s, 4), step_loop_s=round(sim.wall_s, 4),
+                    timesteps=sim.timesteps, stop=sim.stop_reason, cells=sim.cells, us_per_step=round(1e6 * sim.wall_s / sim.timesteps, 2),
+                    mcells_per_s=round(sim.cells * sim.timesteps / sim.wall_s / 1e6, 1), dmax_dbi=round(float(10 * np.log10(dmax)), 4))
+    tscenes.use_cuda_engine()
+    out["cold"] = once("cold")
+    out["warm"] = once("warm")
+    if not args.no_cpu_baseline:
+        tscenes.use_oracle_engine(threads=os.cpu_count() or 4)
+        try:
+            out["cpu"] = once("cpu")
+            out["cpu"]["cores"] = os.cpu_count()
+            out["speedup_total_warm"] = round(out["cpu"]["total_s"] / out["warm"]["total_s"], 2)
+            out["speedup_run_warm"] = round(out["cpu"]["run_s"] / out["warm"]["run_s"], 2)
+        finally:
+            tscenes.use_cuda_engine()
+    return out
+
+
 def sub_workload(kind, args, local, world, K, W, peak, peak_src):
     """further records of the same line: 'strong' = BASELINE configs[4] 1024^3 vacuum cube with Mur, total size fixed as N grows;
     'config3' = BASELINE configs[2] 4x4 array at ~1 B cells over N GPUs"""
@@ -493,7 +535,7 @@ def run_b200(args):
 
     line = None
     if rank == 0:
-        kname_f = "update_he_kernel fused H->E launch over the plain region (one launch = both passes)"
+        kname_f = "update_he6_kernel<7> fused H->E launch over the plain region (one launch = both passes)"
         kname_s = "update_e_kernel<4,0,1>/update_h_kernel<4,0,1> plain launch (mean of both passes)"
         roof = roofline_record(fused_he, kms, plain_cells, peak, peak_src, kname_f, kname_s,
                                ("dram_bytes_per_cell_fused_launch", "dram_bytes_per_cell_pass"))
@@ -534,6 +576,14 @@ def run_b200(args):
     import gc
     gc.collect()
     torch.cuda.empty_cache()
+    # ---- latency regime, N = 1: the reference's own ~0.3 M-cell scene end to end ----
+    if world == 1 and not args.no_latency and args.workload == "patch100m":
+        try:
+            rec = latency_record(args, local)
+        except Exception as e:
+            rec = {"failed": repr(e)}
+        if line is not None:
+            line["latency"] = rec
     # ---- strong-scaling record (every N, so the driver's N = 1, 2, 4, 8 lines carry the series) and config 3 (N > 1) ----
     for kind, on in (("strong", not args.no_strong), ("config3", world > 1 and not args.no_config3)):
         if not on or args.workload != "patch100m":

@@ -254,11 +254,11 @@ __global__ void __launch_bounds__(256) energy_partial_kernel(const float* __rest
 }
 __global__ void energy_final_kernel(const double* __restrict__ partials, int n, double* __restrict__ out)
 {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        double a = 0, b = 0;
-        for (int i = 0; i < n; ++i) { a += partials[2 * i]; b += partials[2 * i + 1]; }
-        out[0] = a; out[1] = b;
-    }
+    // one warp, fixed order: lane l adds partials l, l+32, ...; then a shuffle tree (deterministic)
+    double a = 0, b = 0;
+    for (int i = threadIdx.x; i < n; i += 32) { a += partials[2 * i]; b += partials[2 * i + 1]; }
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_down_sync(0xffffffffu, a, o); b += __shfl_down_sync(0xffffffffu, b, o); }
+    if (threadIdx.x == 0) { out[0] = a; out[1] = b; }
 }
 
 // K11 far field: N = sum J e^{jk r^.r'}, L = sum M e^{jk r^.r'} projected on theta^/phi^ (App. A6)

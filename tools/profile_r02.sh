@@ -24,3 +24,7 @@ for R in he6 he_seeded he6_cube; do
   ncu -i gpurun_out/prof_${TAG}_$R.ncu-rep --page raw --csv > gpurun_out/ncu_raw_${TAG}_$R.csv 2>/dev/null
 done
 ls -la gpurun_out | grep -E "${TAG}.*(ncu-rep|csv)"
+# one merged slab launch of each pass
+timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:update_slabs_kernel -c 2 -f \
+    -o gpurun_out/prof_${TAG}_slabs python tools/prof_step.py --workload patch100m > gpurun_out/ncu_${TAG}_slabs.log 2>&1
+ncu -i gpurun_out/prof_${TAG}_slabs.ncu-rep --page raw --csv > gpurun_out/ncu_raw_${TAG}_slabs.csv 2>/dev/null
