@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--no-latency", action="store_true", help="skip the small-scene end-to-end record (N = 1)")
     ap.add_argument("--no-config3", action="store_true", help="skip the 4x4 array record (N > 1)")
     ap.add_argument("--strong-n", type=int, default=1024, help="edge of the strong-scaling cube")
+    ap.add_argument("--strong-nz", type=int, default=0, help="experiment: z extent of the strong-scaling grid (0 = cube)")
     ap.add_argument("--config3-cells", type=float, default=1.0e9, help="total cells of the 4x4 array mesh")
     ap.add_argument("--kz", type=int, default=0, help="tuning experiment: planes marched per CTA")
     ap.add_argument("--ty", type=int, default=0, help="tuning experiment: rows per CTA")
@@ -264,7 +265,9 @@ class Runner:
         self.barrier()
         E._pre()
         ev0.record(E.stream)
+        t_h = time.perf_counter()
         self.step(K)
+        host_ms = 1e3 * (time.perf_counter() - t_h)      # time the host needed to enqueue the K steps (not a GPU time)
         ev1.record(E.stream)
         self.barrier()
         ms = ev0.elapsed_time(ev1)
@@ -278,7 +281,7 @@ class Runner:
             torch.distributed.all_reduce(t)
             ms, launches = float(m[0].item()), int(t[1].item())
         return ms, int(launches), dict(start_ts=int(ts0), sampling_launch_sets=int(samplings), graph_replayed_steps=int(graph_steps),
-                                       eager_steps=int(K - graph_steps))
+                                       eager_steps=int(K - graph_steps), host_enqueue_ms_per_step=round(host_ms / K, 4))
 
     def kernel_times(self, reps=10):
         """the dominant kernel alone, same data, same stream: the fused H->E launch if the run used it, else the plain E and H launches"""
@@ -404,7 +407,7 @@ def sub_workload(kind, args, local, world, K, W, peak, peak_src):
     t0 = time.time()
     if kind == "strong":
         from b200fdtd import scenes
-        F = scenes.vacuum_cube(args.strong_n, nrts=10 ** 6)
+        F = scenes.vacuum_cube(args.strong_n, nrts=10 ** 6, nz=args.strong_nz or None)
         desc = f"uniform vacuum cube {args.strong_n}^3, Mur on 6 faces, centre soft source, one V probe (config 5); total size fixed (strong scaling)"
         extra = {}
     else:

@@ -411,20 +411,27 @@ class Simulation:
         return self._copies_v[self._vcur], self._copies_c[self._ccur]
 
     def _exchange_async(self, f, direction, ncomp):
-        """direction +1: my top owned plane -> upper neighbour's lower ghost; -1: my plane 0 -> lower neighbour's upper ghost"""
+        """direction +1: my top owned plane -> upper neighbour's lower ghost; -1: my plane 0 -> lower neighbour's upper ghost.
+        The P2P op lists (plane views of a given array) are built once and reused: at ~1 ms of GPU work per step the host
+        side of the exchange is on the critical path."""
         dist = torch.distributed
-        ops = []
-        up, dn = self.rank + 1, self.rank - 1
-        if direction > 0:
-            if up < self.world:
-                ops += [dist.P2POp(dist.isend, f[c, self.nz], up, self.group) for c in range(ncomp)]
-            if dn >= 0:
-                ops += [dist.P2POp(dist.irecv, f[c, 0], dn, self.group) for c in range(ncomp)]
-        else:
-            if dn >= 0:
-                ops += [dist.P2POp(dist.isend, f[c, 1], dn, self.group) for c in range(ncomp)]
-            if up < self.world:
-                ops += [dist.P2POp(dist.irecv, f[c, self.nz + 1], up, self.group) for c in range(ncomp)]
+        cache = self.__dict__.setdefault("_p2p_cache", {})
+        key = (f.data_ptr(), direction, ncomp)
+        ops = cache.get(key)
+        if ops is None:
+            ops = []
+            up, dn = self.rank + 1, self.rank - 1
+            if direction > 0:
+                if up < self.world:
+                    ops += [dist.P2POp(dist.isend, f[c, self.nz], up, self.group) for c in range(ncomp)]
+                if dn >= 0:
+                    ops += [dist.P2POp(dist.irecv, f[c, 0], dn, self.group) for c in range(ncomp)]
+            else:
+                if dn >= 0:
+                    ops += [dist.P2POp(dist.isend, f[c, 1], dn, self.group) for c in range(ncomp)]
+                if up < self.world:
+                    ops += [dist.P2POp(dist.irecv, f[c, self.nz + 1], up, self.group) for c in range(ncomp)]
+            cache[key] = ops
         return dist.batch_isend_irecv(ops) if ops else []
 
     @staticmethod
@@ -463,7 +470,22 @@ class Simulation:
         self._vcur ^= 1
         self._pend_e = self._exchange_async(self._cur()[0], -1, 2)
 
+    def _sample_multi(self, pipelined):
+        """probe / NF2FF sampling of a z-slab rank at a sampling step.  pipelined: between two fused steps the E update of the
+        next step is already done; the sample takes E from the copy that fused launch only read (csrc: launch_sampling)."""
+        E = self.engine
+        self._wait(self._pend_h); self._pend_h = []
+        if self.faces:                               # NF2FF node interpolation reads E of plane K0-1 too
+            ev = self._copies_v[self._vcur ^ 1] if pipelined else self._cur()[0]
+            if pipelined:                            # (the E exchange of the running step must not be reordered around it)
+                self._wait(self._pend_e); self._pend_e = []
+            self._wait(self._exchange_async(ev, +1, 3))
+        E.half_step_raw(3 if pipelined else 2)
+
     def _step_multi(self, n):
+        """n steps of a z-slab rank.  With the fused steps the whole call is one span E(0) | H(0)+E(1) | ... | H(n-1) (an even
+        number of fused steps, so the state ends in the bound arrays), sampling points inside it are served in the pipelined
+        state; without them: E and H half steps with one exchange each."""
         import contextlib
         E = self.engine
         self._views()
@@ -473,36 +495,28 @@ class Simulation:
             E._pre()
         ctx = torch.cuda.stream(E.stream) if self._gpu else contextlib.nullcontext()
         sampling = bool(self.faces) or bool(self.probe_names)
+        iv = self.interval
         with ctx:
-            left = n
-            while left > 0:
-                span = left
-                if sampling:
-                    span = min(span, self.interval - (E.ts % self.interval))
-                # E(0) | H(0)+E(1) | ... | H(span-2)+E(span-1) | H(span-1)
+            fused = (n - 2 if (n - 1) & 1 else n - 1) if self._fused else 0
+            done = 0
+            while done < n:
                 self._e_half()
-                for _ in range(span - 1):
-                    if self._fused:
+                if done == 0:
+                    for _ in range(fused):
                         self._fused_step()
-                    else:
-                        self._h_half(); self._e_half()
+                        if sampling and (E.ts % iv) == 0:
+                            self._sample_multi(True)
+                    done += fused
                 self._h_half()
-                left -= span
-                if sampling and (E.ts % self.interval) == 0:
-                    self._wait(self._pend_h); self._pend_h = []
-                    if self.faces:                           # NF2FF node interpolation reads E of plane K0-1 too
-                        self._wait(self._exchange_async(self._cur()[0], +1, 3))
-                    E.half_step_raw(2)
+                done += 1
+                if sampling and (E.ts % iv) == 0:
+                    self._sample_multi(False)
             self._wait(self._pend_h); self._pend_h = []
             self._wait(self._pend_e); self._pend_e = []
             if self._fused and (self._vcur or self._ccur):
-                # hand the state back in the bound arrays (the caller, tests and collect() look at those)
-                if self._vcur:
-                    self._copies_v[0].copy_(self._copies_v[1])
-                if self._ccur:
-                    self._copies_c[0].copy_(self._copies_c[1])
-                self._vcur = self._ccur = 0
-                E.reset_current_copy()
+                raise RuntimeError("fused z-slab steps did not return to the bound field arrays")
+            if self._fused:
+                E.reset_current_copy()               # (the library's PML flux copy goes back to the caller's arrays too)
         if self._gpu:
             torch.cuda.current_stream(E.device).wait_stream(E.stream)
 

@@ -76,7 +76,9 @@ int b200fdtd_expand_rows(b200fdtd_ctx* ctx, int which, int nvec, const float* xv
  * bit 20 = high-end H / low-end E slab launches beside the fused launch instead of before / after it,
  * bit 23 = whole-row PML slabs inside the fused H->E launch (double-buffered current flux; bit-exact, measured slower than
  * their own launches on B200, hence off by default), bit 22 = never (overrides bit 23),
- * bit 24 = Mur edges by index lists even where they form long arithmetic runs */
+ * bit 24 = Mur edges by index lists even where they form long arithmetic runs, bit 25 = per-row 1-D TMA copies instead of
+ * tiled copies in the fused launch, bit 26 = one launch per PML slab instead of one for all, bit 27 = one fused span per
+ * sampling interval instead of one per b200fdtd_run call */
 int b200fdtd_set_tuning(b200fdtd_ctx* ctx, int kz, int ty, int variant);
 
 /* ---- excitation (openEMS Engine_Ext_Excitation::Apply2Voltages; AddLumpedPort's
@@ -166,7 +168,10 @@ int b200fdtd_run(b200fdtd_ctx* ctx, int64_t nsteps, int use_graph);
  *   phase 0: everything up to and including Apply2Voltages (E half step)
  *   phase 1: current half step; increments the step counter
  *   phase 2: probe / NF2FF sampling if the new step count is a multiple of the interval
- *            (after the H halo so slab-boundary nodes see their neighbour's new values) */
+ *            (after the H halo so slab-boundary nodes see their neighbour's new values)
+ *   phase 3: the same between two fused steps (b200fdtd_fused_step_part), where the E update of the next step has
+ *            already been done: the voltages are taken from the field copy that is NOT current (the fused launch only
+ *            read it), the currents from the current one */
 int b200fdtd_half_step(b200fdtd_ctx* ctx, int phase);
 /* the same half steps cut in two so the halo exchange hides behind the interior launch:
  *   phase 0: part 0 = pre passes + planes [1,nz),   part 1 = plane 0 (reads the lower ghost H) + post passes

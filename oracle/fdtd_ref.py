@@ -263,6 +263,21 @@ class RefEngine:
         self._store_current()
 
     def half_step_raw(self, phase):
+        if phase == 3:
+            # sampling between two fused steps: H from the current copy, E from the copy that is NOT current (it still holds
+            # the voltages of the step being sampled, with the ghost planes the caller has exchanged into it)
+            if getattr(self, "volt2", None) is None:
+                raise RuntimeError("pipelined sampling needs the second field copy")
+            if self._ccur:
+                self.curr[...] = self.curr2
+            keep = self.volt.copy()
+            if self._vcur == 0:
+                self.volt[...] = self.volt2          # old copy = copy 1
+            lib().ref_half_step(C.byref(self.e), 2)
+            self.volt[...] = keep
+            if self._ccur:
+                self.curr[:, 1:self.nz + 1] = np.nan
+            return
         self._load_current()
         self.half_step(phase)
         self._store_current()
@@ -324,14 +339,17 @@ class RefEngine:
         elif part == 3:                                 # E: needs the new H with its freshly received lower ghost plane
             if self._ccur:
                 self.curr[...] = self.curr2             # owned planes parked in part 1 + ghost plane 0 received since
+            if self._vcur:
+                self.volt[...] = self.volt2             # the current E (copy 1) into the engine array, ghost planes included
+            old = self.volt[:, o].copy()                # the fused launch only reads the old E: its copy keeps holding it
             lib().ref_half_step_part(C.byref(self.e), 0, 0)
             lib().ref_half_step_part(C.byref(self.e), 0, 1)
             if self._ccur:
                 self.curr[:, o] = np.nan                # H was only read: copy 1 still holds it
-            if self._vcur == 0:                         # the new E belongs in copy 1
-                self.volt2[:, o] = self.volt[:, o]; self.volt[:, o] = np.nan
-            else:                                       # it belongs in copy 0 (the engine array)
-                self.volt2[:, o] = np.nan
+            if self._vcur == 0:                         # the new E belongs in copy 1, copy 0 keeps the old one
+                self.volt2[:, o] = self.volt[:, o]; self.volt[:, o] = old
+            else:                                       # it belongs in copy 0 (the engine array), copy 1 keeps the old one
+                self.volt2[:, o] = old
             self._vcur ^= 1
         else:
             raise ValueError("part must be 0..4")
