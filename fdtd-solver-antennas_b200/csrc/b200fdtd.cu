@@ -139,7 +139,7 @@ struct b200fdtd_ctx {
     // graph
     cudaGraphExec_t graph = nullptr; int graph_steps = 0; int64_t graph_kernels = 0;
     // pipelined stepping (run_pipelined): one graph of `pgraph_steps` fused steps per parity of the field copies at its entry
-    cudaGraphExec_t pgraph[2] = {nullptr, nullptr}; int pgraph_steps = 0; int64_t pgraph_kernels[2] = {0, 0};
+    cudaGraphExec_t pgraph[4] = {nullptr, nullptr, nullptr, nullptr}; int pgraph_steps = 0; int64_t pgraph_kernels[4] = {0, 0, 0, 0};
     bool he_fused = false;                 // the last b200fdtd_run used fused H->E launches
     bool graph_fused = false;              // ... and so does the captured chunk
     // device copies of the slab / face tables
@@ -702,7 +702,7 @@ static int upload(T** dst, const T* src, int64_t n, cudaStream_t s)
 static void drop_graph(b200fdtd_ctx* c)
 {
     if (c->graph) { cudaGraphExecDestroy(c->graph); c->graph = nullptr; c->graph_steps = 0; }
-    for (int q = 0; q < 2; ++q) if (c->pgraph[q]) { cudaGraphExecDestroy(c->pgraph[q]); c->pgraph[q] = nullptr; }
+    for (int q = 0; q < 4; ++q) if (c->pgraph[q]) { cudaGraphExecDestroy(c->pgraph[q]); c->pgraph[q] = nullptr; }
     c->pgraph_steps = 0;
 }
 
@@ -1443,7 +1443,8 @@ static int build_graph(b200fdtd_ctx* c, int steps)
 // half steps are paid once per call (~1 % of a run), not once per sampling interval (4 steps on the 10 GHz vacuum cube,
 // 13 on the reference scene).  Whole sampling intervals are replayed from a CUDA graph of g fused steps (g = interval, or
 // twice that if it is odd: the field copies swap roles every step, so a graph must span an even number; one graph per
-// parity of the copies at its entry).  The number of fused steps of a call is even, so the state ends in the bound arrays.
+// state of the copies at its entry).  When the number of fused steps of a call is odd, the two unfused half steps at its
+// ends write the other copy as well, so the state always ends in the bound arrays.
 static int build_pgraph(b200fdtd_ctx* c, int g, int iv, int parity)
 {
     cudaGraph_t gr = nullptr;
@@ -1473,18 +1474,19 @@ static int run_pipelined(b200fdtd_ctx* c, int64_t n, bool use_graph)
     const int iv = sample_interval(c);
     const int64_t T0 = c->ts;
     int64_t dts = T0;                                        // value of the device step counter
-    const int64_t F = ((n - 1) & 1) ? n - 2 : n - 1;         // fused steps: an even number
+    const int64_t F = n - 1;                                 // fused steps
+    const bool odd = (F & 1) != 0;
     int g = 0;                                               // graph chunk (fused steps), 0 = no graph
     if (use_graph && c->stream != nullptr && iv <= 4096) { g = iv > 0 ? iv : 16; if (g & 1) g *= 2; }
-    if (g != c->pgraph_steps) { for (int q = 0; q < 2; ++q) if (c->pgraph[q]) { cudaGraphExecDestroy(c->pgraph[q]); c->pgraph[q] = nullptr; } c->pgraph_steps = g; }
+    if (g != c->pgraph_steps) { for (int q = 0; q < 4; ++q) if (c->pgraph[q]) { cudaGraphExecDestroy(c->pgraph[q]); c->pgraph[q] = nullptr; } c->pgraph_steps = g; }
     c->he_fused = F > 0;
     if (sync_alt_ghosts(c)) return 1;
-    c->vcur = c->ccur = 0; c->flip = false;
-    if (e_half(c, 0)) return 1;                              // E(T0): into the pipelined state
+    c->vcur = c->ccur = 0;
+    c->flip = odd; { const int rc = e_half(c, 0); c->flip = false; if (rc) return 1; }     // E(T0): into the pipelined state
     int64_t q = 0;
     while (q < F) {
         if (g > 0 && ((T0 + q) % g) == 0 && F - q >= g) {
-            const int par = c->vcur;
+            const int par = 2 * c->vcur + c->ccur;
             if (dts != T0 + q) { if (launch_ts_add(c, (int)(T0 + q - dts))) return 1; dts = T0 + q; }
             if (!c->pgraph[par]) if (build_pgraph(c, g, iv, par)) return 1;
             CK(cudaGraphLaunch(c->pgraph[par], c->stream));
@@ -1496,16 +1498,9 @@ static int run_pipelined(b200fdtd_ctx* c, int64_t n, bool use_graph)
         ++q;
         if (iv > 0 && ((T0 + q) % iv) == 0) if (launch_sampling(c, (int)(T0 + q - dts), true)) return 1;
     }
+    c->flip = odd; { const int rc = h_half(c); c->flip = false; if (rc) return 1; }          // H(T0+F): out of the pipelined state
     if (c->vcur || c->ccur) return fail("pipelined run did not return to the bound field arrays");
-    if (h_half(c)) return 1;                                 // H(T0+F): out of the pipelined state
-    int64_t done = F + 1;
-    if (iv > 0 && ((T0 + done) % iv) == 0) if (launch_sampling(c, (int)(T0 + done - dts))) return 1;
-    while (done < n) {                                       // (at most one more step, when n-1 is odd)
-        if (e_half(c, (int)(T0 + done - dts))) return 1;
-        if (h_half(c)) return 1;
-        ++done;
-        if (iv > 0 && ((T0 + done) % iv) == 0) if (launch_sampling(c, (int)(T0 + done - dts))) return 1;
-    }
+    if (iv > 0 && ((T0 + n) % iv) == 0) if (launch_sampling(c, (int)(T0 + n - dts))) return 1;
     if (normalize_flux(c)) return 1;
     if (T0 + n != dts) if (launch_ts_add(c, (int)(T0 + n - dts))) return 1;
     c->ts = T0 + n;
