@@ -464,8 +464,12 @@ class OperatorBuilder:
         The stretching of a coordinate is a property of the coordinate, not of the material it runs through: with the
         local phase velocity instead of c0 the stretch factor jumps at a material interface that enters the PML (a
         substrate under a microstrip line) and the layer goes unstable (tests/test_oracle_physics.py::
-        test_microstrip_line_impedance_and_effective_permittivity blows up within 4000 steps).  In vacuum, i.e. in every
-        reference scene (substrate and ground plane end inside the domain), both choices are the same number.
+        test_microstrip_line_impedance_and_effective_permittivity blows up within 4000 steps).  In a vacuum-filled PML both
+        choices are the same number: that is the case in the live reference scenes (…microstrip_3d.py, …multi_3d.py,
+        …fixed.py: substrate and ground plane end inside the domain).  It is NOT the case in the legacy backend
+        (solver_fdtd_openems.py:209-217: substrate and ground plane span the whole SimBox into PML_8); there openEMS would
+        use kappa/eps_eff of the material inside the layer, so agreement with openEMS for that backend is not exact and
+        rests on this project's own oracle, which shares this formulation.
         B200FDTD_PML_LOCAL_C=1 restores the material-dependent rates for comparison."""
         eps = ec["epsE"][comp] if field_kind == 0 else ec["epsH"][comp]
         c_loc = C0 / torch.sqrt(eps) if os.environ.get("B200FDTD_PML_LOCAL_C") else torch.full_like(eps, C0)

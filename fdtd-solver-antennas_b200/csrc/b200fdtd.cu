@@ -235,7 +235,16 @@ static int build_plan(b200fdtd_ctx* c)
             if (B.z0 == 0 && B.bz < c->nz && B.bz > zlo) { kind[b] = 1; }
             else if (B.z0 + B.bz == c->nz && B.z0 > 0) { kind[b] = 1; }
             else if (B.z0 == 0 && B.bz == c->nz) { kind[b] = 1; }      // the whole slab is PML
-        } else kind[b] = 2;
+        } else if (B.y0 == 0 || B.y0 + B.by == c->ny) kind[b] = 2;     // y-slabs sit at the low or the high end of y
+    }
+    {   // at most four whole-row slabs are folded into the volume launches (two z, two y): decided BEFORE their rows and
+        // planes are carved out of the plain launch, so a slab beyond that keeps the separate pre/post passes over cells
+        // the plain launch still updates
+        int nlo = 0, nhi = 0;                                // one z-slab per end; the y-slabs are limited to two below
+        for (int b = 0; b < A.n; ++b) if (kind[b] == 1) {
+            const bool lo = A.b[b].z0 == 0;
+            if ((lo ? nlo++ : nhi++) > 0) kind[b] = 0;
+        }
     }
     for (int b = 0; b < A.n; ++b) if (kind[b] == 1) {
         const PmlBoxDev& B = A.b[b];
@@ -1057,6 +1066,12 @@ extern "C" int b200fdtd_set_pml(b200fdtd_ctx* c, int nboxes, const b200fdtd_pml_
             B.x0 + B.bx > c->px || B.y0 + B.by > c->ny || B.z0 + B.bz > c->nz)
             return fail("PML box %d outside the grid", b);
         if (!B.flux_v || !B.flux_i || !B.vv || !B.vvfo || !B.vvfn || !B.ii || !B.iifo || !B.iifn) return fail("PML box %d has NULL arrays", b);
+        for (int q = 0; q < b; ++q) {
+            const b200fdtd_pml_box& O = boxes[q];
+            const bool apart = B.x0 >= O.x0 + O.bx || O.x0 >= B.x0 + B.bx || B.y0 >= O.y0 + O.by || O.y0 >= B.y0 + B.by ||
+                               B.z0 >= O.z0 + O.bz || O.z0 >= B.z0 + B.bz;
+            if (!apart) return fail("PML boxes %d and %d overlap (every cell belongs to at most one box)", q, b);
+        }
         PmlBoxDev& D = t.b[b];
         D.x0 = B.x0; D.y0 = B.y0; D.z0 = B.z0; D.bx = B.bx; D.by = B.by; D.bz = B.bz; D.start = start;
         D.flux_v = B.flux_v; D.flux_i = B.flux_i; D.vv = B.vv; D.vvfo = B.vvfo; D.vvfn = B.vvfn; D.ii = B.ii; D.iifo = B.iifo; D.iifn = B.iifn;

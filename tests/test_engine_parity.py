@@ -245,3 +245,40 @@ def test_fused_step_parts_of_a_z_slab_rank(layout, shape):
     R.run(n)
     assert G.ts == n
     _assert_fields_equal(R, G, f"{n} steps through the fused step parts")
+
+
+def test_overlapping_pml_boxes_are_rejected():
+    """every cell belongs to at most one PML box: the C-ABI refuses overlapping boxes instead of updating cells twice"""
+    from b200fdtd.engine import Engine
+    from b200fdtd import B200FDTDError
+    P = synth.make_problem(37, 29, 23, 40, seed=3, fused_pml=True)
+    G = Engine(P["nx"], P["ny"], P["nz"], P["px"])
+    G.set_coeffs(P["vv"], P["vi"], P["ii"], P["iv"])
+    boxes = [dict(b) for b in P["pml"]]
+    boxes.append(dict(boxes[0]))                  # the first box once more
+    with pytest.raises(B200FDTDError):
+        G.set_pml(boxes)
+
+
+def test_operator_built_on_the_gpu_equals_the_cpu_build():
+    """the operator build runs as torch tensor code on the GPU for large slabs; the arrays it produces
+    (coefficients, row-compression tables, PML slab coefficients) must be the ones the CPU build produces"""
+    import torch
+    import replay
+    from b200fdtd.operator import OperatorBuilder
+    F = replay.replay("trace_multi2_mur_q2")["FDTD"]          # rotated / translated boxes, thick copper, two ports
+    S = F._setup()
+    out = {}
+    for dev in ("cpu", "cuda"):
+        B = OperatorBuilder(S, device=torch.device(dev))
+        dt = B.estimate_timestep()
+        px = (B.n[0] + 31) // 32 * 32
+        co = [t.cpu() for t in B.coefficients(0, B.n[2], px, dt)]
+        tabs = [(None if xv is None else xv.cpu(), None if meta is None else meta.cpu()) for xv, meta in (B.row_compression[0], B.row_compression[1])]
+        out[dev] = (dt, co, tabs)
+    assert out["cpu"][0] == out["cuda"][0], "time step differs"
+    for name, a, b in zip(("vv", "vi", "ii", "iv"), out["cpu"][1], out["cuda"][1]):
+        diff = int((a.view(torch.int32) != b.view(torch.int32)).sum())
+        assert diff == 0, f"{name}: {diff} coefficients differ between the GPU and the CPU build"
+    for (xa, ma), (xb, mb) in zip(out["cpu"][2], out["cuda"][2]):
+        assert torch.equal(xa, xb) and torch.equal(ma, mb)
