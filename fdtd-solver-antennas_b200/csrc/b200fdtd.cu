@@ -604,10 +604,9 @@ static int launch_he(b200fdtd_ctx* c, cudaStream_t stream, int zc0 = -1, int zc1
     dim3 block(32, ty + 1);
     dim3 grid((c->px - p.X0s + HE_SEG - 1) / HE_SEG, (p.Y1 - p.Y0 + ty - 1) / ty, (p.Z1 - p.Z0 + kz - 1) / kz);
     if (grid.y > 65535 || grid.z > 65535) return fail("grid too large for the fused launch");
-    p.b_sz = 4 * p.sz; p.b_cs = 4 * p.cs; p.b_2cs = 8 * p.cs; p.b_sz_cs = 4 * (p.sz + p.cs); p.b_sz_2cs = 4 * (p.sz + 2 * p.cs);
+    p.b_sz = 4 * p.sz; p.b_cs = 4 * p.cs; p.b_2cs = 8 * p.cs;
     p.b_row = 4LL * p.px; p.b_row_2cs = 4 * (p.px + 2 * p.cs);
-    for (int q = 0; q < 3; ++q) { p.b_pfe[q] = 4 * (2 * p.sz + q * p.cs); p.b_pfh[q] = 4 * (p.sz + q * p.cs); }   // one plane ahead
-    p.xv_pitch = 4u * (unsigned)p.px; p.meta_step = 32 * p.ny;
+    p.meta_step = 32 * p.ny;
     p.nv_e = c->cmp_nvec[0]; p.nv_h = c->cmp_nvec[1];
     const size_t xs_bytes = (size_t)(p.nv_e + p.nv_h) * 32 * sizeof(float4);
     // whole-tile staging by tiled TMA copies (one instruction per field and plane instead of eight row copies per warp);

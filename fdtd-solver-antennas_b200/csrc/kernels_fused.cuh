@@ -1,4 +1,5 @@
-// kernels_fused.cuh - fused H->E launch (temporal blocking): every generation from the plain fusion to the TMA-staged default
+// kernels_fused.cuh - fused H->E launch (temporal blocking): update_he_kernel (plain fusion, any operator) and update_he6_kernel
+// (row-compressed operator, whole tiles staged by the TMA engine; the production path)
 // Part of libb200fdtd (textually included by b200fdtd.cu; see that file for the data layout and the arithmetic contract).
 #pragma once
 
@@ -24,11 +25,11 @@ struct HeParams {
     int Y0, Y1, Z0, Z1;             // owned rows and planes
     int kz;
     int pf;                         // planes of L2 prefetch distance (0 = off)
-    // byte offsets as launch constants (update_he2_kernel adds them to per-thread plane pointers: two integer
-    // instructions per address instead of a 64-bit index computation)
-    long long b_sz, b_cs, b_2cs, b_sz_cs, b_sz_2cs, b_row, b_row_2cs, b_pfe[3], b_pfh[3];
-    unsigned xv_pitch; int meta_step;
-    int nv_e, nv_h;                 // x-vectors of the E / H pass (update_he2_kernel keeps its 128-column slice of them in smem)
+    // byte offsets as launch constants (update_he6_kernel adds them to one per-thread byte offset: two integer instructions
+    // per address instead of a 64-bit index computation)
+    long long b_sz, b_cs, b_2cs, b_row, b_row_2cs;
+    int meta_step;
+    int nv_e, nv_h;                 // x-vectors of the E / H pass (update_he6_kernel keeps its 128-column slice of them in smem)
 };
 
 template <bool CMP>
@@ -151,8 +152,6 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 
 
 __device__ __forceinline__ float4 ldb4(const char* p) { return *reinterpret_cast<const float4*>(p); }
-__device__ __forceinline__ float4 ldb4_cs(const char* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
-__device__ __forceinline__ float4 ldb4_nc(const char* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void stb4(char* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ float4 xv4(const float4* xs, unsigned id, float sc)      // xs = this lane's column of the smem copy
 {

@@ -180,3 +180,33 @@ def test_live_run_prepared_functions_run_unmodified(tmp_path, monkeypatch):
         assert np.array_equal(dbi, res.intensity)
     finally:
         scenes.use_cuda_engine()
+
+
+def test_setup_only_keeps_the_prepared_scene_and_a_changed_scene_is_rebuilt():
+    """FDTD.Run(sim_path, setup_only=True) (openEMS's own flag) keeps the prepared scene; a later Run of the SAME scene
+    restarts it from zero fields and reproduces the first run; a shorter NrTS reuses it, a changed scene does not"""
+    import scenes
+    scenes.use_oracle_engine(threads=4)
+    try:
+        F, nf, port = scenes.dipole("PML_8", cells=(20, 20, 24), nrts=240, end=1e-12)
+        p = scenes.tmp_sim_path("reuse")
+        F.Run(p, cleanup=True)
+        first = F.results["probes"]["port_ut_1"]["val"].copy()
+        acc0 = [a.copy() for a in F.results["nf2ff"]["acc"]]
+        F.Run(p, setup_only=True)
+        sim = F._prepared[1]
+        for _ in range(2):
+            F.Run(p)
+            assert F.sim is sim, "the prepared scene was not reused"
+            assert np.array_equal(F.results["probes"]["port_ut_1"]["val"], first)
+            for a, b in zip(F.results["nf2ff"]["acc"], acc0):
+                assert np.array_equal(a, b)
+        F.SetNumberOfTimeSteps(120)
+        F.Run(p)
+        assert F.sim is sim and F.sim.timesteps == 120
+        assert np.array_equal(F.results["probes"]["port_ut_1"]["val"], first[:len(F.results["probes"]["port_ut_1"]["val"])])
+        F.GetCSX().AddMetal("extra").AddBox([1.0, 1.0, 1.0], [4.0, 4.0, 1.0], priority=10)     # the scene changes
+        F.Run(p)
+        assert F.sim is not sim, "a changed scene must be prepared again"
+    finally:
+        scenes.use_cuda_engine()
