@@ -404,6 +404,10 @@ class Simulation:
                 except Exception:            # e.g. out of memory: keep the separate half steps
                     self._fused = False
             self._vcur = self._ccur = 0
+            # the fused launch in two halves hides the wait for the upper ghost E behind the lower half; B200FDTD_SPLIT_HE=0:
+            # one launch (the exchange then has to fit behind the boundary-plane launches of part 0)
+            import os
+            self._split_he = os.environ.get("B200FDTD_SPLIT_HE", "1") != "0"
         return self._tv, self._tc
 
     def _cur(self):
@@ -458,7 +462,8 @@ class Simulation:
         """H(n) + E(n+1): boundary planes by separate launches, interior planes by the fused launch (csrc, part 0..3)"""
         E = self.engine
         E.fused_step_part(0)                         # H: plane 0 + interior PML slabs
-        E.fused_step_part(4)                         # fused launch, lower half of the interior planes (overlaps the E halo)
+        if self._split_he:
+            E.fused_step_part(4)                     # fused launch, lower half of the interior planes (overlaps the E halo)
         self._wait(self._pend_e); self._pend_e = []
         E.fused_step_part(1)                         # H: top plane (needed the upper ghost E)
         h_new = self._copies_c[self._ccur ^ 1]       # the H launches wrote the other copy; it becomes current in part 2

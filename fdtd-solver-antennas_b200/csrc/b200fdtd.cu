@@ -962,7 +962,8 @@ extern "C" int b200fdtd_set_mur(b200fdtd_ctx* c, int64_t n, const int64_t* dst, 
     if (upload(&c->mur_coeff, coeff, n, c->stream)) return 1;
     if (c->mur_tmp) { cudaFree(c->mur_tmp); c->mur_tmp = nullptr; }
     if (n > 0) { CK(cudaMalloc((void**)&c->mur_tmp, sizeof(float) * n)); CK(cudaMemsetAsync(c->mur_tmp, 0, sizeof(float) * n, c->stream)); }
-    // arithmetic runs of (dst, src): rows / columns of the boundary faces (at most 1024 edges each: one warp sweeps a run)
+    // arithmetic runs of (dst, src): rows / columns of the boundary faces (at most MUR_RUN_MAX edges each: one warp sweeps a
+    // run, so short runs keep the sweep a few loads deep and the faces spread over the whole machine)
     std::vector<MurSeg> segs;
     for (int64_t e = 0; e < n;) {
         MurSeg S; S.dst0 = dst[e]; S.src0 = src[e]; S.e0 = e; S.pad = 0; S.sd = 0; S.ss = 0; S.count = 1;
@@ -970,7 +971,7 @@ extern "C" int b200fdtd_set_mur(b200fdtd_ctx* c, int64_t n, const int64_t* dst, 
             const long long sd = dst[e + 1] - dst[e], ss = src[e + 1] - src[e];
             if (sd > -(1LL << 30) && sd < (1LL << 30) && ss > -(1LL << 30) && ss < (1LL << 30)) {
                 S.sd = (int)sd; S.ss = (int)ss;
-                while (e + S.count < n && S.count < 1024 && dst[e + S.count] - dst[e + S.count - 1] == sd &&
+                while (e + S.count < n && S.count < MUR_RUN_MAX && dst[e + S.count] - dst[e + S.count - 1] == sd &&
                        src[e + S.count] - src[e + S.count - 1] == ss) S.count++;
             }
         }

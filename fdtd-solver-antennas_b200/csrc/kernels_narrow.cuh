@@ -39,17 +39,34 @@ __global__ void mur_kernel(float* __restrict__ volt, const int64_t* __restrict__
 // column of an x-face: stride px), so the lists are stored as segments {first dst, first src, strides, count, first
 // entry}: 40 bytes per run instead of 16 bytes of int64 indices per edge.  One warp per segment; same arithmetic per edge.
 struct MurSeg { long long dst0, src0; int sd, ss; int count; int pad; long long e0; };
+#define MUR_RUN_MAX 128            // 4 edges per lane: all loads of a run are in flight at once
 __global__ void __launch_bounds__(128) mur_seg_kernel(float* __restrict__ volt, const MurSeg* __restrict__ segs, int nsegs,
                                                       const float* __restrict__ coeff, float* __restrict__ tmp, int phase)
 {
     const int w = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
     if (w >= nsegs) return;
     const MurSeg S = segs[w];
-    for (int q = lane; q < S.count; q += 32) {
-        const long long e = S.e0 + q, d = S.dst0 + (long long)q * S.sd, sidx = S.src0 + (long long)q * S.ss;
-        if (phase == 0) tmp[e] = __fmaf_rn(-coeff[e], volt[d], volt[sidx]);
-        else if (phase == 1) tmp[e] = __fmaf_rn(coeff[e], volt[sidx], tmp[e]);
-        else volt[d] = tmp[e];
+    float a[MUR_RUN_MAX / 32], b[MUR_RUN_MAX / 32], k[MUR_RUN_MAX / 32];
+#pragma unroll
+    for (int u = 0; u < MUR_RUN_MAX / 32; ++u) {            // loads first ...
+        const int q = lane + 32 * u;
+        a[u] = b[u] = k[u] = 0.f;
+        if (q < S.count) {
+            const long long e = S.e0 + q, d = S.dst0 + (long long)q * S.sd, sidx = S.src0 + (long long)q * S.ss;
+            if (phase == 0) { k[u] = coeff[e]; a[u] = volt[d]; b[u] = volt[sidx]; }
+            else if (phase == 1) { k[u] = coeff[e]; a[u] = volt[sidx]; b[u] = tmp[e]; }
+            else a[u] = tmp[e];
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < MUR_RUN_MAX / 32; ++u) {            // ... then the same arithmetic per edge as mur_kernel
+        const int q = lane + 32 * u;
+        if (q < S.count) {
+            const long long e = S.e0 + q, d = S.dst0 + (long long)q * S.sd;
+            if (phase == 0) tmp[e] = __fmaf_rn(-k[u], a[u], b[u]);
+            else if (phase == 1) tmp[e] = __fmaf_rn(k[u], a[u], b[u]);
+            else volt[d] = a[u];
+        }
     }
 }
 
