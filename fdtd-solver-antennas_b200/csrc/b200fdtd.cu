@@ -115,6 +115,8 @@ struct b200fdtd_ctx {
     // step counter
     int64_t ts = 0;
     int* d_ts = nullptr;
+    int ts_lag = 0;                        // steps counted on the host but not yet added to the device counter (host-driven
+                                           // z-slab steps pass the lag as an offset instead of launching ts_add every step)
     // excitation
     int64_t n_exc = 0; int64_t* exc_idx = nullptr; float* exc_amp = nullptr; int* exc_delay = nullptr;
     float* exc_sig = nullptr; int exc_siglen = 0;
@@ -168,7 +170,7 @@ static void fill_vol_params(const b200fdtd_ctx* c, int which, VolParams& p)
     p.ca = which == 0 ? c->vv : c->ii;
     p.cb = which == 0 ? c->vi : c->iv;
     p.nx = c->nx; p.ny = c->ny; p.nz = c->nz; p.px = c->px; p.sz = c->sz; p.cs = c->cs;
-    p.kz = 1; p.k0 = 0; p.k1 = 0;
+    p.kz = 1; p.kspan = 0; p.k0 = 0; p.k1 = 0;
     p.xv = c->cmp_xv[which]; p.meta = c->cmp_meta[which];
 }
 
@@ -404,11 +406,16 @@ static int launch_volume_fused(b200fdtd_ctx* c, int which, int k0, int k1, cudaS
 
 // every PML slab of one half step (planes [k0,k1)) in one launch (update_slabs_kernel); variant bit 26: one launch per slab
 static bool slabs_merged(const b200fdtd_ctx* c) { return (c->variant & (1 << 26)) == 0; }
-static int launch_slabs_merged(b200fdtd_ctx* c, int which, int k0, int k1, cudaStream_t stream, bool with_whole_rows = true, int sel = 0)
+static int launch_slabs_merged(b200fdtd_ctx* c, int which, int k0, int k1, cudaStream_t stream, bool with_whole_rows = true, int sel = 0,
+                               int k2 = 0, int k3 = 0 /* optional second plane range [k2,k3) */)
 {
     SlabSet T; memset(&T, 0, sizeof(T));
     if (launch_volume_xslabs(c, which, k0, k1, stream, sel, &T)) return 1;
     if (with_whole_rows) if (launch_volume_fused(c, which, k0, k1, stream, sel, &T)) return 1;
+    if (k3 > k2) {
+        if (launch_volume_xslabs(c, which, k2, k3, stream, sel, &T)) return 1;
+        if (with_whole_rows) if (launch_volume_fused(c, which, k2, k3, stream, sel, &T)) return 1;
+    }
     if (T.n == 0) return 0;
     long long total = 0;
     for (int q = 0; q < T.n; ++q) { T.e[q].cta0 = (int)total; total += (long long)T.e[q].gx * T.e[q].gy * T.e[q].gz; }
@@ -443,6 +450,9 @@ static int launch_slabs(b200fdtd_ctx* c, int which, int k0, int k1, cudaStream_t
     if (with_whole_rows) return launch_volume_fused(c, which, k0, k1, row_stream, sel);
     return 0;
 }
+
+// the two boundary planes ka < kb of a z-slab rank in one plain launch (two z-chunks of one plane each) and one slab launch
+static int launch_volume_two_planes(b200fdtd_ctx* c, int which, int ka, int kb);
 
 // all volume launches of one half step restricted to planes [k0,k1), on the main stream
 static int launch_volume(b200fdtd_ctx* c, int which, int k0, int k1)
@@ -549,6 +559,45 @@ static int normalize_flux(b200fdtd_ctx* c)
     }
     c->fcur = 0;
     return 0;
+}
+
+static int launch_volume_two_planes(b200fdtd_ctx* c, int which, int ka, int kb)
+{
+    if (!c->volt || !c->vv) return fail("fields/coefficients not bound");
+    if (!c->plan.valid) if (build_plan(c)) return 1;
+    const VolumePlan& P = c->plan;
+    const bool plain2 = P.nseg == 1 && ka >= P.seg0[0] && kb < P.seg1[0] && kb > ka && (c->variant & (1 << 28)) == 0;
+    if (!plain2 || !slabs_merged(c)) {                       // a boundary plane inside a z-slab (end ranks), or the per-slab launches
+        if (launch_volume(c, which, ka, ka + 1)) return 1;
+        return launch_volume(c, which, kb, kb + 1);
+    }
+    RowParams r; memset(&r, 0, sizeof(r));
+    r.j0 = 0; r.j1 = c->ny;
+    if (P.nskip > 0) { r.sj0a = P.sj0[0]; r.sj1a = P.sj1[0]; }
+    if (P.nskip > 1) { r.sj0b = P.sj0[1]; r.sj1b = P.sj1[1]; }
+    if (P.has_lo) r.xw0 = P.xw0;
+    if (P.has_hi) { r.xx1 = P.xx1; r.xw1 = P.xw1; }
+    VolParams p; fill_vol_params(c, which, p);
+    p.k0 = ka; p.k1 = kb + 1; p.kz = kb - ka; p.kspan = 1;
+    const int ty = c->ty;
+    dim3 block(32, ty), grid((c->px + 127) / 128, (c->ny + ty - 1) / ty, 2);
+    const bool cmp = c->cmp_meta[which] != nullptr && (c->variant & 4) == 0;
+#define LAUNCH2(TYV) do { \
+        if (which == 0) { if (cmp) update_e_kernel<TYV, 0, true><<<grid, block, 0, c->stream>>>(p, r); \
+                          else update_e_kernel<TYV, 0, false><<<grid, block, 0, c->stream>>>(p, r); } \
+        else { if (cmp) update_h_kernel<TYV, 0, true><<<grid, block, 0, c->stream>>>(p, r); \
+               else update_h_kernel<TYV, 0, false><<<grid, block, 0, c->stream>>>(p, r); } } while (0)
+    switch (ty) {
+        case 1: LAUNCH2(1); break;
+        case 2: LAUNCH2(2); break;
+        case 4: LAUNCH2(4); break;
+        case 8: LAUNCH2(8); break;
+        case 16: LAUNCH2(16); break;
+        default: return fail("unsupported ty=%d", ty);
+    }
+#undef LAUNCH2
+    CKL();
+    return launch_slabs_merged(c, which, ka, ka + 1, c->stream, true, 0, kb, kb + 1);
 }
 
 // fused H->E launch: reads the current copies, writes the other copies (the caller flips)
@@ -1211,6 +1260,7 @@ extern "C" int b200fdtd_set_timestep(b200fdtd_ctx* c, int64_t ts)
     if (ts < 0 || ts > 0x7fffffff) return fail("timestep out of range");
     CK(cudaSetDevice(c->device));
     int v = (int)ts;
+    c->ts_lag = 0;
     CK(cudaMemcpyAsync(c->d_ts, &v, sizeof(int), cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     c->ts = ts;
@@ -1251,7 +1301,7 @@ static int launch_excite(b200fdtd_ctx* c, int ts_off)
     if (c->n_exc == 0) return 0;
     const int threads = 128;
     excite_kernel<<<(unsigned)((c->n_exc + threads - 1) / threads), threads, 0, c->stream>>>(cur_volt(c), c->exc_idx, c->exc_amp,
-        c->exc_delay, c->exc_sig, c->exc_siglen, c->n_exc, c->d_ts, ts_off);
+        c->exc_delay, c->exc_sig, c->exc_siglen, c->n_exc, c->d_ts, ts_off + c->ts_lag);
     CKL();
     return 0;
 }
@@ -1259,6 +1309,7 @@ static int launch_excite(b200fdtd_ctx* c, int ts_off)
 // wants are still intact in the other copy, which that launch only read
 static int launch_sampling(b200fdtd_ctx* c, int ts_off, bool pipelined = false)
 {
+    ts_off += c->ts_lag;
     const float* sv = pipelined ? oth_volt(c) : cur_volt(c);
     if (c->n_probes > 0) {
         probe_kernel<<<c->n_probes, 128, 0, c->stream>>>(sv, cur_curr(c), c->pr_kind, c->pr_off, c->pr_idx, c->pr_w,
@@ -1282,6 +1333,13 @@ static int launch_ts_add(b200fdtd_ctx* c, int n)
     ts_add_kernel<<<1, 32, 0, c->stream>>>(c->d_ts, n);
     CKL();
     return 0;
+}
+// the device counter catches up with the host's (before anything that relies on their being equal: graph replays, resets)
+static int flush_ts_lag(b200fdtd_ctx* c)
+{
+    if (c->ts_lag == 0) return 0;
+    const int n = c->ts_lag; c->ts_lag = 0;
+    return launch_ts_add(c, n);
 }
 
 // E half step with device step offset `off` (host knows ts + off)
@@ -1529,6 +1587,7 @@ extern "C" int b200fdtd_run(b200fdtd_ctx* c, int64_t nsteps, int use_graph)
     if (!c->volt || !c->vv) return fail("fields/coefficients not bound");
     CK(cudaSetDevice(c->device));
     if (!c->plan.valid) if (build_plan(c)) return 1;        // never inside a stream capture
+    if (flush_ts_lag(c)) return 1;
     c->he_fused = false;
     const int iv = sample_interval(c);
     if (nsteps == 0) return 0;
@@ -1569,8 +1628,7 @@ extern "C" int b200fdtd_half_step(b200fdtd_ctx* c, int phase)
     if (phase == 0) return e_half(c, 0);
     if (phase == 1) {
         if (h_half(c)) return 1;
-        if (launch_ts_add(c, 1)) return 1;
-        c->ts += 1;
+        c->ts += 1; c->ts_lag += 1;
         return 0;
     }
     if (phase == 2 || phase == 3) {                          // 3: in the pipelined state of the fused steps (E is one update ahead)
@@ -1612,8 +1670,7 @@ extern "C" int b200fdtd_half_step_part(b200fdtd_ctx* c, int phase, int part)
     if (launch_volume(c, 1, nz - 1, nz)) return 1;
     if (launch_pml(c, 1, 1)) return 1;
     if (c->flux_pp) c->fcur ^= 1;                 // both parts read one copy of the slabs' current flux and wrote the other
-    if (launch_ts_add(c, 1)) return 1;
-    c->ts += 1;
+    c->ts += 1; c->ts_lag += 1;
     return 0;
 }
 
@@ -1670,15 +1727,13 @@ extern "C" int b200fdtd_fused_step_part(b200fdtd_ctx* c, int part)
         c->he_mid = 0;
         c->ccur ^= 1;
         if (c->flux_pp) c->fcur ^= 1;
-        if (launch_ts_add(c, 1)) return 1;
-        c->ts += 1;
+        c->ts += 1; c->ts_lag += 1;
         return 0;
     }
     c->flip = true;
     if (side) rc = fork_side(c);
     if (!rc) rc = launch_slabs(c, 0, 1, nz - 1, side ? c->side : c->stream, side ? c->side : c->stream, side ? slab_stream(c) : c->stream, !inhe);
-    if (!rc) rc = launch_volume(c, 0, 0, 1);
-    if (!rc) rc = launch_volume(c, 0, nz - 1, nz);
+    if (!rc) rc = launch_volume_two_planes(c, 0, 0, nz - 1);
     if (!rc && side) rc = join_side(c);
     c->flip = false;
     if (rc) return 1;

@@ -13,7 +13,9 @@ struct VolParams {
     const float* __restrict__ cb;   // vi / iv
     int nx, ny, nz, px;
     long long sz, cs;
-    int kz;                         // planes marched per CTA
+    int kz;                         // planes between the starts of consecutive z-chunks
+    int kspan;                      // planes a chunk marches (0 = kz); kspan < kz: a launch over scattered planes (the two boundary
+                                    // planes of a z-slab rank in one launch: kz = nz - 1, kspan = 1)
     int k0, k1;                     // plane range [k0,k1) handled by this launch
     const float* __restrict__ xv;   // row compression: table of x-vectors [nvec][px]
     const unsigned char* __restrict__ meta;   // per row (k,j): 6 scales + 6 vector ids (32 B), see RowMeta
@@ -225,7 +227,7 @@ __device__ __forceinline__ void update_e_body(const VolParams& p, const RowParam
     // plain launch: columns owned by a narrow-slab launch are computed but not stored
     const bool own = MODE != 0 || !(i0 < r.xw0 || (i0 >= r.xx1 && i0 < r.xx1 + r.xw1));
     const int kbeg = p.k0 + biz * p.kz;
-    const int kend = min(kbeg + p.kz, p.k1);
+    const int kend = min(kbeg + (p.kspan ? p.kspan : p.kz), p.k1);
     const long long cs = p.cs, sz = p.sz;
     const float* __restrict__ g = p.g;
     float* __restrict__ f = p.f;
@@ -347,7 +349,7 @@ __device__ __forceinline__ void update_h_body(const VolParams& p, const RowParam
     // plain launch: columns owned by a narrow-slab launch are computed but not stored
     const bool own = MODE != 0 || !(i0 < r.xw0 || (i0 >= r.xx1 && i0 < r.xx1 + r.xw1));
     const int kbeg = p.k0 + biz * p.kz;
-    const int kend = min(kbeg + p.kz, p.k1);
+    const int kend = min(kbeg + (p.kspan ? p.kspan : p.kz), p.k1);
     const long long cs = p.cs, sz = p.sz;
     const float* __restrict__ g = p.g;
     float* __restrict__ f = p.f;
@@ -451,7 +453,7 @@ __global__ void __launch_bounds__(32 * TY, MODE ? (16 / TY > 0 ? 16 / TY : 1) : 
 // would.  One grid that fills the machine instead of five small ones on five streams, and 2 instead of 10 slab launches
 // per step (what matters most on small grids, where a step is launch-bound).
 struct SlabEntry { RowParams r; int mode; int gx, gy, gz; int kz, k0, k1; int cta0; };
-#define MAX_SLABS 6
+#define MAX_SLABS 12               // six slabs, each possibly once per boundary plane of a z-slab rank
 struct SlabSet { int n; SlabEntry e[MAX_SLABS]; };
 template <int WHICH, int TY, bool CMP>
 __global__ void __launch_bounds__(32 * TY, (16 / TY > 0 ? 16 / TY : 1)) update_slabs_kernel(const VolParams p0, const __grid_constant__ SlabSet T)
@@ -463,7 +465,7 @@ __global__ void __launch_bounds__(32 * TY, (16 / TY > 0 ? 16 / TY : 1)) update_s
     const unsigned local = blockIdx.x - E.cta0;
     const unsigned bix = local % E.gx, biy = (local / E.gx) % E.gy, biz = local / (E.gx * E.gy);
     VolParams p = p0;
-    p.kz = E.kz; p.k0 = E.k0; p.k1 = E.k1;
+    p.kz = E.kz; p.kspan = 0; p.k0 = E.k0; p.k1 = E.k1;
     if (E.mode == 1) { if (WHICH == 0) update_e_body<TY, 1, CMP>(p, E.r, bix, biy, biz); else update_h_body<TY, 1, CMP>(p, E.r, bix, biy, biz); }
     else             { if (WHICH == 0) update_e_body<TY, 2, CMP>(p, E.r, bix, biy, biz); else update_h_body<TY, 2, CMP>(p, E.r, bix, biy, biz); }
 }

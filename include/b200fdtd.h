@@ -78,7 +78,7 @@ int b200fdtd_expand_rows(b200fdtd_ctx* ctx, int which, int nvec, const float* xv
  * their own launches on B200, hence off by default), bit 22 = never (overrides bit 23),
  * bit 24 = Mur edges by index lists even where they form long arithmetic runs, bit 25 = per-row 1-D TMA copies instead of
  * tiled copies in the fused launch, bit 26 = one launch per PML slab instead of one for all, bit 27 = one fused span per
- * sampling interval instead of one per b200fdtd_run call */
+ * sampling interval instead of one per b200fdtd_run call, bit 28 = one launch per boundary plane of a z-slab rank */
 int b200fdtd_set_tuning(b200fdtd_ctx* ctx, int kz, int ty, int variant);
 
 /* ---- excitation (openEMS Engine_Ext_Excitation::Apply2Voltages; AddLumpedPort's
