@@ -29,6 +29,11 @@ class PmlBox(C.Structure):
                 ("xvecs_i", vp), ("meta_i", vp), ("nvec_i", C.c_int32)]
 
 
+class Nf2ffSrcFace(C.Structure):
+    _fields_ = [("normal", C.c_int32), ("side", C.c_int32), ("na", C.c_int32), ("nb", C.c_int32), ("coord", C.c_double),
+                ("acc", vp), ("comp_stride", C.c_int64), ("xa", c_d), ("xb", c_d), ("wa", c_d), ("wb", c_d)]
+
+
 class Nf2ffFace(C.Structure):
     _fields_ = [("normal", C.c_int32), ("plane", C.c_int32), ("a0", C.c_int32), ("a1", C.c_int32),
                 ("b0", C.c_int32), ("b1", C.c_int32), ("acc", vp)]
@@ -71,6 +76,7 @@ SYMBOLS = {
     "b200fdtd_energy": (C.c_int, [vp, c_d]),
     "b200fdtd_sync": (C.c_int, [vp]),
     "b200fdtd_num_samples": (C.c_int, [vp, C.POINTER(C.c_int)]),
+    "b200fdtd_nf2ff_sources": (C.c_int, [C.c_int, vp, C.c_int, C.POINTER(Nf2ffSrcFace), C.c_double, c_d, vp, vp, vp, c_d]),
     "b200fdtd_farfield": (C.c_int, [C.c_int, vp, C.c_int64, vp, vp, vp, C.c_double, C.c_int, c_d, c_d, vp]),
 }
 

@@ -109,31 +109,34 @@ def device_sources(nf, freq, center):
                              "pass frequency=[...] to CreateNF2FFBox")
         accs = [a[:, 0] for a in D["td_dft"](float(freq))] if faces else []
     scale = float(D["scale"])
-    c = np.asarray(center, np.float64).reshape(3)
-    f32 = dict(dtype=torch.float32, device=dev)
-    pos, Jl, Ml = [torch.zeros((3, 0), **f32)], [torch.zeros((3, 0, 2), **f32)], [torch.zeros((3, 0, 2), **f32)]
-    prad = torch.zeros(1, dtype=torch.float64, device=dev)
-    for F, acc in zip(faces, accs):
-        n = F["normal"]; a, b = (n + 1) % 3, (n + 2) % 3
-        s = 1.0 if F["side"] == 1 else -1.0
-        dA = (torch.as_tensor(F["wb"], dtype=torch.float64, device=dev)[:, None] * torch.as_tensor(F["wa"], dtype=torch.float64, device=dev)[None, :])
-        w32 = (dA * scale).to(torch.float32).unsqueeze(-1)            # dA and the DFT scale in one factor
-        Ea, Eb, Ha, Hb = (acc[q] for q in range(4))                   # [nb][na][2]
-        nb_, na_ = dA.shape
-        P = torch.empty((3, nb_, na_), **f32)
-        P[n] = float(F["coord"] - c[n])
-        P[a] = torch.as_tensor(np.asarray(F["xa"]) - c[a], **f32)[None, :]
-        P[b] = torch.as_tensor(np.asarray(F["xb"]) - c[b], **f32)[:, None]
-        J = torch.zeros((3, nb_, na_, 2), **f32); M = torch.zeros_like(J)
-        J[a] = -s * Hb * w32; J[b] = s * Ha * w32                     # J = n x H
-        M[a] = s * Eb * w32; M[b] = -s * Ea * w32                     # M = -n x E
-        ea, eb, ha, hb = (t.to(torch.float64) for t in (Ea, Eb, Ha, Hb))
-        re = (ea[..., 0] * hb[..., 0] + ea[..., 1] * hb[..., 1]) - (eb[..., 0] * ha[..., 0] + eb[..., 1] * ha[..., 1])
-        prad = prad + 0.5 * s * scale * scale * torch.sum(re * dA)
-        pos.append(P.reshape(3, -1)); Jl.append(J.reshape(3, -1, 2)); Ml.append(M.reshape(3, -1, 2))
+    c = np.ascontiguousarray(np.asarray(center, np.float64).reshape(3))
+    # one kernel per face (K11a, csrc: nf2ff_sources_kernel) through the C-ABI; the spectra are used where they lie
+    from . import _lib
+    import ctypes as C
+    L = _lib.lib()
+    npts = sum(int(a.shape[1]) * int(a.shape[2]) for a in accs)
+    pos = torch.empty((3, npts), dtype=torch.float32, device=dev)
+    J = torch.empty((3, npts, 2), dtype=torch.float32, device=dev)
+    M = torch.empty((3, npts, 2), dtype=torch.float32, device=dev)
+    arr = (_lib.Nf2ffSrcFace * max(1, len(faces)))()
+    keep = []
+    for q, (F, acc) in enumerate(zip(faces, accs)):
+        nb_, na_ = int(acc.shape[1]), int(acc.shape[2])
+        assert acc.stride(3) == 1 and acc.stride(2) == 2 and acc.stride(1) == 2 * na_, "face spectra must be [nb][na][2] rows"
+        xs = [np.ascontiguousarray(F[k], np.float64) for k in ("xa", "xb", "wa", "wb")]
+        keep.append(xs)
+        arr[q].normal, arr[q].side, arr[q].na, arr[q].nb = int(F["normal"]), int(F["side"]), na_, nb_
+        arr[q].coord = float(F["coord"])
+        arr[q].acc = acc.data_ptr(); arr[q].comp_stride = int(acc.stride(0))
+        arr[q].xa, arr[q].xb, arr[q].wa, arr[q].wb = (x.ctypes.data_as(_lib.c_d) for x in xs)
+    prad_h = C.c_double(0.0)
+    st = torch.cuda.current_stream(dev)
+    _lib.check(L.b200fdtd_nf2ff_sources(dev.index, C.c_void_p(st.cuda_stream), len(faces), arr, scale, c.ctypes.data_as(_lib.c_d),
+                                        pos.data_ptr(), J.data_ptr(), M.data_ptr(), C.byref(prad_h)))
+    prad = torch.tensor([prad_h.value], dtype=torch.float64, device=dev)
     if D.get("world", 1) > 1:
         torch.distributed.all_reduce(prad, group=D.get("group"))
-    src = FarfieldSources.from_device(torch.cat(pos, 1).contiguous(), torch.cat(Jl, 1).contiguous(), torch.cat(Ml, 1).contiguous())
+    src = FarfieldSources.from_device(pos, J, M)
     src.world, src.group = D.get("world", 1), D.get("group")
     return src, float(prad.item())
 

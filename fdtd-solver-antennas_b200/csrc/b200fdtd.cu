@@ -1876,6 +1876,56 @@ extern "C" int b200fdtd_num_samples(b200fdtd_ctx* c, int* n)
     return 0;
 }
 
+extern "C" int b200fdtd_nf2ff_sources(int device, void* stream, int nfaces, const b200fdtd_nf2ff_src_face* faces, double scale,
+                                       const double* center, float* pos, float* J, float* M, double* prad)
+{
+    if (nfaces < 0 || nfaces > 16 || (nfaces > 0 && !faces) || !center || !prad) return fail("bad nf2ff_sources arguments");
+    CK(cudaSetDevice(device));
+    cudaStream_t s = (cudaStream_t)stream;
+    long long npts = 0, nblocks = 0; size_t nd = 0;
+    for (int q = 0; q < nfaces; ++q) {
+        const b200fdtd_nf2ff_src_face& F = faces[q];
+        if (F.na < 1 || F.nb < 1 || F.normal < 0 || F.normal > 2 || !F.acc || !F.xa || !F.xb || !F.wa || !F.wb) return fail("bad source face %d", q);
+        npts += (long long)F.na * F.nb; nblocks += ((long long)F.na * F.nb + 255) / 256; nd += 2 * ((size_t)F.na + F.nb);
+    }
+    *prad = 0.0;
+    if (npts == 0) return 0;
+    if (!pos || !J || !M) return fail("NULL output array");
+    // one staging buffer: the faces' line coordinates and weights, then the per-block Prad partials
+    std::vector<double> h(nd);
+    double* d = nullptr;
+    CK(cudaMalloc((void**)&d, sizeof(double) * (nd + (size_t)nblocks)));
+    size_t o = 0; long long off = 0, b0 = 0;
+    std::vector<SrcFace> L(nfaces);
+    for (int q = 0; q < nfaces; ++q) {
+        const b200fdtd_nf2ff_src_face& F = faces[q];
+        SrcFace& S = L[q];
+        S.normal = F.normal; S.side = F.side; S.na = F.na; S.nb = F.nb; S.coord = F.coord; S.acc = F.acc; S.cstride = F.comp_stride;
+        memcpy(&h[o], F.xa, sizeof(double) * F.na); S.xa = d + o; o += F.na;
+        memcpy(&h[o], F.xb, sizeof(double) * F.nb); S.xb = d + o; o += F.nb;
+        memcpy(&h[o], F.wa, sizeof(double) * F.na); S.wa = d + o; o += F.na;
+        memcpy(&h[o], F.wb, sizeof(double) * F.nb); S.wb = d + o; o += F.nb;
+        S.off = off; off += (long long)F.na * F.nb;
+    }
+    cudaError_t e = cudaMemcpyAsync(d, h.data(), sizeof(double) * nd, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);                    // h is a pageable temporary
+    for (int q = 0; q < nfaces && e == cudaSuccess; ++q) {
+        const long long nb = ((long long)L[q].na * L[q].nb + 255) / 256;
+        nf2ff_sources_kernel<<<(unsigned)nb, 256, 0, s>>>(L[q], scale, center[0], center[1], center[2], npts, pos, J, M, d + nd + b0);
+        g_launches.fetch_add(1);
+        e = cudaGetLastError();
+        b0 += nb;
+    }
+    std::vector<double> part((size_t)nblocks);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(part.data(), d + nd, sizeof(double) * nblocks, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail("nf2ff_sources failed: %s", cudaGetErrorString(e));
+    double t = 0; for (double v : part) t += v;
+    *prad = t;
+    return 0;
+}
+
 extern "C" int b200fdtd_farfield(int device, void* stream, int64_t npts, const float* pos, const float* J,
                                   const float* M, double k, int ndir, const double* theta, const double* phi, float* out)
 {

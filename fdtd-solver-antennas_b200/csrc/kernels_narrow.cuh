@@ -278,6 +278,47 @@ __global__ void energy_final_kernel(const double* __restrict__ partials, int n, 
     if (threadIdx.x == 0) { out[0] = a; out[1] = b; }
 }
 
+// K11a equivalent currents of one Huygens face from its spectra: J = n x H, M = -n x E (times dA and the DFT scale), node
+// positions relative to the phase centre, and the face's share of Prad = 1/2 Re sum (E x H*) . n dA (fp64, one partial per
+// block, added on the host in a fixed order).  acc = spectra of the chosen frequency: component c at acc + c * cstride.
+struct SrcFace { int normal, side, na, nb; double coord; const float* acc; long long cstride; const double *xa, *xb, *wa, *wb; long long off; };
+__global__ void __launch_bounds__(256) nf2ff_sources_kernel(const SrcFace F, double scale, double cx, double cy, double cz, long long npts,
+        float* __restrict__ pos, float* __restrict__ J, float* __restrict__ M, double* __restrict__ prad_partial)
+{
+    const long long nn = (long long)F.na * F.nb;
+    const long long node = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double pr = 0.0;
+    if (node < nn) {
+        const int ia = (int)(node % F.na), ib = (int)(node / F.na);
+        const int n = F.normal, a = (n + 1) % 3, b = (n + 2) % 3;
+        const double s = F.side == 1 ? 1.0 : -1.0;
+        const double dA = F.wb[ib] * F.wa[ia];
+        const float w = (float)(dA * scale), sw = (float)s * w;
+        const float2* A = reinterpret_cast<const float2*>(F.acc);
+        const float2 Ea = A[node], Eb = A[F.cstride / 2 + node], Ha = A[F.cstride + node], Hb = A[3 * F.cstride / 2 + node];
+        const double c3[3] = {cx, cy, cz};
+        float P[3]; P[n] = (float)(F.coord - c3[n]); P[a] = (float)(F.xa[ia] - c3[a]); P[b] = (float)(F.xb[ib] - c3[b]);
+        float2 Jv[3], Mv[3];
+        Jv[n] = Mv[n] = make_float2(0.f, 0.f);
+        Jv[a] = make_float2(-sw * Hb.x, -sw * Hb.y); Jv[b] = make_float2(sw * Ha.x, sw * Ha.y);      // J = n x H
+        Mv[a] = make_float2(sw * Eb.x, sw * Eb.y);   Mv[b] = make_float2(-sw * Ea.x, -sw * Ea.y);    // M = -n x E
+        const long long q = F.off + node;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            pos[c * npts + q] = P[c];
+            reinterpret_cast<float2*>(J)[c * npts + q] = Jv[c];
+            reinterpret_cast<float2*>(M)[c * npts + q] = Mv[c];
+        }
+        const double re = ((double)Ea.x * Hb.x + (double)Ea.y * Hb.y) - ((double)Eb.x * Ha.x + (double)Eb.y * Ha.y);
+        pr = 0.5 * s * scale * scale * re * dA;
+    }
+    __shared__ double red[8];
+    for (int o = 16; o > 0; o >>= 1) pr += __shfl_down_sync(0xffffffffu, pr, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = pr;
+    __syncthreads();
+    if (threadIdx.x == 0) { double t = 0; for (int i = 0; i < 8; ++i) t += red[i]; prad_partial[blockIdx.x] = t; }
+}
+
 // K11 far field: N = sum J e^{jk r^.r'}, L = sum M e^{jk r^.r'} projected on theta^/phi^ (App. A6)
 // grid (ceil(ndir / 8), nsplit): a block sums its share of the surface points for 8 directions, one per warp.  The points
 // are staged through shared memory in chunks of 256, so every point is fetched once per 8 directions (the sources of a

@@ -217,6 +217,23 @@ int b200fdtd_sync(b200fdtd_ctx* ctx);
 /* number of probe samples taken so far */
 int b200fdtd_num_samples(b200fdtd_ctx* ctx, int* n);
 
+/* ---- equivalent currents of the Huygens box (first half of nf2ff.CalcNF2FF, …microstrip_3d.py:225) ------------------ */
+/* One face of the box with its spectra at ONE frequency resident on the device: component c (Ea, Eb, Ha, Hb: the two
+ * tangential axes a = (normal+1)%3, b = (normal+2)%3) at acc + c*comp_stride floats, each [nb][na][2] f32 (re, im).
+ * xa/xb = node coordinates along a / b (host, metres), wa/wb = trapezoid weights (host), coord = position of the face along
+ * its normal, side = 0 lower / 1 upper face (outward normal -n / +n). */
+typedef struct {
+    int32_t normal, side, na, nb;
+    double coord;
+    const float* acc; int64_t comp_stride;
+    const double *xa, *xb, *wa, *wb;
+} b200fdtd_nf2ff_src_face;
+/* Fills pos[3][npts], J[3][npts][2], M[3][npts][2] (dev f32, npts = sum na*nb, faces in order) with the node positions
+ * relative to `center` and J = n x H, M = -n x E times dA times `scale` (the DFT normalisation 2*dt_sample), and returns
+ * Prad = 1/2 Re sum (E x H*) . n dA * scale^2 in *prad (host).  Synchronises the stream. */
+int b200fdtd_nf2ff_sources(int device, void* stream, int nfaces, const b200fdtd_nf2ff_src_face* faces /*host*/, double scale,
+                           const double* center /*host [3]*/, float* pos, float* J, float* M, double* prad /*host out*/);
+
 /* ---- far field (nf2ff.CalcNF2FF radiation integral, …microstrip_3d.py:225) ------ */
 /* npts surface points with equivalent currents (dev, f32 SoA arrays of npts):
  *   pos[3][npts], J[3][npts][2], M[3][npts][2] (already multiplied by dA).
