@@ -278,7 +278,9 @@ class Runner:
         ms = ev0.elapsed_time(ev1)
         launches = eng_mod.launch_count() - l0
         samplings = (ts0 + K) // iv - ts0 // iv
-        graph_steps = (K // iv) * iv if (self.world == 1 and K >= iv) else 0
+        # one fused span per call: K - 1 fused steps, replayed from graphs of g steps (g = interval, twice that if odd)
+        g = iv if iv % 2 == 0 else 2 * iv
+        graph_steps = ((K - 1) // g) * g if (self.world == 1 and K >= iv and getattr(E, "he_active", False)) else 0
         if self.world > 1:
             t = torch.tensor([ms, float(launches)], dtype=torch.float64, device="cuda")
             m = t.clone()
