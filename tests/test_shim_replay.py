@@ -210,3 +210,26 @@ def test_setup_only_keeps_the_prepared_scene_and_a_changed_scene_is_rebuilt():
         assert F.sim is not sim, "a changed scene must be prepared again"
     finally:
         scenes.use_cuda_engine()
+
+
+def test_a_z_slab_builds_the_rows_of_the_whole_grid_bit_for_bit():
+    """the float32 operator is defined row by row (operator.py:RowFactor), so what a z-slab rank builds for its planes is
+    bit-identical to the single-GPU build, whatever the chunking and whichever rows share an x-vector (16-element array:
+    translated boxes, 16 ports, thick copper)"""
+    import torch
+    from b200fdtd.operator import OperatorBuilder
+    S = replay.replay("trace_array16_mur_q1")["FDTD"]._setup()
+    nz = len(S.lines[2])
+    px = (len(S.lines[0]) + 31) // 32 * 32
+    B = OperatorBuilder(S, device=torch.device("cpu"), k_nodes=(0, nz))
+    dt = B.estimate_timestep()
+    full = [t.reshape(3, nz + 2, -1, px) for t in B.coefficients(0, nz, px, dt)]
+    cuts = [0, nz // 3, nz // 2 + 1, nz]
+    dts = []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        Bs = OperatorBuilder(S, device=torch.device("cpu"), k_nodes=(a, b))
+        dts.append(Bs.estimate_timestep())
+        part = [t.reshape(3, b - a + 2, -1, px) for t in Bs.coefficients(a, b, px, dt, chunk=7)]
+        for name, f, p in zip(("vv", "vi", "ii", "iv"), full, part):
+            assert torch.equal(f[:, a + 1:b + 1].view(torch.int32), p[:, 1:-1].view(torch.int32)), (name, a, b)
+    assert min(dts) == dt                      # the global time step is the minimum over the slabs
